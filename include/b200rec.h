@@ -1,0 +1,229 @@
+/*
+ * b200rec.h -- C ABI of libb200rec.so: the B200 (sm_100a) hot path of
+ * yaochitc/recommendation-models behind the reference's own operator surface.
+ *
+ * Reference paths are relative to /root/reference/src/main/scala:
+ *   nn/  = com/intel/analytics/bigdl/nn/        rec/ = io/yaochi/recommendation/
+ *
+ * Conventions
+ *  - Every function returns an int status: 0 = ok, negative = error (enum below).
+ *    b200rec_last_error() returns the message of the calling thread's last failure.
+ *    Nothing throws or aborts across the ABI.  A Scala shim turns a non-zero status into
+ *    IllegalArgumentException, which is what the reference's `require`s raise
+ *    (nn/Scatter.scala:29-30).
+ *  - The caller owns every array it passes; the callee never keeps a pointer after return.
+ *  - Functions without a suffix take HOST pointers (what JNA hands over for Array[Float] /
+ *    Array[Int]) and do the host<->device copies themselves on the handle's stream.
+ *    Functions with the suffix _dev take DEVICE pointers and an explicit cudaStream_t (as
+ *    void*); they never synchronise the host unless a scalar result is requested.
+ *  - A handle is not thread safe; distinct handles are independent.  Every call sets the
+ *    handle's CUDA device first, so JVM threads may call from anywhere.
+ *  - Gradient write-back follows the reference: backward OVERWRITES weights / bias /
+ *    embedding / mats with their gradients (rec/util/GradUtil.scala:7-42,
+ *    rec/util/BackwardUtil.scala:6-42).
+ *  - There is no CPU fallback.  Without a usable sm_100 device every compute entry point
+ *    fails with B200REC_ERR_CUDA.
+ */
+#ifndef B200REC_H_
+#define B200REC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REC_ABI_VERSION 1
+
+typedef struct b200rec_model_s* b200rec_model_t;
+typedef struct b200rec_table_s* b200rec_table_t;
+
+enum b200rec_status {
+  B200REC_OK = 0,
+  B200REC_ERR_ARG = -1,      /* null pointer, negative size, unknown kind ...            */
+  B200REC_ERR_SHAPE = -2,    /* nnz != B*F where the reference's Reshape would fail       */
+  B200REC_ERR_INDEX = -3,    /* index >= batchSize (nn/Scatter.scala:29) or id >= rows   */
+  B200REC_ERR_CUDA = -4,     /* CUDA runtime error / no sm_100 device                    */
+  B200REC_ERR_STATE = -5,    /* call order (e.g. backward_step before params were set)   */
+  B200REC_ERR_NOMEM = -6
+};
+
+/* rec/model/RecModelType.scala:3-9 decides which buffers exist; `kind` implies it. */
+enum b200rec_kind {
+  B200REC_LR = 0,       /* rec/model/lr/LR.scala:42-90            BIAS_WEIGHT                 */
+  B200REC_FM = 1,       /* no class in the reference (SURVEY B-1) BIAS_WEIGHT_EMBEDDING       */
+  B200REC_DEEPFM = 2,   /* rec/model/deepfm/DeepFM.scala:51-125   BIAS_WEIGHT_EMBEDDING_MATS  */
+  B200REC_XDEEPFM = 3,  /* rec/model/xdeepfm/XDeepFM.scala:58-126                             */
+  B200REC_DCN = 4,      /* rec/model/dcn/DCN.scala:62-130                                     */
+  B200REC_PNN = 5       /* rec/model/pnn/PNN.scala:56-132                                     */
+};
+
+/* ---- library ------------------------------------------------------------------------- */
+int b200rec_abi_version(void);
+const char* b200rec_last_error(void);
+/* Number of usable sm_100 devices (0 and B200REC_ERR_CUDA when there is none). */
+int b200rec_device_count(int* count);
+/* Kernels launched by this library in the calling process since load (bench.py's
+ * gpu_launches claim is read from here). */
+int b200rec_launch_count(int64_t* count);
+
+/* ---- model: Internal<M>Model (constructor args are the reference's) -------------------- */
+/* DeepFM.scala:51-53, XDeepFM.scala:58-61, DCN.scala:62-65, PNN.scala:56-58.
+ * fc_dims / cin_dims may be NULL when the count is 0.  `device` = CUDA ordinal. */
+int b200rec_model_create(int kind, int n_fields, int embedding_dim,
+                         const int* fc_dims, int n_fc,
+                         const int* cin_dims, int n_cin,
+                         int cross_depth, int device, b200rec_model_t* out);
+int b200rec_model_destroy(b200rec_model_t m);
+/* getMatsSize (DeepFM.scala:15-20, XDeepFM.scala:15-28, DCN.scala:15-32, PNN.scala:15-25):
+ * writes up to `cap` ints of (in,out) pairs, returns the count in *n. */
+int b200rec_model_mats_size(b200rec_model_t m, int* pairs, int cap, int* n);
+/* sum(in*out) over the pairs (rec/model/ParRecModel.scala:107-113). */
+int b200rec_model_mats_len(b200rec_model_t m, int64_t* len);
+/* The handle's stream (cudaStream_t) so callers can order their own work against it. */
+int b200rec_model_stream(b200rec_model_t m, void** stream);
+
+/* Internal<M>Model.forward (e.g. DeepFM.scala:54-81): host arrays in, preds[B] out.
+ * index[nnz] = COO row of each non-zero; weights[nnz]; bias[1]; embedding[nnz*K] (NULL for
+ * LR); mats[mats_len] (NULL for LR/FM). */
+int b200rec_forward(b200rec_model_t m, int batch_size, int64_t nnz, const int* index,
+                    const float* weights, const float* bias, const float* embedding,
+                    const float* mats, float* preds);
+/* Internal<M>Model.backward (e.g. DeepFM.scala:83-124): returns the mean BCE loss in *loss
+ * and overwrites weights / bias / embedding / mats with their gradients. */
+int b200rec_backward(b200rec_model_t m, int batch_size, int64_t nnz, const int* index,
+                     float* weights, float* bias, float* embedding, float* mats,
+                     const float* targets, float* loss);
+/* Same two calls on device memory.  `index` may be NULL = canonical COO rows (index[i] = i/F,
+ * what SampleParser emits).  loss_dev is a device float. */
+int b200rec_forward_dev(b200rec_model_t m, int batch_size, int64_t nnz, const int* index,
+                        const float* weights, const float* bias, const float* embedding,
+                        const float* mats, float* preds, void* stream);
+int b200rec_backward_dev(b200rec_model_t m, int batch_size, int64_t nnz, const int* index,
+                         float* weights, float* bias, float* embedding, float* mats,
+                         const float* targets, float* loss_dev, void* stream);
+
+/* ---- table: the device-resident stand-in for the PS matrices ---------------------------- */
+/* ParRecModel.initMats(inputDim) / initMats(inputDim, embeddingDim) :74-105.  One table holds
+ * the `embedding` matrix (rows x dim, row-major; the reference's PS layout is dim-major,
+ * which is not observable through the ABI) and the first-order `weights` vector (rows).
+ * row_begin/row_end: the contiguous or strided shard this table owns (see shard_mod). */
+int b200rec_table_create(int64_t rows, int dim, int device, b200rec_table_t* out);
+int b200rec_table_destroy(b200rec_table_t t);
+/* Deterministic U(lo,hi) init from a counter hash: value(row,col) = f(seed, global_row*dim+col);
+ * global_row = row_offset + local_row * row_stride (so a shard reproduces its slice of the
+ * global table).  ParRecModel.initEmbedding :66-69 (Xavier on the PS; parity unpinned). */
+int b200rec_table_init_uniform(b200rec_table_t t, uint64_t seed, float lo, float hi,
+                               int64_t row_offset, int64_t row_stride);
+/* Host <-> table rows [row0, row0+nrows). Either pointer may be NULL. */
+int b200rec_table_write(b200rec_table_t t, int64_t row0, int64_t nrows,
+                        const float* embedding, const float* weights);
+int b200rec_table_read(b200rec_table_t t, int64_t row0, int64_t nrows,
+                       float* embedding, float* weights);
+/* Device pointers of the table storage (embedding rows, weights). */
+int b200rec_table_ptrs(b200rec_table_t t, float** embedding, float** weights);
+
+/* makeEmbeddings + makeWeights (ParRecModel.scala:300-306, :279-284):
+ * embedding_out[i*K+j] = E[feats[i], j]; weights_out[i] = w[feats[i]].  Bit-exact copies. */
+int b200rec_table_lookup(b200rec_table_t t, int64_t nnz, const int* feats,
+                         float* embedding_out, float* weights_out);
+int b200rec_table_lookup_dev(b200rec_table_t t, int64_t nnz, const int* feats,
+                             float* embedding_out, float* weights_out, void* stream);
+
+/* distinctIntIndices (ParRecModel.scala:337-345).  Output is sorted ascending (the reference's
+ * order is hash order, i.e. unspecified).  unique_out needs room for nnz ints. */
+int b200rec_distinct(int device, int64_t nnz, const int* feats, int* unique_out, int64_t* n_unique);
+
+/* makeEmbeddingGrad + makeWeightsGrad (ParRecModel.scala:316-328, :293-298): per distinct id,
+ * the rows of embedding_grad (and entries of weights_grad) are summed IN NNZ ORDER i=0..N-1 in
+ * fp32 -- the order of Int2FloatOpenHashMap.addTo -- so the result is bit-identical to the
+ * reference.  unique_out[U] ascending, emb_out[U*K], w_out[U]; buffers sized for nnz.
+ * embedding_grad or weights_grad may be NULL (then the matching output is untouched). */
+int b200rec_scatter_add(int device, int dim, int64_t nnz, const int* feats,
+                        const float* embedding_grad, const float* weights_grad,
+                        int* unique_out, float* emb_out, float* w_out, int64_t* n_unique);
+
+/* ---- resident training / prediction step -------------------------------------------------
+ * ParRecModel.optimizeBiasWeightEmbeddingMats :439-478 and predictBiasWeightEmbeddingMats
+ * :555-567 without the PS RPC: lookup (gather) -> forward -> backward -> dedup scatter-add,
+ * parameters and gradients resident in HBM. */
+/* Dense params the PS would hold: bias[1] and mats[mats_len] (host).  makeBias/makeMats. */
+int b200rec_model_set_params(b200rec_model_t m, const float* bias, const float* mats);
+int b200rec_model_get_params(b200rec_model_t m, float* bias, float* mats);
+/* One step from HOST ids: feats[B*F] and targets[B] are copied in, *loss is copied out.
+ * Gradients stay on the device until fetched. */
+int b200rec_step(b200rec_model_t m, b200rec_table_t t, int batch_size,
+                 const int* feats, const float* targets, float* loss);
+/* Same with DEVICE ids / targets; no host synchronisation; loss stays in the handle. */
+int b200rec_step_dev(b200rec_model_t m, b200rec_table_t t, int batch_size,
+                     const int* feats, const float* targets, void* stream);
+/* Predict: preds[B] = sigmoid(logit) (ParRecModel.predict :519-533). */
+int b200rec_predict(b200rec_model_t m, b200rec_table_t t, int batch_size,
+                    const int* feats, float* preds);
+/* Results of the last step (host copies).  Any pointer may be NULL.
+ *  loss; n_unique; unique[U]; emb_grad[U*K]; w_grad[U]; bias_grad[1]; mats_grad[mats_len]. */
+int b200rec_step_results(b200rec_model_t m, float* loss, int64_t* n_unique, int* unique,
+                         float* emb_grad, float* w_grad, float* bias_grad, float* mats_grad);
+/* Device pointers of the same (valid until the next step on this handle). */
+int b200rec_step_result_ptrs(b200rec_model_t m, float** loss, int** n_unique, int** unique,
+                             float** emb_grad, float** w_grad, float** bias_grad,
+                             float** mats_grad);
+/* Per-nnz gradients of the last step before dedup: dE[nnz*K], dw[nnz] (device pointers). */
+int b200rec_step_nnz_grad_ptrs(b200rec_model_t m, float** emb_grad, float** w_grad);
+/* Split step for a row-sharded table: the caller gathered rows itself (all-to-all)
+ * and hands over device buffers emb[B*F*K], w[B*F]; grads are written in place (per nnz). */
+int b200rec_step_gathered_dev(b200rec_model_t m, int batch_size, float* emb, float* w,
+                              const float* targets, void* stream);
+/* Plain SGD on the touched rows: E[id] -= lr * G[id], w[id] -= lr * gw[id] (rec/optim/
+ * AsyncSGD.scala:10-31 applies the pushed gradient on the PS; textbook form, parity unpinned). */
+int b200rec_table_apply_sgd_dev(b200rec_table_t t, int64_t n_unique_cap, const int* n_unique,
+                                const int* unique, const float* emb_grad, const float* w_grad,
+                                float lr, void* stream);
+
+/* ---- the reference's own BigDL modules (updateOutput / updateGradInput / accGradParameters) */
+/* nn/Scatter.scala:17-36  output[index[i], :] += input[i, :]  (i ascending; bit-exact order). */
+int b200rec_scatter_update_output(int device, int batch_size, int n_output, int64_t n,
+                                  const float* input, const int* index, float* output);
+/* nn/Scatter.scala:38-59  grad_input[i, :] = grad_output[index[i], :]. */
+int b200rec_scatter_update_grad_input(int device, int batch_size, int n_output, int64_t n,
+                                      const int* index, const float* grad_output, float* grad_input);
+/* nn/Gather.scala:19-48   row_out[b,p,:] = input[b,rows[p],:], col_out[b,p,:] = input[b,cols[p],:]. */
+int b200rec_gather_update_output(int device, int batch_size, int n_fields, int n_pairs, int dim,
+                                 const float* input, const int* rows, const int* cols,
+                                 float* row_out, float* col_out);
+/* nn/Gather.scala:50-78   grad_input[b,rows[p],:] += g_row[b,p,:]; [b,cols[p],:] += g_col[b,p,:]
+ * (p ascending, row before col; grad_input zeroed first, see SURVEY B-9). */
+int b200rec_gather_update_grad_input(int device, int batch_size, int n_fields, int n_pairs, int dim,
+                                     const int* rows, const int* cols, const float* g_row,
+                                     const float* g_col, float* grad_input);
+/* nn/DotProduct2.scala:16-26  out[b,p] = sum_k a[b,p,k]*b[b,p,k] (k ascending). */
+int b200rec_dotproduct2_update_output(int device, int64_t n_rows, int dim, const float* a,
+                                      const float* b, float* out);
+/* nn/DotProduct2.scala:28-53  ga = b*go, gb = a*go. */
+int b200rec_dotproduct2_update_grad_input(int device, int64_t n_rows, int dim, const float* a,
+                                          const float* b, const float* grad_output,
+                                          float* ga, float* gb);
+/* rec/model/encoder/SecondOrderEncoder.scala:19-34 forward / backward.
+ * out[b] = 0.5 * mean_k[(sum_f v)^2 - sum_f v^2];  grad_in = (g_b/K)(S - v). */
+int b200rec_second_order_update_output(int device, int batch_size, int n_fields, int dim,
+                                       const float* embedding, float* out);
+int b200rec_second_order_update_grad_input(int device, int batch_size, int n_fields, int dim,
+                                           const float* embedding, const float* grad_output,
+                                           float* grad_input);
+/* BigDL Linear as used by rec/util/LayerUtil.scala:7-24: y = x W^T + b, W:[out,in].
+ * bias may be NULL.  relu != 0 fuses the following ReLU (HigherOrderEncoder.scala:40-43). */
+int b200rec_linear_update_output(int device, int batch_size, int in_dim, int out_dim,
+                                 const float* x, const float* w, const float* bias, int relu,
+                                 float* y);
+/* grad_x = gy W.   */
+int b200rec_linear_update_grad_input(int device, int batch_size, int in_dim, int out_dim,
+                                     const float* gy, const float* w, float* gx);
+/* grad_w += scale * gy^T x ; grad_b += scale * sum_b gy  (accGradParameters accumulates). */
+int b200rec_linear_acc_grad_parameters(int device, int batch_size, int in_dim, int out_dim,
+                                       const float* x, const float* gy, float scale,
+                                       float* grad_w, float* grad_b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REC_H_ */

@@ -1,0 +1,102 @@
+// Shared helpers for libb200rec (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <atomic>
+
+#include "../../include/b200rec.h"
+
+namespace b200rec {
+
+// ---- error plumbing: nothing throws across the ABI -----------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define B200_CUDA(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::b200rec::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                 \
+                           cudaGetErrorString(_e));                                      \
+      return B200REC_ERR_CUDA;                                                           \
+    }                                                                                    \
+  } while (0)
+
+#define B200_TRY(expr)                 \
+  do {                                 \
+    int _s = (expr);                   \
+    if (_s != B200REC_OK) return _s;   \
+  } while (0)
+
+#define B200_REQUIRE(cond, code, ...)      \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::b200rec::set_error(__VA_ARGS__);   \
+      return (code);                       \
+    }                                      \
+  } while (0)
+
+// Every kernel launch of this library goes through LAUNCH so b200rec_launch_count is honest.
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+  do {                                                                      \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
+    ::b200rec::g_launches.fetch_add(1, std::memory_order_relaxed);          \
+  } while (0)
+
+#define B200_CHECK_LAUNCH() B200_CUDA(cudaGetLastError())
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- device buffer that grows on demand ---------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return B200REC_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      return B200REC_ERR_NOMEM;
+    }
+    cap = want;
+    return B200REC_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---- device helpers ----------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+// streaming (read-once) 128-bit load: do not pollute L1
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_f4(float* p, const float4& v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
+
+}  // namespace b200rec

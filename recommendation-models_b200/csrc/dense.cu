@@ -1,0 +1,240 @@
+// Dense (Linear) layers on the exact-fp32 SIMT GEMM, plus the small reductions around them.
+//
+// Reference: BigDL Linear as instantiated by rec/util/LayerUtil.scala:7-24 (y = x W^T + b with
+// W:[out,in] row-major inside `mats`), its gradients copied back by rec/util/BackwardUtil.scala:6-31,
+// stacked by rec/model/encoder/HigherOrderEncoder.scala:34-58.
+#include "gemm_simt.cuh"
+#include "kernels.h"
+
+namespace b200rec {
+
+__global__ void splitk_reduce_kernel(const float* ws, int splits, long long MN, float scale,
+                                     bool accumulate, float* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < MN;
+       i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += ws[z * MN + i];
+    s *= scale;
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+
+static int grid1d(long long n, int threads = 256, int cap = 148 * 16) {
+  int g = cdiv(n, threads);
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : g;
+}
+
+int splitk_reduce(const float* ws, int splits, long long MN, float scale, bool accumulate,
+                  float* out, cudaStream_t st) {
+  B200_LAUNCH(splitk_reduce_kernel, grid1d(MN), 256, 0, st, ws, splits, MN, scale, accumulate, out);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+int linear_fwd(int M, int N, int K, const float* x, const float* w, const float* b, bool relu,
+               float* y, cudaStream_t st) {
+  if (N == 1) {  // Linear(K -> 1): a row dot product
+    B200_TRY(gemv_rows(M, K, x, K, w, b, false, y, st));
+    if (relu) return add_bias_relu(M, y, nullptr, y, st);
+    return B200REC_OK;
+  }
+  return gemm_simt(M, N, K, 1, RowMajorOp{x, K}, RowMajorOp{w, K}, EpBiasAct{y, N, b, relu}, st);
+}
+
+int linear_bwd_input(int M, int N, int K, const float* gy, const float* w, const float* mask,
+                     float* gx, bool accumulate, cudaStream_t st) {
+  // gx[M,K] = gy[M,N] W[N,K]: contraction over N
+  return gemm_simt(M, K, N, 1, RowMajorOp{gy, N}, ColMajorOp{w, K},
+                   EpMaskAcc{gx, K, mask, K, accumulate}, st);
+}
+
+// column sums of gy[M,N] in two fixed-order stages
+__global__ void colsum_stage1(int M, int N, const float* g, int rows_per_chunk, float* part) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (n >= N) return;
+  const int r0 = c * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += g[(long long)r * N + n];
+  part[(long long)c * N + n] = s;
+}
+__global__ void colsum_stage2(int N, int chunks, const float* part, float scale, bool accumulate,
+                              float* out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += part[(long long)c * N + n];
+  s *= scale;
+  out[n] = accumulate ? out[n] + s : s;
+}
+
+int colsum(int M, int N, const float* g, float scale, bool accumulate, float* out, float* part,
+           cudaStream_t st) {
+  const int chunks = 64;
+  dim3 g1(cdiv(N, 128), chunks);
+  B200_LAUNCH(colsum_stage1, g1, 128, 0, st, M, N, g, cdiv(M, chunks), part);
+  B200_LAUNCH(colsum_stage2, cdiv(N, 128), 128, 0, st, N, chunks, part, scale, accumulate, out);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+int linear_bwd_params(int M, int N, int K, const float* x, const float* gy, float scale,
+                      bool accumulate, float* gw, float* gb, DevBuf& scratch, cudaStream_t st) {
+  // gw[N,K] = gy^T x : output N x K, contraction over the batch M
+  const int splits = pick_splits(N, K, M);
+  const long long MN = (long long)N * K;
+  B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)64 * N) * sizeof(float)));
+  float* ws = scratch.as<float>();
+  B200_TRY(gemm_simt(N, K, M, splits, ColMajorOp{gy, N}, ColMajorOp{x, K}, EpPartial{ws, MN, K},
+                     st));
+  B200_TRY(splitk_reduce(ws, real_splits(M, splits), MN, scale, accumulate, gw, st));
+  if (gb) B200_TRY(colsum(M, N, gy, scale, accumulate, gb, ws + (size_t)splits * MN, st));
+  return B200REC_OK;
+}
+
+// out[m] (+)= x[m,:] . w + b0      one warp per row
+__global__ void gemv_rows_kernel(int M, int K, const float* x, int ldx, const float* w,
+                                 const float* b0, bool accumulate, float* out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int m = blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += gridDim.x * wpb) {
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(x[(long long)m * ldx + k], __ldg(w + k), s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (b0) s += __ldg(b0);
+      out[m] = accumulate ? out[m] + s : s;
+    }
+  }
+}
+int gemv_rows(int M, int K, const float* x, int ldx, const float* w, const float* b0,
+              bool accumulate, float* out, cudaStream_t st) {
+  if (M <= 0) return B200REC_OK;
+  B200_LAUNCH(gemv_rows_kernel, grid1d((long long)M * 32), 256, 0, st, M, K, x, ldx, w, b0,
+              accumulate, out);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+// g[m,k] = d[m] * w[k] (* (mask[m,k] > 0))
+__global__ void outer_rows_kernel(int M, int K, const float* d, const float* w, const float* mask,
+                                  int ldm, float* g, int ldg) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)M * K;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(t / K), k = (int)(t - (long long)m * K);
+    float v = __ldg(d + m) * __ldg(w + k);
+    if (mask && !(mask[(long long)m * ldm + k] > 0.f)) v = 0.f;
+    g[(long long)m * ldg + k] = v;
+  }
+}
+int outer_rows(int M, int K, const float* d, const float* w, const float* mask, int ldm, float* g,
+               int ldg, cudaStream_t st) {
+  if ((long long)M * K <= 0) return B200REC_OK;
+  B200_LAUNCH(outer_rows_kernel, grid1d((long long)M * K), 256, 0, st, M, K, d, w, mask, ldm, g,
+              ldg);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+// gw[k] = sum_m d[m] x[m,k]   (two fixed-order stages)
+__global__ void wcolsum_stage1(int M, int K, const float* d, const float* x, int ldx,
+                               int rows_per_chunk, float* part) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (k >= K) return;
+  const int r0 = c * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s = fmaf(__ldg(d + r), x[(long long)r * ldx + k], s);
+  part[(long long)c * K + k] = s;
+}
+int wcolsum(int M, int K, const float* d, const float* x, int ldx, float* gw, DevBuf& scratch,
+            cudaStream_t st) {
+  const int chunks = 64;
+  B200_TRY(scratch.reserve((size_t)chunks * K * sizeof(float)));
+  float* part = scratch.as<float>();
+  dim3 g1(cdiv(K, 128), chunks);
+  B200_LAUNCH(wcolsum_stage1, g1, 128, 0, st, M, K, d, x, ldx, cdiv(M, chunks), part);
+  B200_LAUNCH(colsum_stage2, cdiv(K, 128), 128, 0, st, K, chunks, part, 1.0f, false, gw);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+// deterministic sum of n floats
+__global__ void reduce_stage1(long long n, const float* x, float* part) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long b0 = blockIdx.x * per, b1 = min(n, b0 + per);
+  for (long long i = b0 + threadIdx.x; i < b1; i += blockDim.x) s += x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void reduce_stage2(int nparts, const float* part, float scale, float* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < nparts; ++i) t += part[i];
+    out[0] = t * scale;
+  }
+}
+int reduce_sum(long long n, const float* x, float scale, float* out, DevBuf& scratch,
+               cudaStream_t st) {
+  const int parts = 64;
+  B200_TRY(scratch.reserve(parts * sizeof(float)));
+  B200_LAUNCH(reduce_stage1, parts, 256, 0, st, n, x, scratch.as<float>());
+  B200_LAUNCH(reduce_stage2, 1, 32, 0, st, parts, scratch.as<float>(), scale, out);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+// h = relu(a + c0)  (c0 optional scalar)
+__global__ void add_bias_relu_kernel(long long n, const float* a, const float* c0, float* h) {
+  const float c = c0 ? __ldg(c0) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    h[i] = fmaxf(a[i] + c, 0.f);
+}
+int add_bias_relu(long long n, const float* a, const float* c0, float* h, cudaStream_t st) {
+  if (n <= 0) return B200REC_OK;
+  B200_LAUNCH(add_bias_relu_kernel, grid1d(n), 256, 0, st, n, a, c0, h);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+__global__ void relu_mask_kernel(long long n, const float* g, const float* h, float* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = h[i] > 0.f ? g[i] : 0.f;
+}
+int relu_mask(long long n, const float* g, const float* h, float* out, cudaStream_t st) {
+  if (n <= 0) return B200REC_OK;
+  B200_LAUNCH(relu_mask_kernel, grid1d(n), 256, 0, st, n, g, h, out);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+__global__ void axpy_kernel(long long n, const float* x, float* y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] += x[i];
+}
+int axpy(long long n, const float* x, float* y, cudaStream_t st) {
+  if (n <= 0) return B200REC_OK;
+  B200_LAUNCH(axpy_kernel, grid1d(n), 256, 0, st, n, x, y);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+int pnn_lp_fwd(int B, int P, int O, const float* ip, const float* wp, const float* prev,
+               const float* c0, float* h, cudaStream_t st) {
+  // ProductEncoder.scala:97-108: CAddTable(lz, lp) -> CAdd(scalar) -> ReLU
+  return gemm_simt(B, O, P, 1, RowMajorOp{ip, P}, RowMajorOp{wp, P}, EpAddBiasRelu2{h, O, prev, c0},
+                   st);
+}
+
+}  // namespace b200rec

@@ -1,0 +1,172 @@
+// Internal (C++) interface between the kernel translation units and the C ABI / model driver.
+#pragma once
+#include "common.cuh"
+
+namespace b200rec {
+
+// ---------------------------------------------------------------- sparse.cu (HBM-bound) ------
+// Device-side status word written by kernels that validate ids / indices.
+enum DevErr : int { DEV_OK = 0, DEV_BAD_ID = 1, DEV_BAD_INDEX = 2 };
+
+struct SparseFwd {
+  int B = 0, F = 0, K = 0;
+  long long rows = 0;            // table rows (gather mode) for the id range check
+  const int* feats = nullptr;    // [B*F] global ids; nullptr => rows are already in emb_in
+  const float* table = nullptr;  // [rows,K]
+  const float* wtable = nullptr; // [rows]
+  const float* emb_in = nullptr; // [B*F*K]  (flat mode)
+  const float* w_in = nullptr;   // [B*F]    (flat mode)
+  float* X = nullptr;            // [B,F*K] gathered rows out (gather mode, optional)
+  float* w_out = nullptr;        // [B*F]   gathered first-order weights out (optional)
+  float* first = nullptr;        // [B]  sum_f w   (canonical index only)          (optional)
+  float* second = nullptr;       // [B]  0.5/K sum_k (S^2 - Q)                     (optional)
+  float* S = nullptr;            // [B,K] sum_f v  (saved for the backward)        (optional)
+  int* err = nullptr;            // DevErr word
+};
+int sparse_fwd(const SparseFwd& a, cudaStream_t st);
+
+struct SparseBwd {
+  int B = 0, F = 0, K = 0;
+  const float* X = nullptr;       // [B,F*K] rows (v)
+  const float* S = nullptr;       // [B,K]  or nullptr when the model has no second-order term
+  const float* dX = nullptr;      // [B,F*K] dense-branch input grad, or nullptr
+  const float* dlogit = nullptr;  // [B]
+  const int* index = nullptr;     // [B*F] or nullptr (canonical)
+  float* dE = nullptr;            // [B*F*K] out (may alias X)
+  float* dw = nullptr;            // [B*F] out
+};
+int sparse_bwd(const SparseBwd& a, cudaStream_t st);
+
+// nn/Scatter.scala generic forms (arbitrary index, n_output columns)
+int scatter_fwd(int B, int n_out, long long n, const float* in, const int* index, float* out,
+                int* err, cudaStream_t st);
+int scatter_bwd(int B, int n_out, long long n, const int* index, const float* gout, float* gin,
+                int* err, cudaStream_t st);
+int lookup_rows(long long rows, int K, long long n, const int* feats, const float* table,
+                const float* wtable, float* emb_out, float* w_out, int* err, cudaStream_t st);
+// nn/Gather.scala / nn/DotProduct2.scala
+int pair_gather_fwd(int B, int F, int P, int K, const float* in, const int* rows, const int* cols,
+                    float* row_out, float* col_out, cudaStream_t st);
+int pair_gather_bwd(int B, int F, int P, int K, const int* rows, const int* cols,
+                    const float* g_row, const float* g_col, float* gin, cudaStream_t st);
+int dot2_fwd(long long n, int K, const float* a, const float* b, float* out, cudaStream_t st);
+int dot2_bwd(long long n, int K, const float* a, const float* b, const float* go, float* ga,
+             float* gb, cudaStream_t st);
+
+// ---------------------------------------------------------------- segsum.cu (scatter-add) ----
+struct SegSumWorkspace {
+  DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, seg_start, long_list, counters;
+  long long cap_n = 0;
+  int reserve(long long n);
+  void release();
+};
+struct SegSum {
+  long long n = 0;
+  int K = 0;
+  int key_bits = 31;              // radix-sort only the bits that can be set
+  const int* feats = nullptr;     // [n]
+  const float* dE = nullptr;      // [n,K] or nullptr
+  const float* dw = nullptr;      // [n]   or nullptr
+  int* unique = nullptr;          // [n] out (ascending)
+  float* G = nullptr;             // [n,K] out (first U rows valid)
+  float* gw = nullptr;            // [n]   out
+  int* n_unique = nullptr;        // device int out
+};
+// sort half (depends only on feats: can run on a side stream while the dense math runs)
+int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st);
+// reduce half (needs dE / dw)
+int segsum_reduce(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st);
+int apply_sgd(int K, long long cap, const int* n_unique, const int* unique, const float* G,
+              const float* gw, float lr, float* table, float* wtable, cudaStream_t st);
+
+// ---------------------------------------------------------------- dense.cu (SIMT fp32) --------
+// y[M,N] = act(x[M,K] W[N,K]^T + b[N])   (BigDL Linear + optional ReLU)
+int linear_fwd(int M, int N, int K, const float* x, const float* w, const float* b, bool relu,
+               float* y, cudaStream_t st);
+// gx[M,K] = (gy[M,N] W[N,K]) (* (mask[M,K] > 0) if mask)
+int linear_bwd_input(int M, int N, int K, const float* gy, const float* w, const float* mask,
+                     float* gx, bool accumulate, cudaStream_t st);
+// gw[N,K] (+)= scale * gy[M,N]^T x[M,K] ; gb[N] (+)= scale * colsum(gy)   (split-K, fixed order)
+int linear_bwd_params(int M, int N, int K, const float* x, const float* gy, float scale,
+                      bool accumulate, float* gw, float* gb, DevBuf& scratch, cudaStream_t st);
+// out[M] = x[M,K] . w[K] (+ b0)      (Linear(K -> 1))
+int gemv_rows(int M, int K, const float* x, int ldx, const float* w, const float* b0,
+              bool accumulate, float* out, cudaStream_t st);
+// g[M,K] = d[M] (x) w[K]  (* (mask>0))   -- backward of Linear(K->1) w.r.t. its input
+int outer_rows(int M, int K, const float* d, const float* w, const float* mask, int ldm,
+               float* g, int ldg, cudaStream_t st);
+// gw[K] = sum_m d[m] * x[m,k] ;  deterministic two-stage
+int wcolsum(int M, int K, const float* d, const float* x, int ldx, float* gw, DevBuf& scratch,
+            cudaStream_t st);
+// sum of n floats into out[0] (deterministic two-stage); scale applied
+int reduce_sum(long long n, const float* x, float scale, float* out, DevBuf& scratch,
+               cudaStream_t st);
+
+// ---------------------------------------------------------------- head.cu ---------------------
+// logit = sum branches + bias ; p = sigmoid ; (optional) BCE loss + dlogit + dbias
+struct Head {
+  int B = 0;
+  const float* br[4] = {nullptr, nullptr, nullptr, nullptr};  // up to 4 branches [B]
+  int n_br = 0;
+  const float* bias = nullptr;     // [1]
+  const float* targets = nullptr;  // [B] or nullptr (forward only)
+  float* preds = nullptr;          // [B]
+  float* dlogit = nullptr;         // [B]
+  float* loss = nullptr;           // [1]
+  float* dbias = nullptr;          // [1]
+};
+int head_run(const Head& h, DevBuf& scratch, cudaStream_t st);
+
+// ---------------------------------------------------------------- cin.cu ----------------------
+struct CinDims {
+  int B, F, K;
+  int n_layers;
+  int H[9];  // H[0]=F, H[l]=cin_dims[l-1]
+};
+// x0[(b,k),f] = X[b,f,k]
+int cin_transpose_in(int B, int F, int K, const float* X, float* x0, cudaStream_t st);
+// ge[b,f,k] (+)= gx0[(b,k),f]
+int cin_transpose_out(int B, int F, int K, const float* gx0, float* gE, bool accumulate,
+                      cudaStream_t st);
+// x_out[r,c] = relu( sum_{i,j} x0[r,i] x_in[r,j] W[c,i*H+j] + b[c] )
+int cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
+                  const float* b, float* x_out, cudaStream_t st);
+// pooled[b, col0 + c] = sum_k x[(b,k), c]
+int cin_pool(int B, int K, int C, const float* x, float* pooled, int ld, int col0, cudaStream_t st);
+// gy[r,c] = (gp[b, col0+c] + (g_next? g_next[r,c] : 0)) * (x_out[r,c] > 0)
+int cin_gy(int B, int K, int C, const float* gp, int ld, int col0, const float* g_next,
+           const float* x_out, float* gy, cudaStream_t st);
+// layer backward: gW[c, i*H+j] = sum_r gy Z ; gb ; gx_in[r,j] ; gx0[r,i] +=
+int cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
+                  const float* gy, float* gW, float* gb, float* gx_in, float* gx0,
+                  DevBuf& scratch, cudaStream_t st);
+
+// ---------------------------------------------------------------- cross.cu (DCN) ---------------
+// forward: xL[B,D], s[L,B]
+int cross_fwd(int B, int D, int L, const float* X, const float* w, const float* c, float* xL,
+              float* s, cudaStream_t st);
+// backward: g_xL[B,D] in -> dX[B,D] out, gw[L,D], gc[L]
+int cross_bwd(int B, int D, int L, const float* X, const float* w, const float* c, const float* s,
+              const float* g_xL, float* dX, float* gw, float* gc, DevBuf& scratch,
+              cudaStream_t st);
+
+// ---------------------------------------------------------------- pnn.cu -----------------------
+// ip[b,p] = <v_i, v_j>, pairs i<j lexicographic
+int pnn_ip_fwd(int B, int F, int K, const float* X, float* ip, cudaStream_t st);
+// h = relu(prev + x W^T + c0)   (second product GEMM of the PNN layer)
+int pnn_lp_fwd(int B, int P, int O, const float* ip, const float* wp, const float* prev,
+               const float* c0, float* h, cudaStream_t st);
+// dX[b,i,:] (+)= sum_{j != i} gip[b,pair(i,j)] v_j   (j ascending = reference order)
+int pnn_ip_bwd(int B, int F, int K, const float* X, const float* gip, float* dX, bool accumulate,
+               cudaStream_t st);
+// h = relu(a + b + c0)  /  g = gout * (h > 0)
+int add_bias_relu(long long n, const float* a, const float* c0, float* h, cudaStream_t st);
+int relu_mask(long long n, const float* g, const float* h, float* out, cudaStream_t st);
+// y += x
+int axpy(long long n, const float* x, float* y, cudaStream_t st);
+
+// ---------------------------------------------------------------- table.cu ---------------------
+int table_init_uniform(float* table, float* wtable, long long rows, int K, uint64_t seed, float lo,
+                       float hi, long long row_offset, long long row_stride, cudaStream_t st);
+
+}  // namespace b200rec

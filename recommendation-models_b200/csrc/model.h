@@ -1,0 +1,93 @@
+// Model / table handle definitions (opaque through the C ABI).
+#pragma once
+#include <vector>
+
+#include "kernels.h"
+
+namespace b200rec {
+
+struct MlpPlan {
+  int in_dim = 0;
+  std::vector<int> dims;
+  bool head = false;
+  long long off = 0, end = 0;
+  std::vector<long long> w_off, b_off;
+  void build(int in, const std::vector<int>& d, bool with_head, long long start);
+};
+
+struct RunArgs {
+  int B = 0;
+  long long nnz = 0;
+  const int* index = nullptr;  // device; nullptr = canonical (index[i] = i / F)
+  // resident source (gather fused into the forward)
+  const int* feats = nullptr;
+  const float* table_emb = nullptr;
+  const float* table_w = nullptr;
+  long long table_rows = 0;
+  // flat source (rows already gathered)
+  const float* w_nz = nullptr;
+  const float* emb = nullptr;
+  // dense params
+  const float* bias = nullptr;
+  const float* mats = nullptr;
+  const float* targets = nullptr;  // nullptr => forward only
+  float* preds = nullptr;
+  // backward outputs
+  float* dw_out = nullptr;     // [nnz]
+  float* dE_out = nullptr;     // [nnz*K]  (may alias emb / X)
+  float* dbias_out = nullptr;  // [1]
+  float* gmats_out = nullptr;  // [mats_len]
+  float* loss_out = nullptr;   // [1]
+};
+
+}  // namespace b200rec
+
+struct b200rec_table_s {
+  long long rows = 0;
+  int dim = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  b200rec::DevBuf emb, w, stage_i, stage_e, stage_w, err;
+};
+
+struct b200rec_model_s {
+  int kind = 0, F = 0, K = 0, D = 0, depth = 0, device = 0;
+  std::vector<int> fc, cin, pairs;
+  long long mats_len = 0;
+  b200rec::MlpPlan mlp;
+  std::vector<long long> cin_w, cin_b;
+  long long out_off = 0;
+  cudaStream_t stream = nullptr, side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float* h_scal = nullptr;  // pinned 16 words: loss, dbias, n_unique, -, err, sorted
+  bool params_set = false;
+  int last_B = 0;
+  long long last_nnz = 0;
+  using DevBuf = b200rec::DevBuf;
+  DevBuf p_bias, p_mats, gmats, scal;
+  DevBuf d_feats, d_targets, d_index, stage_a, stage_b;
+  DevBuf X, wnz, S, first, second, branch, preds, dlogit, dXd, dw, gA, gB, scratch;
+  DevBuf uniq, G, gwU;
+  DevBuf x0, gx0, gy, gnA, gnB, pooled, gpooled;
+  DevBuf xL, s_cross, g_xL;
+  DevBuf ip, gip, pre, hbuf;
+  std::vector<DevBuf> acts, xl;
+  b200rec::SegSumWorkspace seg;
+
+  int init(int kind, int F, int K, const int* fc, int n_fc, const int* cin, int n_cin, int depth,
+           int device);
+  void destroy();
+  int reserve(int B, long long nnz);
+  int mlp_forward(int B, const float* x_in, const float* mats, const float** last_out,
+                  float* head_out, cudaStream_t st);
+  int mlp_backward(int B, const float* x_in, const float* mats, float* gm, float* dx,
+                   const float* in_mask, cudaStream_t st);
+  int mlp_head_backward(int B, const float* x_in, const float* mats, float* gm, const float* dlg,
+                        float* dx_if_no_hidden, cudaStream_t st);
+  int run(const b200rec::RunArgs& a, cudaStream_t st);
+};
+
+namespace b200rec {
+using Model = ::b200rec_model_s;
+using Table = ::b200rec_table_s;
+}  // namespace b200rec

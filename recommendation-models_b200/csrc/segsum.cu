@@ -1,0 +1,311 @@
+// Sorted-index segmented scatter-add (deterministic, reference order).
+//
+// Reference: rec/model/ParRecModel.scala:316-328 (makeEmbeddingGrad) and :293-298
+// (makeWeightsGrad): for every non-zero i = 0..N-1 IN ORDER, grads(j).addTo(feats(i), buf(i*K+j)).
+// So the gradient of a distinct id is the fp32 sum of its rows in increasing i.
+//
+// Here: a stable LSD radix sort of (id, i) pairs groups equal ids while keeping i ascending;
+// segment heads give the distinct ids (ascending); each segment is then summed strictly in
+// order.  Loads are issued in parallel, only the fp32 adds are sequential, so the result is
+// bit-identical to the reference's hash-map accumulation regardless of grid size -- there are
+// no float atomics anywhere.
+//   * short segments (<= LONG_T rows): LPR = K/4 lanes per segment, 128-bit loads
+//   * long segments  (hot ids of the power law): one warp per segment; 32/LPR rows are loaded
+//     per instruction, then folded into the accumulator in order through shuffles.
+// The sort half depends only on the ids, so the driver runs it on a side stream while the
+// dense math runs (model.cu).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "kernels.h"
+
+namespace b200rec {
+
+static constexpr int LONG_T = 32;
+
+int SegSumWorkspace::reserve(long long n) {
+  if (n <= cap_n) return B200REC_OK;
+  const size_t ni = (size_t)n + 8;
+  B200_TRY(keys_b.reserve(ni * 4));
+  B200_TRY(vals_a.reserve(ni * 4));
+  B200_TRY(vals_b.reserve(ni * 4));
+  B200_TRY(seg_start.reserve(ni * 4));
+  B200_TRY(long_list.reserve(ni / LONG_T * 4 + 64));
+  B200_TRY(counters.reserve(64));
+  size_t sort_bytes = 0, scan_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                  (const unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 32);
+  cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)n);
+  B200_TRY(cub_tmp.reserve((sort_bytes > scan_bytes ? sort_bytes : scan_bytes) * 2 + 1024));
+  cap_n = n;
+  return B200REC_OK;
+}
+
+void SegSumWorkspace::release() {
+  keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); cub_tmp.release();
+  seg_start.release(); long_list.release(); counters.release();
+  cap_n = 0;
+}
+
+__global__ void iota_kernel(long long n, unsigned* v, int* counters) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (unsigned)i;
+  if (i == 0) { counters[0] = 0; counters[1] = 0; }
+}
+
+struct HeadFlag {
+  const unsigned* keys;
+  __host__ __device__ int operator()(int i) const {
+    return (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+  }
+};
+
+// seg_idx[i] = 1-based segment number of sorted position i (inclusive scan of the head flags)
+__global__ void seg_heads_kernel(long long n, const unsigned* keys, const int* seg_idx,
+                                 int* seg_start, int* unique, int* n_unique) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = seg_idx[i];
+  if (i == 0 || keys[i] != keys[i - 1]) {
+    seg_start[s - 1] = (int)i;
+    unique[s - 1] = (int)keys[i];
+  }
+  if (i == n - 1) {
+    *n_unique = s;
+    seg_start[s] = (int)n;
+  }
+}
+
+int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
+  B200_TRY(ws.reserve(a.n));
+  int* counters = ws.counters.as<int>();
+  if (a.n <= 0) {
+    B200_CUDA(cudaMemsetAsync(a.n_unique, 0, sizeof(int), st));
+    return B200REC_OK;
+  }
+  const int n = (int)a.n;
+  unsigned* vals_in = ws.vals_a.as<unsigned>();
+  unsigned* perm = ws.vals_b.as<unsigned>();
+  unsigned* keys_sorted = ws.keys_b.as<unsigned>();
+  B200_LAUNCH(iota_kernel, cdiv(n, 256), 256, 0, st, (long long)n, vals_in, counters);
+  size_t tmp = ws.cub_tmp.cap;
+  int bits = a.key_bits < 1 ? 1 : (a.key_bits > 32 ? 32 : a.key_bits);
+  B200_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp.p, tmp, (const unsigned*)a.feats,
+                                            keys_sorted, vals_in, perm, n, 0, bits, st));
+  g_launches.fetch_add(2 + (bits + 7) / 8, std::memory_order_relaxed);  // cub's own kernels
+  // head flags -> inclusive scan -> segment table.  vals_a (the iota) is free again: reuse it.
+  int* seg_idx = ws.vals_a.as<int>();
+  cub::CountingInputIterator<int> cnt(0);
+  cub::TransformInputIterator<int, HeadFlag, cub::CountingInputIterator<int>> flags(
+      cnt, HeadFlag{keys_sorted});
+  tmp = ws.cub_tmp.cap;
+  B200_CUDA(cub::DeviceScan::InclusiveSum(ws.cub_tmp.p, tmp, flags, seg_idx, n, st));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  B200_LAUNCH(seg_heads_kernel, cdiv(n, 256), 256, 0, st, (long long)n, keys_sorted, seg_idx,
+              ws.seg_start.as<int>(), a.unique, a.n_unique);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+// ---- in-order segment sums --------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256) segsum_short_kernel(const int* n_unique,
+                                                           const int* seg_start,
+                                                           const unsigned* perm, const float* dE,
+                                                           const float* dw, float* G, float* gw,
+                                                           int* long_list, int* long_count) {
+  constexpr int K = 4 * LPR;
+  constexpr int UNR = 4;
+  const int U = *n_unique;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int sub = (int)(tid % LPR);
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
+  for (long long seg = tid / LPR; seg < U; seg += n_groups) {
+    const int start = seg_start[seg];
+    const int len = seg_start[seg + 1] - start;
+    if (len > LONG_T) {
+      if (sub == 0) long_list[atomicAdd(long_count, 1)] = (int)seg;
+      continue;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float aw = 0.f;
+    for (int j0 = 0; j0 < len; j0 += UNR) {
+      float4 v[UNR];
+      float w[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w[u] = 0.f;
+        if (j0 + u < len) {
+          const long long p = perm[start + j0 + u];
+          if (dE) v[u] = ldg_f4(dE + p * K + sub * 4);
+          if (dw && sub == 0) w[u] = __ldg(dw + p);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (j0 + u < len) {
+          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+          aw += w[u];
+        }
+      }
+    }
+    if (G) st_f4(G + seg * K + sub * 4, acc);
+    if (gw && sub == 0) gw[seg] = aw;
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) segsum_long_kernel(const int* seg_start,
+                                                          const unsigned* perm, const float* dE,
+                                                          const float* dw, float* G, float* gw,
+                                                          const int* long_list,
+                                                          const int* long_count) {
+  constexpr int K = 4 * LPR;
+  constexpr int RPW = 32 / LPR;
+  constexpr int UNR = 4;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, slot = lane / LPR;
+  const int n_long = *long_count;
+  const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int n_warps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  for (int wi = warp; wi < n_long; wi += n_warps) {
+    const int seg = long_list[wi];
+    const int start = seg_start[seg];
+    const int len = seg_start[seg + 1] - start;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float aw = 0.f;
+    for (int base = 0; base < len; base += RPW * UNR) {
+      float4 v[UNR];
+      float w[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int j = base + u * RPW + slot;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w[u] = 0.f;
+        if (j < len) {
+          const long long p = perm[start + j];
+          if (dE) v[u] = ldg_f4(dE + p * K + sub * 4);
+          if (dw && sub == 0) w[u] = __ldg(dw + p);
+        }
+      }
+      // fold the RPW*UNR rows into the accumulator strictly in order (all lanes keep a copy)
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+        for (int s = 0; s < RPW; ++s) {
+          const int src = s * LPR + sub;
+          const float x = __shfl_sync(0xffffffffu, v[u].x, src);
+          const float y = __shfl_sync(0xffffffffu, v[u].y, src);
+          const float z = __shfl_sync(0xffffffffu, v[u].z, src);
+          const float q = __shfl_sync(0xffffffffu, v[u].w, src);
+          const float ww = __shfl_sync(0xffffffffu, w[u], s * LPR);
+          if (base + u * RPW + s < len) {
+            acc.x += x; acc.y += y; acc.z += z; acc.w += q;
+            aw += ww;
+          }
+        }
+      }
+    }
+    if (G && slot == 0) st_f4(G + (long long)seg * K + sub * 4, acc);
+    if (gw && lane == 0) gw[seg] = aw;
+  }
+}
+
+// any K: one thread per (segment, k), strictly sequential
+__global__ void segsum_generic_kernel(const int* n_unique, const int* seg_start,
+                                      const unsigned* perm, int K, const float* dE,
+                                      const float* dw, float* G, float* gw) {
+  const int U = *n_unique;
+  const int KK = K + 1;  // column K = the first-order weight gradient
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)U * KK;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long seg = t / KK;
+    const int k = (int)(t - seg * KK);
+    const int start = seg_start[seg], end = seg_start[seg + 1];
+    float acc = 0.f;
+    if (k < K) {
+      if (!dE) continue;
+      for (int j = start; j < end; ++j) acc += dE[(long long)perm[j] * K + k];
+      G[seg * K + k] = acc;
+    } else {
+      if (!dw) continue;
+      for (int j = start; j < end; ++j) acc += dw[perm[j]];
+      gw[seg] = acc;
+    }
+  }
+}
+
+template <int LPR>
+static int launch_segsum(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
+  const int* seg_start = ws.seg_start.as<int>();
+  const unsigned* perm = ws.vals_b.as<unsigned>();
+  int* counters = ws.counters.as<int>();
+  int* long_list = ws.long_list.as<int>();
+  long long groups = a.n;  // upper bound on the number of segments
+  int grid = cdiv(groups * LPR, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  B200_LAUNCH((segsum_short_kernel<LPR>), grid, 256, 0, st, a.n_unique, seg_start, perm, a.dE, a.dw,
+              a.G, a.gw, long_list, counters);
+  long long max_long = a.n / LONG_T + 1;
+  int lgrid = cdiv(max_long * 32, 256);
+  if (lgrid > 148 * 4) lgrid = 148 * 4;
+  B200_LAUNCH((segsum_long_kernel<LPR>), lgrid, 256, 0, st, seg_start, perm, a.dE, a.dw, a.G, a.gw,
+              long_list, counters);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+int segsum_reduce(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
+  if (a.n <= 0) return B200REC_OK;
+  int lpr = 0;
+  if (a.K % 4 == 0) {
+    int l = a.K / 4;
+    if (l >= 1 && l <= 32 && (l & (l - 1)) == 0) lpr = l;
+  }
+  switch (lpr) {
+    case 1: return launch_segsum<1>(ws, a, st);
+    case 2: return launch_segsum<2>(ws, a, st);
+    case 4: return launch_segsum<4>(ws, a, st);
+    case 8: return launch_segsum<8>(ws, a, st);
+    case 16: return launch_segsum<16>(ws, a, st);
+    case 32: return launch_segsum<32>(ws, a, st);
+    default: {
+      int grid = cdiv(a.n * (a.K + 1), 256);
+      if (grid > 148 * 8) grid = 148 * 8;
+      B200_LAUNCH(segsum_generic_kernel, grid, 256, 0, st, a.n_unique, ws.seg_start.as<int>(),
+                  ws.vals_b.as<unsigned>(), a.K, a.dE, a.dw, a.G, a.gw);
+      B200_CHECK_LAUNCH();
+      return B200REC_OK;
+    }
+  }
+}
+
+// rec/optim/AsyncSGD.scala:10-31 applies w -= lr * g on the PS (textbook SGD; Angel's PSF source
+// is third-party, parity unpinned).  Touched rows only.
+__global__ void apply_sgd_kernel(int K, const int* n_unique, const int* unique, const float* G,
+                                 const float* gw, float lr, float* table, float* wtable) {
+  const int U = *n_unique;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)U * K;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long seg = t / K;
+    const int k = (int)(t - seg * K);
+    const long long id = unique[seg];
+    if (G) table[id * K + k] -= lr * G[t];
+    if (k == 0 && gw && wtable) wtable[id] -= lr * gw[seg];
+  }
+}
+
+int apply_sgd(int K, long long cap, const int* n_unique, const int* unique, const float* G,
+              const float* gw, float lr, float* table, float* wtable, cudaStream_t st) {
+  if (cap <= 0) return B200REC_OK;
+  int grid = cdiv(cap * K, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  B200_LAUNCH(apply_sgd_kernel, grid, 256, 0, st, K, n_unique, unique, G, gw, lr, table, wtable);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+}  // namespace b200rec
