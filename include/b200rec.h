@@ -82,6 +82,13 @@ int b200rec_model_mats_size(b200rec_model_t m, int* pairs, int cap, int* n);
 int b200rec_model_mats_len(b200rec_model_t m, int64_t* len);
 /* The handle's stream (cudaStream_t) so callers can order their own work against it. */
 int b200rec_model_stream(b200rec_model_t m, void** stream);
+/* Arithmetic of the dense contractions (BigDL Linear / MM -> MKL sgemm in the reference,
+ * rec/util/LayerUtil.scala:22-24, rec/model/xdeepfm/CINEncoder.scala:152):
+ *   0 = fp32 FFMA (SIMT), 1 = 3xTF32 error-compensated tcgen05 (fp32-class accuracy, default where a
+ *   tensor-core kernel exists), 2 = single-pass TF32 tcgen05 (about 1e-3 relative; NOT parity grade). */
+int b200rec_model_set_gemm_mode(b200rec_model_t m, int mode);
+/* Wait for the handle's streams and report a deferred index / id error of a *_dev call. */
+int b200rec_model_sync(b200rec_model_t m);
 
 /* Internal<M>Model.forward (e.g. DeepFM.scala:54-81): host arrays in, preds[B] out.
  * index[nnz] = COO row of each non-zero; weights[nnz]; bias[1]; embedding[nnz*K] (NULL for
@@ -160,6 +167,11 @@ int b200rec_step_dev(b200rec_model_t m, b200rec_table_t t, int batch_size,
 /* Predict: preds[B] = sigmoid(logit) (ParRecModel.predict :519-533). */
 int b200rec_predict(b200rec_model_t m, b200rec_table_t t, int batch_size,
                     const int* feats, float* preds);
+int b200rec_predict_dev(b200rec_model_t m, b200rec_table_t t, int batch_size,
+                        const int* feats, float* preds, void* stream);
+/* Device pointers of the resident dense params (bias[1], mats[mats_len]) -- e.g. for an NCCL
+ * broadcast / an optimizer kernel of the caller. */
+int b200rec_model_param_ptrs(b200rec_model_t m, float** bias, float** mats);
 /* Results of the last step (host copies).  Any pointer may be NULL.
  *  loss; n_unique; unique[U]; emb_grad[U*K]; w_grad[U]; bias_grad[1]; mats_grad[mats_len]. */
 int b200rec_step_results(b200rec_model_t m, float* loss, int64_t* n_unique, int* unique,
@@ -174,6 +186,12 @@ int b200rec_step_nnz_grad_ptrs(b200rec_model_t m, float** emb_grad, float** w_gr
  * and hands over device buffers emb[B*F*K], w[B*F]; grads are written in place (per nnz). */
 int b200rec_step_gathered_dev(b200rec_model_t m, int batch_size, float* emb, float* w,
                               const float* targets, void* stream);
+/* makeEmbeddingGrad / makeWeightsGrad on DEVICE buffers (the owner-side reduce of a row-sharded
+ * table): sort + in-order segment sums of (feats[nnz], emb_grad[nnz*dim], w_grad[nnz]) into
+ * unique_out / emb_out / w_out (sized for nnz) and *n_unique_dev.  Uses the handle's workspace. */
+int b200rec_segsum_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, const int* feats,
+                       const float* emb_grad, const float* w_grad, int* unique_out, float* emb_out,
+                       float* w_out, int* n_unique_dev, void* stream);
 /* Plain SGD on the touched rows: E[id] -= lr * G[id], w[id] -= lr * gw[id] (rec/optim/
  * AsyncSGD.scala:10-31 applies the pushed gradient on the PS; textbook form, parity unpinned). */
 int b200rec_table_apply_sgd_dev(b200rec_table_t t, int64_t n_unique_cap, const int* n_unique,

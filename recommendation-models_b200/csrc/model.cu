@@ -251,7 +251,6 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
 
   // ---- sparse forward: (gather) + first-order + second-order -----------------------------------
   const float* Xp = a.emb;
-  const float* wnz_p = a.w_nz;
   if (a.table_emb) {
     SparseFwd s;
     s.B = B; s.F = F; s.K = has_emb ? K : 0; s.rows = a.table_rows; s.feats = a.feats;

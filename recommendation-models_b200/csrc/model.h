@@ -61,6 +61,7 @@ struct b200rec_model_s {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* h_scal = nullptr;  // pinned 16 words: loss, dbias, n_unique, -, err, sorted
   bool params_set = false;
+  int gemm_mode = 0;  // 0 fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32 tcgen05
   int last_B = 0;
   long long last_nnz = 0;
   using DevBuf = b200rec::DevBuf;

@@ -16,8 +16,6 @@
 // dense math runs (model.cu).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "kernels.h"
 
@@ -55,12 +53,10 @@ __global__ void iota_kernel(long long n, unsigned* v, int* counters) {
   if (i == 0) { counters[0] = 0; counters[1] = 0; }
 }
 
-struct HeadFlag {
-  const unsigned* keys;
-  __host__ __device__ int operator()(int i) const {
-    return (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
-  }
-};
+__global__ void head_flag_kernel(long long n, const unsigned* keys, int* flags) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
 
 // seg_idx[i] = 1-based segment number of sorted position i (inclusive scan of the head flags)
 __global__ void seg_heads_kernel(long long n, const unsigned* keys, const int* seg_idx,
@@ -97,11 +93,9 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
   g_launches.fetch_add(2 + (bits + 7) / 8, std::memory_order_relaxed);  // cub's own kernels
   // head flags -> inclusive scan -> segment table.  vals_a (the iota) is free again: reuse it.
   int* seg_idx = ws.vals_a.as<int>();
-  cub::CountingInputIterator<int> cnt(0);
-  cub::TransformInputIterator<int, HeadFlag, cub::CountingInputIterator<int>> flags(
-      cnt, HeadFlag{keys_sorted});
+  B200_LAUNCH(head_flag_kernel, cdiv(n, 256), 256, 0, st, (long long)n, keys_sorted, seg_idx);
   tmp = ws.cub_tmp.cap;
-  B200_CUDA(cub::DeviceScan::InclusiveSum(ws.cub_tmp.p, tmp, flags, seg_idx, n, st));
+  B200_CUDA(cub::DeviceScan::InclusiveSum(ws.cub_tmp.p, tmp, seg_idx, seg_idx, n, st));
   g_launches.fetch_add(2, std::memory_order_relaxed);
   B200_LAUNCH(seg_heads_kernel, cdiv(n, 256), 256, 0, st, (long long)n, keys_sorted, seg_idx,
               ws.seg_start.as<int>(), a.unique, a.n_unique);

@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(256) fm_fwd_kernel(SparseFwd a) {
           if (GATHER && a.w_out && sub == 0) a.w_out[base + f] = w[u];
         }
         S.x += v[u].x; S.y += v[u].y; S.z += v[u].z; S.w += v[u].w;
-        Q.x = fmaf(v[u].x, v[u].x, Q.x); Q.y = fmaf(v[u].y, v[u].y, Q.y);
-        Q.z = fmaf(v[u].z, v[u].z, Q.z); Q.w = fmaf(v[u].w, v[u].w, Q.w);
+        // Power(2) then Sum (SecondOrderEncoder.scala:24-26): rounded squares, then added -- no fma
+        Q.x = __fadd_rn(Q.x, __fmul_rn(v[u].x, v[u].x)); Q.y = __fadd_rn(Q.y, __fmul_rn(v[u].y, v[u].y));
+        Q.z = __fadd_rn(Q.z, __fmul_rn(v[u].z, v[u].z)); Q.w = __fadd_rn(Q.w, __fmul_rn(v[u].w, v[u].w));
         wsum += w[u];
       }
     }
@@ -92,7 +93,9 @@ __global__ void __launch_bounds__(256) fm_fwd_kernel(SparseFwd a) {
     }
     if (a.S && slot == 0) st_f4(a.S + (long long)b * K + sub * 4, S);
     if (a.second) {
-      float d = (S.x * S.x - Q.x) + (S.y * S.y - Q.y) + (S.z * S.z - Q.z) + (S.w * S.w - Q.w);
+      // Sum -> Power(2), CSubTable: (rounded S^2) - Q, so that F = 1 gives exactly 0 like the reference
+      float d = __fsub_rn(__fmul_rn(S.x, S.x), Q.x) + __fsub_rn(__fmul_rn(S.y, S.y), Q.y) +
+                __fsub_rn(__fmul_rn(S.z, S.z), Q.z) + __fsub_rn(__fmul_rn(S.w, S.w), Q.w);
 #pragma unroll
       for (int o = 1; o < LPR; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
       if (lane == 0) a.second[b] = 0.5f * (d / (float)K);
@@ -123,10 +126,10 @@ __global__ void __launch_bounds__(256) fm_fwd_generic_kernel(SparseFwd a) {
           v = a.emb_in[(base + f) * K + k];
         }
         s += v;
-        q = fmaf(v, v, q);
+        q = __fadd_rn(q, __fmul_rn(v, v));
       }
       if (a.S) a.S[(long long)b * K + k] = s;
-      d += s * s - q;
+      d += __fsub_rn(__fmul_rn(s, s), q);
     }
     d = warp_sum(d);
     float wsum = 0.f;
@@ -428,7 +431,8 @@ __global__ void dot2_fwd_kernel(long long n, int K, const float* a, const float*
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float acc = 0.f;
-    for (int k = 0; k < K; ++k) acc += a[i * K + k] * b[i * K + k];  // cmul then sum: no fma
+    for (int k = 0; k < K; ++k)  // cmul then sum (DotProduct2.scala:24-25): no fma
+      acc = __fadd_rn(acc, __fmul_rn(a[i * K + k], b[i * K + k]));
     out[i] = acc;
   }
 }
@@ -438,8 +442,8 @@ __global__ void dot2_bwd_kernel(long long n, int K, const float* a, const float*
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n * K;
        t += (long long)gridDim.x * blockDim.x) {
     const float g = go[t / K];
-    ga[t] = b[t] * g;
-    gb[t] = a[t] * g;
+    ga[t] = __fmul_rn(b[t], g);
+    gb[t] = __fmul_rn(a[t], g);
   }
 }
 

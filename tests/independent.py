@@ -102,4 +102,4 @@ def run(kind, B, F, K, index, weights, bias, embedding, mats, targets, fc=(), ci
     loss = -(t * torch.log(p) + (1 - t) * torch.log(1 - p)).mean()
     loss.backward()
     g = lambda x: None if x.grad is None else x.grad.numpy().copy()
-    return dict(pred=p.detach().numpy().copy(), loss=float(loss), gw=g(w), gb=g(b), ge=g(e), gm=g(m))
+    return dict(pred=p.detach().numpy().copy(), loss=float(loss.detach()), gw=g(w), gb=g(b), ge=g(e), gm=g(m))

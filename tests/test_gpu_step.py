@@ -1,0 +1,73 @@
+"""GPU parity of the resident step (lookup -> forward -> backward -> dedup scatter-add) against
+the oracle's gather + Model.backward + make*Grad, on synthetic Criteo-shaped batches."""
+import numpy as np
+import pytest
+
+from common import CONFIGS, assert_close, kind_of
+from oracle import refport
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+@pytest.mark.parametrize("B", [1, 96, 257])
+def test_resident_step(gpu_pkg, name, B):
+    synth = gpu_pkg.synth
+    cfg = CONFIGS[name]
+    kind = kind_of(name)
+    F, K, rows = 39, 16, 39 * 300
+    model = gpu_pkg.make_model(kind, F, K, cfg.get("fc_dims", ()), cfg.get("cin_dims", ()), cfg.get("cross_depth", 0))
+    table = gpu_pkg.EmbeddingTable(rows, K if kind != "lr" else 0)
+    table.init_uniform(42, -0.3, 0.3)
+    index, feats = synth.make_feats(1234, 3, B, F, rows)
+    targets = synth.make_targets(1234, feats, B, F)
+    mats = synth.init_mats(7, model.getMatsSize())
+    bias = np.array([0.1], np.float32)
+    ps = gpu_pkg.ParRecModel(model, table)
+    ps.setParams(bias, mats)
+    # predict
+    preds = ps.predict(feats, B)
+    emb = synth.table_rows(42, feats, K, -0.3, 0.3).reshape(-1) if kind != "lr" else None
+    w = synth.wtable_rows(42, feats, -0.3, 0.3)
+    o = refport.Model(kind, F, K, cfg.get("fc_dims", ()), cfg.get("cin_dims", ()), cfg.get("cross_depth", 0))
+    o64 = refport.Model(kind, F, K, cfg.get("fc_dims", ()), cfg.get("cin_dims", ()), cfg.get("cross_depth", 0), np.float64)
+    assert_close(preds, o.forward(B, index, w, bias, emb, mats), what="preds",
+                 ref64=o64.forward(B, index, w, bias, emb, mats))
+    # optimize
+    loss = ps.optimize(feats, targets) / B
+    res = ps.stepResults()
+    cp = lambda a: None if a is None else a.copy()
+    oe, ow, ob, om = cp(emb), cp(w), cp(bias), cp(mats)
+    oloss = o.backward(B, index, ow, ob, oe, om if om is not None and om.size else None, targets)
+    c64 = lambda a: None if a is None else a.astype(np.float64)
+    de, dw, db, dm = c64(emb), c64(w), c64(bias), c64(mats)
+    o64.backward(B, index, dw, db, de, dm if dm is not None and dm.size else None, targets)
+    assert abs(loss - oloss) <= 1e-5 * abs(oloss)
+    ids, gw = refport.make_weights_grad(ow, feats)
+    _, gw64 = refport.make_weights_grad(dw, feats)
+    assert np.array_equal(res["unique"], ids)
+    assert_close(res["w_grad"], gw, what="w_grad", ref64=gw64)
+    if kind != "lr":
+        _, G = refport.make_embedding_grad(oe, feats, K)
+        _, G64 = refport.make_embedding_grad(de, feats, K)
+        assert_close(res["emb_grad"], G, what="emb_grad", ref64=G64)
+    assert abs(res["bias_grad"] - ob[0]) <= 1e-5 * abs(ob[0]) + 2 * abs(ob[0] - db[0])
+    if mats is not None and mats.size:
+        assert_close(res["mats_grad"], om, what="mats_grad", ref64=dm)
+    model.close()
+    table.close()
+
+
+def test_step_needs_params_and_valid_ids(gpu_pkg):
+    F, K, rows, B = 5, 8, 100, 4
+    model = gpu_pkg.make_model("fm", F, K)
+    table = gpu_pkg.EmbeddingTable(rows, K)
+    ps = gpu_pkg.ParRecModel(model, table)
+    feats = np.zeros(B * F, np.int32)
+    with pytest.raises(gpu_pkg.B200RecError):
+        ps.optimize(feats, np.zeros(B, np.float32))
+    ps.setParams(np.zeros(1, np.float32))
+    feats[3] = rows
+    with pytest.raises(ValueError):
+        ps.optimize(feats, np.zeros(B, np.float32))
+    model.close(); table.close()
