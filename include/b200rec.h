@@ -67,6 +67,13 @@ int b200rec_device_count(int* count);
  * gpu_launches claim is read from here). */
 int b200rec_launch_count(int64_t* count);
 
+/* Per-kernel device timing of the calling thread's launches (CUDA events on the launching stream).
+ * The reference has wall-clock phase counters (rec/model/ParRecModel.scala:34-40,584-626); this is
+ * their device-side equivalent.  _end synchronises the device and writes lines
+ * "phase|kernel|launches|total_ms\n" into buf (truncated to cap; *needed = full size). */
+int b200rec_profile_begin(void);
+int b200rec_profile_end(char* buf, int64_t cap, int64_t* needed);
+
 /* ---- model: Internal<M>Model (constructor args are the reference's) -------------------- */
 /* DeepFM.scala:51-53, XDeepFM.scala:58-61, DCN.scala:62-65, PNN.scala:56-58.
  * fc_dims / cin_dims may be NULL when the count is 0.  `device` = CUDA ordinal. */

@@ -1,0 +1,53 @@
+"""Summarise ncu outputs brought back in gpurun_out/ into small text files under profiles/.
+
+  python profiles/summarize.py launches gpurun_out/launches_deepfm.csv > profiles/r01_launches_deepfm.txt
+  python profiles/summarize.py full gpurun_out/prof_sparse.ncu-rep > profiles/r01_full_sparse.txt
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    H = rows[h]
+    ki, vi = H.index("Kernel Name"), H.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[h + 1:]:
+        if len(r) <= vi:
+            continue
+        a = agg.setdefault(r[ki].split("(")[0][:90], [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[vi].replace(",", ""))
+    tot = sum(a[1] for a in agg.values())
+    print(f"# {path}: {sum(a[0] for a in agg.values())} launches, {tot / 1e3:.1f} us total (cold-cache, serialised: compare SHARES)")
+    print(f"{'kernel':90s} {'n':>5s} {'total_us':>10s} {'avg_us':>9s} {'share':>6s}")
+    for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{n:90s} {a[0]:5d} {a[1] / 1e3:10.1f} {a[1] / a[0] / 1e3:9.2f} {100 * a[1] / tot:5.1f}%")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    H = rows[0]
+    units = rows[1]
+    name_i = H.index("Kernel Name")
+    cols = [(k, H.index(k)) for k in KEYS if k in H]
+    for r in rows[2:]:
+        print(f"## {r[name_i][:110]}")
+        for k, i in cols:
+            print(f"   {k:70s} {r[i]:>16s} {units[i]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])

@@ -27,6 +27,8 @@ SIGNATURES = {
     "b200rec_last_error": [],
     "b200rec_device_count": [c_int_p],
     "b200rec_launch_count": [c_i64_p],
+    "b200rec_profile_begin": [],
+    "b200rec_profile_end": [C.c_char_p, C.c_int64, c_i64_p],
     "b200rec_model_create": [C.c_int, C.c_int, C.c_int, c_int_p, C.c_int, c_int_p, C.c_int, C.c_int,
                              C.c_int, C.POINTER(vp)],
     "b200rec_model_destroy": [vp],
@@ -144,3 +146,19 @@ def launch_count() -> int:
     n = C.c_int64(0)
     check(lib().b200rec_launch_count(C.byref(n)))
     return n.value
+
+
+def profile_begin():
+    check(lib().b200rec_profile_begin())
+
+
+def profile_end():
+    """-> list of (phase, kernel, launches, total_ms) for the launches since profile_begin()."""
+    buf = C.create_string_buffer(1 << 16)
+    need = C.c_int64(0)
+    check(lib().b200rec_profile_end(buf, len(buf), C.byref(need)))
+    rows = []
+    for line in buf.value.decode().splitlines():
+        tag, name, cnt, ms = line.split("|")
+        rows.append((tag, name, int(cnt), float(ms)))
+    return rows

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <string>
+#include <vector>
 
 #include "kernels.h"
 #include "model.h"
@@ -23,6 +25,23 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof g_err, fmt, ap);
   va_end(ap);
+}
+
+thread_local Prof* tl_prof = nullptr;
+thread_local const char* tl_tag = nullptr;
+
+void Prof::begin(const char* name, cudaStream_t st) {
+  if (n >= kMax) return;
+  if (!recs) recs = new Rec[kMax]();
+  Rec& r = recs[n];
+  if (!r.a) { cudaEventCreate(&r.a); cudaEventCreate(&r.b); }
+  r.tag = tl_tag; r.name = name;
+  cudaEventRecord(r.a, st);
+}
+void Prof::end(cudaStream_t st) {
+  if (n >= kMax) return;
+  cudaEventRecord(recs[n].b, st);
+  ++n;
 }
 
 // A usable device is an sm_100 (B200) one: the library carries sm_100a SASS only, no CPU path.
@@ -136,6 +155,46 @@ int b200rec_launch_count(int64_t* count) {
   B200_REQUIRE(count, B200REC_ERR_ARG, "count is NULL");
   *count = (int64_t)g_launches.load();
   return B200REC_OK;
+}
+
+int b200rec_profile_begin(void) {
+  static thread_local Prof prof;
+  prof.n = 0;
+  tl_prof = &prof;
+  return B200REC_OK;
+}
+
+int b200rec_profile_end(char* buf, int64_t cap, int64_t* needed) {
+  B200_GUARD_BEGIN
+  Prof* p = tl_prof;
+  tl_prof = nullptr;
+  B200_REQUIRE(p, B200REC_ERR_STATE, "b200rec_profile_begin was not called on this thread");
+  B200_CUDA(cudaDeviceSynchronize());
+  struct Agg { std::string key; int count; double ms; };
+  std::vector<Agg> agg;
+  for (int i = 0; i < p->n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->recs[i].a, p->recs[i].b) != cudaSuccess) { cudaGetLastError(); continue; }
+    std::string key = std::string(p->recs[i].tag ? p->recs[i].tag : "-") + "|" + p->recs[i].name;
+    size_t j = 0;
+    for (; j < agg.size(); ++j) if (agg[j].key == key) break;
+    if (j == agg.size()) agg.push_back({key, 0, 0.0});
+    agg[j].count++; agg[j].ms += ms;
+  }
+  std::string out;
+  char line[64];
+  for (auto& a : agg) {
+    snprintf(line, sizeof line, "|%d|%.6f\n", a.count, a.ms);
+    out += a.key + line;
+  }
+  if (needed) *needed = (int64_t)out.size() + 1;
+  if (buf && cap > 0) {
+    size_t ncopy = out.size() < (size_t)cap - 1 ? out.size() : (size_t)cap - 1;
+    memcpy(buf, out.data(), ncopy);
+    buf[ncopy] = 0;
+  }
+  return B200REC_OK;
+  B200_GUARD_END
 }
 
 // ---- model ---------------------------------------------------------------------------------------

@@ -38,10 +38,32 @@ extern std::atomic<long long> g_launches;
     }                                      \
   } while (0)
 
+// ---- optional per-kernel timing (b200rec_profile_begin / _end): CUDA events on the launching
+// stream around every launch of the calling thread.  Off by default; bench.py turns it on for a
+// separate pass to get per-kernel durations for the roofline lines.
+struct Prof {
+  struct Rec { const char* tag; const char* name; cudaEvent_t a, b; };
+  static constexpr int kMax = 1 << 15;
+  Rec* recs = nullptr;
+  int n = 0;
+  void begin(const char* name, cudaStream_t st);
+  void end(cudaStream_t st);
+};
+extern thread_local Prof* tl_prof;
+extern thread_local const char* tl_tag;
+struct ProfTag {  // names the phase the following launches belong to
+  const char* prev;
+  explicit ProfTag(const char* t) : prev(tl_tag) { tl_tag = t; }
+  ~ProfTag() { tl_tag = prev; }
+};
+
 // Every kernel launch of this library goes through LAUNCH so b200rec_launch_count is honest.
 #define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
   do {                                                                      \
+    ::b200rec::Prof* _prof = ::b200rec::tl_prof;                            \
+    if (_prof) _prof->begin(#kernel, (stream));                             \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
+    if (_prof) _prof->end((stream));                                        \
     ::b200rec::g_launches.fetch_add(1, std::memory_order_relaxed);          \
   } while (0)
 

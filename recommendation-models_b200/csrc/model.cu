@@ -250,6 +250,9 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   const float* mats = a.mats;
 
   // ---- sparse forward: (gather) + first-order + second-order -----------------------------------
+  struct PhaseScope { const char* prev = tl_tag; ~PhaseScope() { tl_tag = prev; } } phase_scope;
+  auto phase = [](const char* name) { tl_tag = name; };
+  phase("gather_fm_fwd");
   const float* Xp = a.emb;
   if (a.table_emb) {
     SparseFwd s;
@@ -289,6 +292,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   }
 
   // ---- dense branch forward ---------------------------------------------------------------------
+  phase("dense_fwd");
   Head h;
   h.B = B;
   h.br[h.n_br++] = first.as<float>();
@@ -338,6 +342,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   }
 
   // ---- head ---------------------------------------------------------------------------------------
+  phase("head");
   h.bias = a.bias;
   h.targets = a.targets;
   h.preds = a.preds ? a.preds : preds.as<float>();
@@ -348,6 +353,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   if (!train) return B200REC_OK;
 
   // ---- dense branch backward ----------------------------------------------------------------------
+  phase("dense_bwd");
   const float* dlg = dlogit.as<float>();
   float* gm = a.gmats_out;
   float* dxd = nullptr;  // dense-branch gradient w.r.t. the embedding input
@@ -417,6 +423,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   }
 
   // ---- per-nnz gradients (GradUtil.scala:7-42) ------------------------------------------------------
+  phase("emb_grad");
   SparseBwd sb;
   sb.B = B; sb.F = has_emb ? F : (int)(B ? nnz / B : 0); sb.K = has_emb ? K : 0;
   sb.X = Xp; sb.S = second_order ? S.as<float>() : nullptr; sb.dX = dxd; sb.dlogit = dlg;

@@ -75,6 +75,7 @@ __global__ void seg_heads_kernel(long long n, const unsigned* keys, const int* s
 }
 
 int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
+  ProfTag tag("scatter_sort");
   B200_TRY(ws.reserve(a.n));
   int* counters = ws.counters.as<int>();
   if (a.n <= 0) {
@@ -88,14 +89,18 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
   B200_LAUNCH(iota_kernel, cdiv(n, 256), 256, 0, st, (long long)n, vals_in, counters);
   size_t tmp = ws.cub_tmp.cap;
   int bits = a.key_bits < 1 ? 1 : (a.key_bits > 32 ? 32 : a.key_bits);
+  if (tl_prof) tl_prof->begin("cub::DeviceRadixSort::SortPairs", st);
   B200_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp.p, tmp, (const unsigned*)a.feats,
                                             keys_sorted, vals_in, perm, n, 0, bits, st));
+  if (tl_prof) tl_prof->end(st);
   g_launches.fetch_add(2 + (bits + 7) / 8, std::memory_order_relaxed);  // cub's own kernels
   // head flags -> inclusive scan -> segment table.  vals_a (the iota) is free again: reuse it.
   int* seg_idx = ws.vals_a.as<int>();
   B200_LAUNCH(head_flag_kernel, cdiv(n, 256), 256, 0, st, (long long)n, keys_sorted, seg_idx);
   tmp = ws.cub_tmp.cap;
+  if (tl_prof) tl_prof->begin("cub::DeviceScan::InclusiveSum", st);
   B200_CUDA(cub::DeviceScan::InclusiveSum(ws.cub_tmp.p, tmp, seg_idx, seg_idx, n, st));
+  if (tl_prof) tl_prof->end(st);
   g_launches.fetch_add(2, std::memory_order_relaxed);
   B200_LAUNCH(seg_heads_kernel, cdiv(n, 256), 256, 0, st, (long long)n, keys_sorted, seg_idx,
               ws.seg_start.as<int>(), a.unique, a.n_unique);
@@ -253,6 +258,7 @@ static int launch_segsum(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) 
 }
 
 int segsum_reduce(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
+  ProfTag tag("scatter_add");
   if (a.n <= 0) return B200REC_OK;
   int lpr = 0;
   if (a.K % 4 == 0) {
