@@ -94,6 +94,8 @@ int b200rec_model_stream(b200rec_model_t m, void** stream);
  *   0 = fp32 FFMA (SIMT), 1 = 3xTF32 error-compensated tcgen05 (fp32-class accuracy, default where a
  *   tensor-core kernel exists), 2 = single-pass TF32 tcgen05 (about 1e-3 relative; NOT parity grade). */
 int b200rec_model_set_gemm_mode(b200rec_model_t m, int mode);
+/* Process-wide default (new model handles and the stand-alone Linear module calls use it). */
+int b200rec_set_default_gemm_mode(int mode);
 /* Wait for the handle's streams and report a deferred index / id error of a *_dev call. */
 int b200rec_model_sync(b200rec_model_t m);
 

@@ -547,6 +547,7 @@ class Model:
             ctx["end"] = end
             branches.append(out)
         p = head_forward(branches, b)
+        self.last_ctx = ctx
         if targets is None:
             return p.reshape(-1).astype(dt)
         loss, dlogit, dbias = head_backward(p, self._cast(targets))
@@ -568,6 +569,26 @@ class Model:
             ge = product_bwd(gh, ctx["prod"], gm, batch_size, f, k, self.fc[0]).reshape(-1)
         return loss, gw, dbias, ge, gm
 
+    def relu_preactivations(self, batch_size):
+        """Pre-activations of every ReLU of the last forward, one [B, units] array per layer.
+        Tests use them to keep inputs away from the ReLU kinks, where ANY two fp32 implementations
+        (MKL vs OpenBLAS vs this GPU path) may legitimately disagree about the sign."""
+        ctx, out = self.last_ctx, []
+        def mlp(saved):
+            for (_, _, y, is_head) in saved:
+                if not is_head:
+                    out.append(y.reshape(batch_size, -1))
+        if "mlp" in ctx:
+            mlp(ctx["mlp"])
+        if "cin" in ctx:
+            mlp(ctx["cin"]["dnn_saved"])
+            out.extend(y.reshape(batch_size, -1) for y in ctx["cin"]["ys"])
+        if "cross" in ctx:
+            mlp(ctx["cross"]["dnn_saved"])
+        if "prod" in ctx:
+            out.append(ctx["prod"]["pre"].reshape(batch_size, -1))
+        return out
+
     def forward(self, batch_size, index, weights, bias, embedding=None, mats=None):
         """-> float[B] sigmoid(logit)   (e.g. DeepFM.scala:54-81)."""
         return self._run(batch_size, index, weights, bias, embedding, mats, None)
@@ -583,6 +604,35 @@ class Model:
         if gm is not None:
             mats[...] = gm
         return float(loss)
+
+
+def away_from_kinks(model64, B, F, K, index, w, bias, emb, mats, margin=2e-4, keep=None):
+    """Select `keep` of the B candidate samples whose ReLU pre-activations (fp64 oracle) all stay at
+    least `margin` (relative to the layer's largest pre-activation) away from zero.
+
+    ReLU is discontinuous in its derivative: a pre-activation within rounding distance of zero can
+    come out on either side in two correct fp32 implementations (the reference's MKL sgemm and the
+    oracle's OpenBLAS already differ there), and one flipped unit changes a weight-gradient row by
+    O(1/sqrt(B)) -- far above any arithmetic tolerance.  Parity of the ARITHMETIC is therefore
+    tested on inputs that avoid the kinks; samples are independent, so dropping some is harmless.
+    Returns (index, w, emb, sample_ids) for the kept samples."""
+    keep = keep or B
+    c64 = lambda a: None if a is None else np.asarray(a, np.float64)
+    model64.forward(B, index, c64(w), c64(bias), c64(emb), c64(mats))
+    pre = model64.relu_preactivations(B)
+    if not pre:
+        ids = np.arange(keep)
+    else:
+        m = np.full(B, np.inf)
+        for z in pre:
+            m = np.minimum(m, np.abs(z).min(axis=1) / np.abs(z).max())
+        order = np.argsort(-m)
+        ids = np.sort(order[:keep])
+        assert m[ids].min() >= margin, f"only {(m >= margin).sum()} of {B} candidates clear the margin; need {keep}"
+    w2 = w.reshape(B, F)[ids].reshape(-1)
+    e2 = None if emb is None else emb.reshape(B, F * K)[ids].reshape(-1)
+    idx2 = np.repeat(np.arange(keep, dtype=np.int32), F)
+    return idx2, np.ascontiguousarray(w2), (None if e2 is None else np.ascontiguousarray(e2)), ids
 
 
 # ----------------------------------------------------------------------------

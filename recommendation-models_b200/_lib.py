@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200rec_model_mats_len": [vp, c_i64_p],
     "b200rec_model_stream": [vp, C.POINTER(vp)],
     "b200rec_model_set_gemm_mode": [vp, C.c_int],
+    "b200rec_set_default_gemm_mode": [C.c_int],
     "b200rec_model_sync": [vp],
     "b200rec_forward": [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp],
     "b200rec_backward": [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp, c_float_p],
@@ -162,3 +163,8 @@ def profile_end():
         tag, name, cnt, ms = line.split("|")
         rows.append((tag, name, int(cnt), float(ms)))
     return rows
+
+
+def set_default_gemm_mode(mode: int):
+    """0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (default), 2 = 1xTF32 tcgen05 (not parity grade)."""
+    check(lib().b200rec_set_default_gemm_mode(int(mode)))

@@ -27,6 +27,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int g_default_gemm_mode = 1;  // 3xTF32 tcgen05 wherever a tensor-core kernel exists
 thread_local Prof* tl_prof = nullptr;
 thread_local const char* tl_tag = nullptr;
 
@@ -244,6 +245,12 @@ int b200rec_model_mats_len(b200rec_model_t m, int64_t* len) {
 int b200rec_model_stream(b200rec_model_t m, void** stream) {
   B200_REQUIRE(m && stream, B200REC_ERR_ARG, "NULL argument");
   *stream = (void*)m->stream;
+  return B200REC_OK;
+}
+
+int b200rec_set_default_gemm_mode(int mode) {
+  B200_REQUIRE(mode >= 0 && mode <= 2, B200REC_ERR_ARG, "gemm mode must be 0 (fp32 SIMT), 1 (3xTF32 tcgen05) or 2 (1xTF32)");
+  g_default_gemm_mode = mode;
   return B200REC_OK;
 }
 
@@ -1081,7 +1088,7 @@ int b200rec_linear_update_output(int device, int batch_size, int in_dim, int out
   if (bias) B200_TRY(upload(d_b, bias, (size_t)out_dim * sizeof(float), c.st));
   B200_TRY(d_y.reserve((size_t)batch_size * out_dim * sizeof(float)));
   B200_TRY(linear_fwd(batch_size, out_dim, in_dim, d_x.as<float>(), d_w.as<float>(),
-                      bias ? d_b.as<float>() : nullptr, relu != 0, d_y.as<float>(), c.st));
+                      bias ? d_b.as<float>() : nullptr, relu != 0, d_y.as<float>(), c.st, g_default_gemm_mode));
   B200_TRY(download(y, d_y.p, (size_t)batch_size * out_dim * sizeof(float), c.st));
   return c.finish(batch_size);
   B200_GUARD_END
@@ -1101,7 +1108,7 @@ int b200rec_linear_update_grad_input(int device, int batch_size, int in_dim, int
   B200_TRY(upload(d_w, w, (size_t)out_dim * in_dim * sizeof(float), c.st));
   B200_TRY(d_x.reserve((size_t)batch_size * in_dim * sizeof(float)));
   B200_TRY(linear_bwd_input(batch_size, out_dim, in_dim, d_g.as<float>(), d_w.as<float>(), nullptr,
-                            d_x.as<float>(), false, c.st));
+                            d_x.as<float>(), false, c.st, g_default_gemm_mode));
   B200_TRY(download(gx, d_x.p, (size_t)batch_size * in_dim * sizeof(float), c.st));
   return c.finish(batch_size);
   B200_GUARD_END
@@ -1124,7 +1131,7 @@ int b200rec_linear_acc_grad_parameters(int device, int batch_size, int in_dim, i
   if (grad_b) B200_TRY(upload(d_gb, grad_b, (size_t)out_dim * sizeof(float), c.st));
   B200_TRY(linear_bwd_params(batch_size, out_dim, in_dim, d_x.as<float>(), d_g.as<float>(), scale,
                              true, d_gw.as<float>(), grad_b ? d_gb.as<float>() : nullptr, scratch,
-                             c.st));
+                             c.st, g_default_gemm_mode));
   B200_TRY(download(grad_w, d_gw.p, (size_t)out_dim * in_dim * sizeof(float), c.st));
   if (grad_b) B200_TRY(download(grad_b, d_gb.p, (size_t)out_dim * sizeof(float), c.st));
   return c.finish(batch_size);

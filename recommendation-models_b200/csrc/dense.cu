@@ -33,7 +33,8 @@ int splitk_reduce(const float* ws, int splits, long long MN, float scale, bool a
 }
 
 int linear_fwd(int M, int N, int K, const float* x, const float* w, const float* b, bool relu,
-               float* y, cudaStream_t st) {
+               float* y, cudaStream_t st, int mode) {
+  if (N > 1 && mode) return tc_linear_fwd(M, N, K, x, w, b, relu, y, mode == 1 ? 3 : 1, st);
   if (N == 1) {  // Linear(K -> 1): a row dot product
     B200_TRY(gemv_rows(M, K, x, K, w, b, false, y, st));
     if (relu) return add_bias_relu(M, y, nullptr, y, st);
@@ -43,7 +44,8 @@ int linear_fwd(int M, int N, int K, const float* x, const float* w, const float*
 }
 
 int linear_bwd_input(int M, int N, int K, const float* gy, const float* w, const float* mask,
-                     float* gx, bool accumulate, cudaStream_t st) {
+                     float* gx, bool accumulate, cudaStream_t st, int mode) {
+  if (mode) return tc_linear_bwd_input(M, N, K, gy, w, mask, gx, accumulate, mode == 1 ? 3 : 1, st);
   // gx[M,K] = gy[M,N] W[N,K]: contraction over N
   return gemm_simt(M, K, N, 1, RowMajorOp{gy, N}, ColMajorOp{w, K},
                    EpMaskAcc{gx, K, mask, K, accumulate}, st);
@@ -80,7 +82,10 @@ int colsum(int M, int N, const float* g, float scale, bool accumulate, float* ou
 }
 
 int linear_bwd_params(int M, int N, int K, const float* x, const float* gy, float scale,
-                      bool accumulate, float* gw, float* gb, DevBuf& scratch, cudaStream_t st) {
+                      bool accumulate, float* gw, float* gb, DevBuf& scratch, cudaStream_t st,
+                      int mode) {
+  if (mode)
+    return tc_linear_bwd_params(M, N, K, x, gy, scale, accumulate, gw, gb, scratch, mode == 1 ? 3 : 1, st);
   // gw[N,K] = gy^T x : output N x K, contraction over the batch M
   const int splits = pick_splits(N, K, M);
   const long long MN = (long long)N * K;
@@ -231,7 +236,8 @@ int axpy(long long n, const float* x, float* y, cudaStream_t st) {
 }
 
 int pnn_lp_fwd(int B, int P, int O, const float* ip, const float* wp, const float* prev,
-               const float* c0, float* h, cudaStream_t st) {
+               const float* c0, float* h, cudaStream_t st, int mode) {
+  if (mode) return tc_pnn_lp_fwd(B, P, O, ip, wp, prev, c0, h, mode == 1 ? 3 : 1, st);
   // ProductEncoder.scala:97-108: CAddTable(lz, lp) -> CAdd(scalar) -> ReLU
   return gemm_simt(B, O, P, 1, RowMajorOp{ip, P}, RowMajorOp{wp, P}, EpAddBiasRelu2{h, O, prev, c0},
                    st);

@@ -81,14 +81,16 @@ int apply_sgd(int K, long long cap, const int* n_unique, const int* unique, cons
 
 // ---------------------------------------------------------------- dense.cu (SIMT fp32) --------
 // y[M,N] = act(x[M,K] W[N,K]^T + b[N])   (BigDL Linear + optional ReLU)
+// mode: 0 = fp32 FFMA (SIMT), 1 = 3xTF32 tcgen05, 2 = 1xTF32 tcgen05
 int linear_fwd(int M, int N, int K, const float* x, const float* w, const float* b, bool relu,
-               float* y, cudaStream_t st);
+               float* y, cudaStream_t st, int mode = 0);
 // gx[M,K] = (gy[M,N] W[N,K]) (* (mask[M,K] > 0) if mask)
 int linear_bwd_input(int M, int N, int K, const float* gy, const float* w, const float* mask,
-                     float* gx, bool accumulate, cudaStream_t st);
+                     float* gx, bool accumulate, cudaStream_t st, int mode = 0);
 // gw[N,K] (+)= scale * gy[M,N]^T x[M,K] ; gb[N] (+)= scale * colsum(gy)   (split-K, fixed order)
 int linear_bwd_params(int M, int N, int K, const float* x, const float* gy, float scale,
-                      bool accumulate, float* gw, float* gb, DevBuf& scratch, cudaStream_t st);
+                      bool accumulate, float* gw, float* gb, DevBuf& scratch, cudaStream_t st,
+                      int mode = 0);
 // out[M] = x[M,K] . w[K] (+ b0)      (Linear(K -> 1))
 int gemv_rows(int M, int K, const float* x, int ldx, const float* w, const float* b0,
               bool accumulate, float* out, cudaStream_t st);
@@ -130,7 +132,7 @@ int cin_transpose_out(int B, int F, int K, const float* gx0, float* gE, bool acc
                       cudaStream_t st);
 // x_out[r,c] = relu( sum_{i,j} x0[r,i] x_in[r,j] W[c,i*H+j] + b[c] )
 int cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
-                  const float* b, float* x_out, cudaStream_t st);
+                  const float* b, float* x_out, cudaStream_t st, int mode = 0);
 // pooled[b, col0 + c] = sum_k x[(b,k), c]
 int cin_pool(int B, int K, int C, const float* x, float* pooled, int ld, int col0, cudaStream_t st);
 // gy[r,c] = (gp[b, col0+c] + (g_next? g_next[r,c] : 0)) * (x_out[r,c] > 0)
@@ -139,7 +141,7 @@ int cin_gy(int B, int K, int C, const float* gp, int ld, int col0, const float* 
 // layer backward: gW[c, i*H+j] = sum_r gy Z ; gb ; gx_in[r,j] ; gx0[r,i] +=
 int cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
                   const float* gy, float* gW, float* gb, float* gx_in, float* gx0,
-                  DevBuf& scratch, cudaStream_t st);
+                  DevBuf& scratch, cudaStream_t st, int mode = 0);
 
 // ---------------------------------------------------------------- cross.cu (DCN) ---------------
 // forward: xL[B,D], s[L,B]
@@ -155,7 +157,7 @@ int cross_bwd(int B, int D, int L, const float* X, const float* w, const float* 
 int pnn_ip_fwd(int B, int F, int K, const float* X, float* ip, cudaStream_t st);
 // h = relu(prev + x W^T + c0)   (second product GEMM of the PNN layer)
 int pnn_lp_fwd(int B, int P, int O, const float* ip, const float* wp, const float* prev,
-               const float* c0, float* h, cudaStream_t st);
+               const float* c0, float* h, cudaStream_t st, int mode = 0);
 // dX[b,i,:] (+)= sum_{j != i} gip[b,pair(i,j)] v_j   (j ascending = reference order)
 int pnn_ip_bwd(int B, int F, int K, const float* X, const float* gip, float* dX, bool accumulate,
                cudaStream_t st);
@@ -164,6 +166,25 @@ int add_bias_relu(long long n, const float* a, const float* c0, float* h, cudaSt
 int relu_mask(long long n, const float* g, const float* h, float* out, cudaStream_t st);
 // y += x
 int axpy(long long n, const float* x, float* y, cudaStream_t st);
+
+// ---------------------------------------------------------------- tc_gemm.cu (tcgen05) --------
+// passes: 3 = error-compensated 3xTF32 (fp32-class accuracy), 1 = plain TF32
+int tc_linear_fwd(int M, int N, int K, const float* x, const float* w, const float* b, bool relu,
+                  float* y, int passes, cudaStream_t st);
+int tc_pnn_lp_fwd(int B, int P, int O, const float* ip, const float* wp, const float* prev,
+                  const float* c0, float* h, int passes, cudaStream_t st);
+int tc_linear_bwd_input(int M, int N, int K, const float* gy, const float* w, const float* mask,
+                        float* gx, bool accumulate, int passes, cudaStream_t st);
+int tc_linear_bwd_params(int M, int N, int K, const float* x, const float* gy, float scale,
+                         bool accumulate, float* gw, float* gb, DevBuf& scratch, int passes,
+                         cudaStream_t st);
+bool tc_cin_supported(int F, int H, int C);
+int tc_cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
+                     const float* b, float* x_out, int passes, cudaStream_t st);
+int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
+                     const float* gy, float* gW, float* gb, float* gx_in, float* gx0, bool gx_in_acc,
+                     DevBuf& scratch, int passes, cudaStream_t st);
+extern int g_default_gemm_mode;
 
 // ---------------------------------------------------------------- table.cu ---------------------
 int table_init_uniform(float* table, float* wtable, long long rows, int K, uint64_t seed, float lo,

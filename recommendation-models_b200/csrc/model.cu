@@ -72,6 +72,7 @@ using namespace b200rec;
 
 int b200rec_model_s::init(int kind_, int F_, int K_, const int* fc_, int n_fc, const int* cin_, int n_cin,
                 int depth_, int device_) {
+  gemm_mode = g_default_gemm_mode;
   kind = kind_; F = F_; K = K_; D = F_ * K_; depth = depth_; device = device_;
   fc.assign(fc_, fc_ + n_fc);
   cin.assign(cin_, cin_ + n_cin);
@@ -184,7 +185,7 @@ int b200rec_model_s::mlp_forward(int B, const float* x_in, const float* mats, co
   int in = mlp.in_dim;
   for (size_t l = 0; l < mlp.dims.size(); ++l) {
     float* y = acts[l].as<float>();
-    B200_TRY(linear_fwd(B, mlp.dims[l], in, h, mats + mlp.w_off[l], mats + mlp.b_off[l], true, y, st));
+    B200_TRY(linear_fwd(B, mlp.dims[l], in, h, mats + mlp.w_off[l], mats + mlp.b_off[l], true, y, st, gemm_mode));
     h = y;
     in = mlp.dims[l];
   }
@@ -207,12 +208,12 @@ int b200rec_model_s::mlp_backward(int B, const float* x_in, const float* mats, f
     const int out = mlp.dims[l];
     const int in = l == 0 ? mlp.in_dim : mlp.dims[l - 1];
     const float* xp = l == 0 ? x_in : acts[l - 1].as<float>();
-    B200_TRY(linear_bwd_params(B, out, in, xp, g, 1.0f, false, gm + mlp.w_off[l], gm + mlp.b_off[l], scratch, st));
+    B200_TRY(linear_bwd_params(B, out, in, xp, g, 1.0f, false, gm + mlp.w_off[l], gm + mlp.b_off[l], scratch, st, gemm_mode));
     if (l > 0) {
-      B200_TRY(linear_bwd_input(B, out, in, g, mats + mlp.w_off[l], acts[l - 1].as<float>(), g2, false, st));
+      B200_TRY(linear_bwd_input(B, out, in, g, mats + mlp.w_off[l], acts[l - 1].as<float>(), g2, false, st, gemm_mode));
       float* t = g; g = g2; g2 = t;
     } else if (dx) {
-      B200_TRY(linear_bwd_input(B, out, in, g, mats + mlp.w_off[l], in_mask, dx, false, st));
+      B200_TRY(linear_bwd_input(B, out, in, g, mats + mlp.w_off[l], in_mask, dx, false, st, gemm_mode));
     }
   }
   return B200REC_OK;
@@ -311,7 +312,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
     const float* xin = x0.as<float>();
     int hdim = F, col = 0;
     for (size_t l = 0; l < cin.size(); ++l) {
-      B200_TRY(cin_layer_fwd(R, F, hdim, cin[l], x0.as<float>(), xin, mats + cin_w[l], mats + cin_b[l], xl[l].as<float>(), st));
+      B200_TRY(cin_layer_fwd(R, F, hdim, cin[l], x0.as<float>(), xin, mats + cin_w[l], mats + cin_b[l], xl[l].as<float>(), st, gemm_mode));
       B200_TRY(cin_pool(B, K, cin[l], xl[l].as<float>(), pooled.as<float>(), csum, col, st));
       xin = xl[l].as<float>();
       hdim = cin[l];
@@ -334,9 +335,9 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
     const float* wz = mats;
     const float* wp = mats + (long long)D * O;
     const float* c0 = wp + (long long)P * O;
-    B200_TRY(linear_fwd(B, O, D, Xp, wz, nullptr, false, pre.as<float>(), st));
+    B200_TRY(linear_fwd(B, O, D, Xp, wz, nullptr, false, pre.as<float>(), st, gemm_mode));
     B200_TRY(pnn_ip_fwd(B, F, K, Xp, ip.as<float>(), st));
-    B200_TRY(pnn_lp_fwd(B, P, O, ip.as<float>(), wp, pre.as<float>(), c0, hbuf.as<float>(), st));
+    B200_TRY(pnn_lp_fwd(B, P, O, ip.as<float>(), wp, pre.as<float>(), c0, hbuf.as<float>(), st, gemm_mode));
     B200_TRY(mlp_forward(B, hbuf.as<float>(), mats, &last, br, st));
     h.br[h.n_br++] = br;
   }
@@ -383,7 +384,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
       col -= C;
       B200_TRY(cin_gy(B, K, C, gpooled.as<float>(), csum, col, g_next, xl[l].as<float>(), gy.as<float>(), st));
       B200_TRY(cin_layer_bwd(R, F, hdim, C, x0.as<float>(), xin, mats + cin_w[l], gy.as<float>(),
-                             gm + cin_w[l], gm + cin_b[l], gn_cur, gx0.as<float>(), scratch, st));
+                             gm + cin_w[l], gm + cin_b[l], gn_cur, gx0.as<float>(), scratch, st, gemm_mode));
       g_next = gn_cur;
       float* t = gn_cur; gn_cur = gn_other; gn_other = t;
     }
@@ -415,10 +416,10 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
     }
     // ProductEncoder.backward :43-70
     B200_TRY(reduce_sum((long long)B * O, gh, 1.0f, gm + (long long)D * O + (long long)P * O, scratch, st));
-    B200_TRY(linear_bwd_params(B, O, D, Xp, gh, 1.0f, false, gm, nullptr, scratch, st));
-    B200_TRY(linear_bwd_params(B, O, P, ip.as<float>(), gh, 1.0f, false, gm + (long long)D * O, nullptr, scratch, st));
-    B200_TRY(linear_bwd_input(B, O, D, gh, wz, nullptr, dxd, false, st));
-    B200_TRY(linear_bwd_input(B, O, P, gh, wp, nullptr, gip.as<float>(), false, st));
+    B200_TRY(linear_bwd_params(B, O, D, Xp, gh, 1.0f, false, gm, nullptr, scratch, st, gemm_mode));
+    B200_TRY(linear_bwd_params(B, O, P, ip.as<float>(), gh, 1.0f, false, gm + (long long)D * O, nullptr, scratch, st, gemm_mode));
+    B200_TRY(linear_bwd_input(B, O, D, gh, wz, nullptr, dxd, false, st, gemm_mode));
+    B200_TRY(linear_bwd_input(B, O, P, gh, wp, nullptr, gip.as<float>(), false, st, gemm_mode));
     B200_TRY(pnn_ip_bwd(B, F, K, Xp, gip.as<float>(), dxd, true, st));
   }
 

@@ -1,0 +1,170 @@
+// Host-side launchers of the tcgen05 GEMM (tc_gemm.cuh) for the shapes of the path:
+//   BigDL Linear forward / gradInput / accGradParameters (rec/util/LayerUtil.scala:7-24,
+//   rec/model/encoder/HigherOrderEncoder.scala:34-58) and the CIN layer forward / backward
+//   (rec/model/xdeepfm/CINEncoder.scala:60-103,150-157).
+#include "tc_gemm.cuh"
+#include "gemm_simt.cuh"
+#include "kernels.h"
+
+namespace b200rec {
+namespace tc {
+
+// K-blocks per TMEM accumulation chunk in the parity-grade mode (4 x 32 = 128 of K)
+static constexpr int KC_PRECISE = 4;
+static int round16(int n) { return (n + 15) / 16 * 16; }
+// widest tile <= 256 that splits N evenly
+static int pick_bn(int N) {
+  const int tiles = (N + MAX_BN - 1) / MAX_BN;
+  int bn = round16((N + tiles - 1) / tiles);
+  return bn < 16 ? 16 : bn;
+}
+
+template <class AP, class BP, class Sched, class Ep>
+static int launch(int M, int N, int bn, int n_stride, int n_valid, int n_tiles, int splits, Sched sched,
+                  AP ap, BP bp, Ep ep, int passes, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return B200REC_OK;
+  dim3 grid(n_tiles, cdiv(M, BM), splits);
+  const int kc = passes == 3 ? KC_PRECISE : 0;
+  if (passes == 3) {
+    auto k = gemm_tc_kernel<AP, BP, Sched, Ep, 3>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_done = true;
+    }
+    B200_LAUNCH(k, grid, THREADS, SMEM_BYTES, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, ep);
+  } else {
+    auto k = gemm_tc_kernel<AP, BP, Sched, Ep, 1>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_done = true;
+    }
+    B200_LAUNCH(k, grid, THREADS, SMEM_BYTES, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, ep);
+  }
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace tc
+
+using namespace tc;
+
+// y[M,N] = act(x[M,K] W[N,K]^T + b)
+int tc_linear_fwd(int M, int N, int K, const float* x, const float* w, const float* b, bool relu,
+                  float* y, int passes, cudaStream_t st) {
+  const int bn = pick_bn(N);
+  KPlain s{0, K, K};
+  RowProd<4, KPlain> ap{x, K, M, BM, (K % 4 == 0) && aligned16(x)};
+  RowProd<8, KPlain> bp{w, K, N, bn, (K % 4 == 0) && aligned16(w)};
+  return launch(M, N, bn, bn, bn, cdiv(N, bn), 1, s, ap, bp, tc::EpBiasAct{y, N, b, relu}, passes, st);
+}
+
+// PNN product layer: h = relu(prev + ip Wp^T + c0)
+int tc_pnn_lp_fwd(int B, int P, int O, const float* ip, const float* wp, const float* prev,
+                  const float* c0, float* h, int passes, cudaStream_t st) {
+  const int bn = pick_bn(O);
+  KPlain s{0, P, P};
+  RowProd<4, KPlain> ap{ip, P, B, BM, (P % 4 == 0) && aligned16(ip)};
+  RowProd<8, KPlain> bp{wp, P, O, bn, (P % 4 == 0) && aligned16(wp)};
+  return launch(B, O, bn, bn, bn, cdiv(O, bn), 1, s, ap, bp, tc::EpAddBiasRelu2{h, O, prev, c0}, passes, st);
+}
+
+// gx[M,K] = (gy[M,N] W[N,K]) (* mask > 0) (+ gx)
+int tc_linear_bwd_input(int M, int N, int K, const float* gy, const float* w, const float* mask,
+                        float* gx, bool accumulate, int passes, cudaStream_t st) {
+  const int bn = pick_bn(K);
+  KPlain s{0, N, N};
+  RowProd<4, KPlain> ap{gy, N, M, BM, (N % 4 == 0) && aligned16(gy)};
+  ColProd<256, KPlain> bp{w, K, K, bn};   // B(k_out, n) = W[n*K + k_out]
+  return launch(M, K, bn, bn, bn, cdiv(K, bn), 1, s, ap, bp, tc::EpMaskAcc{gx, K, mask, K, accumulate},
+                passes, st);
+}
+
+// gw[N,K] (+)= scale * gy[M,N]^T x[M,K]  (split-K over the batch, fixed-order reduce) ; gb likewise
+int tc_linear_bwd_params(int M, int N, int K, const float* x, const float* gy, float scale,
+                         bool accumulate, float* gw, float* gb, DevBuf& scratch, int passes,
+                         cudaStream_t st) {
+  const int bn = pick_bn(K);
+  const int tiles = cdiv(N, BM) * cdiv(K, bn);
+  int splits = (148 + tiles - 1) / tiles;
+  const int max_s = M / 256 > 0 ? M / 256 : 1;
+  if (splits > max_s) splits = max_s;
+  if (splits < 1) splits = 1;
+  int k_chunk = ((cdiv(M, splits) + BK - 1) / BK) * BK;
+  splits = cdiv(M, k_chunk);
+  const long long MN = (long long)N * K;
+  B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)64 * N) * sizeof(float)));
+  float* ws = scratch.as<float>();
+  KPlain s{0, M, k_chunk};
+  ColProd<128, KPlain> ap{gy, N, N, BM};  // A(n, m) = gy[m*N + n]
+  ColProd<256, KPlain> bp{x, K, K, bn};   // B(k, m) = x[m*K + k]
+  B200_TRY(launch(N, K, bn, bn, bn, cdiv(K, bn), splits, s, ap, bp, tc::EpPartial{ws, MN, K}, passes, st));
+  B200_TRY(splitk_reduce(ws, splits, MN, scale, accumulate, gw, st));
+  if (gb) B200_TRY(colsum(M, N, gy, scale, accumulate, gb, ws + (size_t)splits * MN, st));
+  return B200REC_OK;
+}
+
+// ---- CIN --------------------------------------------------------------------------------------------
+bool tc_cin_supported(int F, int H, int C) {
+  return F <= CinZProd::MAX_F && H <= MAX_BN && C >= 1;
+}
+
+// x_out[r,c] = relu(sum_{i,j} x0[r,i] x_in[r,j] W[c, i*H+j] + b[c])
+int tc_cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
+                     const float* b, float* x_out, int passes, cudaStream_t st) {
+  const int bn = pick_bn(C);
+  KCin s{F, H, 0};
+  CinZProd ap{x0, x_in, R, (H % 4 == 0) && aligned16(x_in)};
+  RowProd<8, KCin> bp{W, (long long)F * H, C, bn, (H % 4 == 0) && aligned16(W)};
+  return launch(R, C, bn, bn, bn, cdiv(C, bn), 1, s, ap, bp, tc::EpBiasAct{x_out, C, b, true}, passes, st);
+}
+
+// layer backward (gy already ReLU-masked):
+//   gW[c, (i,j)] = sum_r gy[r,c] x0[r,i] x_in[r,j]          (split-K over r, fixed-order reduce)
+//   gx0[r,i]    += sum_j (gy W)[r,(i,j)] x_in[r,j]           (one N tile per field, row-dot epilogue)
+//   gx_in[r,j]   = sum_{i,c} x0[r,i] gy[r,c] W[c, i*H+j]     (the forward kernel with (x0 (x) gy) as A)
+int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
+                     const float* gy, float* gW, float* gb, float* gx_in, float* gx0, bool gx_in_acc,
+                     DevBuf& scratch, int passes, cudaStream_t st) {
+  const int FH = F * H;
+  {  // ---- gW^T tile: out(m = (i,j), n = c), contraction over r
+    const int bn = pick_bn(C);
+    const int tiles = cdiv(FH, BM) * cdiv(C, bn);
+    int splits = (2 * 148 + tiles - 1) / tiles;
+    const int max_s = R / 512 > 0 ? R / 512 : 1;
+    if (splits > max_s) splits = max_s;
+    if (splits < 1) splits = 1;
+    int k_chunk = ((cdiv(R, splits) + BK - 1) / BK) * BK;
+    splits = cdiv(R, k_chunk);
+    const long long MN = (long long)C * FH;
+    B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)64 * C) * sizeof(float)));
+    float* ws = scratch.as<float>();
+    KPlain s{0, R, k_chunk};
+    CinZtProd ap{x0, x_in, F, H};
+    ColProd<256, KPlain> bp{gy, C, C, bn};   // B(c, r) = gy[r*C + c]
+    B200_TRY(launch(FH, C, bn, bn, bn, cdiv(C, bn), splits, s, ap, bp, tc::EpPartialT{ws, MN, FH}, passes, st));
+    B200_TRY(splitk_reduce(ws, splits, MN, 1.0f, false, gW, st));
+    B200_TRY(colsum(R, C, gy, 1.0f, false, gb, ws + (size_t)splits * MN, st));
+  }
+  {  // ---- gx0: per field i, T_i[r, j] = sum_c gy[r,c] W[c, i*H + j];  gx0[r,i] += <T_i[r,:], x_in[r,:]>
+    const int bn = round16(H);
+    KPlain s{0, C, C};
+    RowProd<4, KPlain> ap{gy, C, R, BM, (C % 4 == 0) && aligned16(gy)};
+    ColProd<256, KPlain> bp{W, FH, FH, bn};   // B(n = i*H + j, c) = W[c*FH + n]
+    B200_TRY(launch(R, FH, bn, H, H, F, 1, s, ap, bp, tc::EpRowDot{x_in, H, gx0, F}, passes, st));
+  }
+  {  // ---- gx_in[r, j] = sum_{(i,c)} (x0[r,i] gy[r,c]) W[c, i*H + j]
+    const int bn = pick_bn(H);
+    KCin s{F, C, H};
+    CinZProd ap{x0, gy, R, (C % 4 == 0) && aligned16(gy)};
+    ColProd<256, KCin> bp{W, FH, H, bn};      // B(j, (i,c)) = W[c*FH + i*H + j]; tile rows bounded by H
+    B200_TRY(launch(R, H, bn, bn, bn, cdiv(H, bn), 1, s, ap, bp, tc::EpMaskAcc{gx_in, H, nullptr, 0, gx_in_acc},
+                    passes, st));
+  }
+  return B200REC_OK;
+}
+
+}  // namespace b200rec

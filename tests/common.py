@@ -55,7 +55,7 @@ def pkg_model(pkg, name, F, K):
                           cfg.get("cross_depth", 0))
 
 
-def assert_close(got, want, rtol=1e-5, what="", ref64=None):
+def assert_close(got, want, rtol=1e-5, what="", ref64=None, atol=0.0):
     """|got - want| <= rtol * max|want| (+ the fp32 oracle's own distance to its fp64 twin when
     given: both sides are fp32 roundings of the same exact value, so the fp32 oracle is only
     known to that precision)."""
@@ -65,8 +65,11 @@ def assert_close(got, want, rtol=1e-5, what="", ref64=None):
     if got.size == 0:
         return
     scale = np.abs(want).max()
-    tol = rtol * scale
+    tol = rtol * scale + atol
     if ref64 is not None:
         tol += 2.0 * np.abs(want - np.asarray(ref64, np.float64)).max()
     err = np.abs(got - want).max()
     assert err <= tol + 1e-30, f"{what}: max err {err:.3e} > tol {tol:.3e} (scale {scale:.3e})"
+
+
+away_from_kinks = refport.away_from_kinks

@@ -73,8 +73,11 @@ def test_second_order_encoder(gpu_pkg, B, F, K):
         enc.forward(e[:-1])
 
 
-@pytest.mark.parametrize("B,I,O", [(1, 1, 1), (37, 53, 29), (256, 624, 400), (130, 400, 1), (64, 7, 300)])
-def test_linear_module(gpu_pkg, B, I, O):
+@pytest.mark.parametrize("mode", [1, 0], ids=["tc3xtf32", "simt"])
+@pytest.mark.parametrize("B,I,O", [(1, 1, 1), (37, 53, 29), (256, 624, 400), (130, 400, 1), (64, 7, 300),
+                                   (1000, 741, 400), (300, 100, 257)])
+def test_linear_module(gpu_pkg, B, I, O, mode):
+    gpu_pkg._lib.set_default_gemm_mode(mode)
     rng = np.random.default_rng(I * O)
     x = rng.standard_normal((B, I)).astype(np.float32)
     w = (rng.standard_normal((O, I)) / np.sqrt(I)).astype(np.float32)
@@ -92,6 +95,24 @@ def test_linear_module(gpu_pkg, B, I, O):
     gw64 = 2 * (gy.astype(np.float64).T @ x.astype(np.float64))
     assert_close(lin.gradWeight, 2 * rgw, what="linear gW", ref64=gw64)
     assert_close(lin.gradBias, 2 * rgb, what="linear gb", ref64=2 * gy.astype(np.float64).sum(0))
+    gpu_pkg._lib.set_default_gemm_mode(1)
+
+
+def test_tf32_single_pass_is_not_parity_grade(gpu_pkg):
+    """Mode 2 (one TF32 pass) exists for comparison only: its error is ~1e-3, which is why the
+    parity path uses the 3xTF32 split."""
+    rng = np.random.default_rng(0)
+    B, I, O = 256, 512, 256
+    x = rng.standard_normal((B, I)).astype(np.float32)
+    w = (rng.standard_normal((O, I)) / np.sqrt(I)).astype(np.float32)
+    y64 = x.astype(np.float64) @ w.astype(np.float64).T
+    errs = {}
+    for mode in (1, 2):
+        gpu_pkg._lib.set_default_gemm_mode(mode)
+        y = gpu_pkg.Linear(I, O, False, w).updateOutput(x)
+        errs[mode] = np.abs(y - y64).max() / np.abs(y64).max()
+    gpu_pkg._lib.set_default_gemm_mode(1)
+    assert errs[1] < 3e-6 and 1e-4 < errs[2] < 1e-2, errs
 
 
 @pytest.mark.parametrize("rows,K,n", [(10, 16, 1), (1000, 16, 5000), (77, 8, 300), (50, 6, 100), (33, 64, 64),
