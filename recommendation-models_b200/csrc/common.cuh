@@ -67,6 +67,15 @@ struct ProfTag {  // names the phase the following launches belong to
     ::b200rec::g_launches.fetch_add(1, std::memory_order_relaxed);          \
   } while (0)
 
+#define B200_LAUNCH_NAMED(name, kernel, grid, block, smem, stream, ...)     \
+  do {                                                                      \
+    ::b200rec::Prof* _prof = ::b200rec::tl_prof;                            \
+    if (_prof) _prof->begin((name), (stream));                              \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
+    if (_prof) _prof->end((stream));                                        \
+    ::b200rec::g_launches.fetch_add(1, std::memory_order_relaxed);          \
+  } while (0)
+
 #define B200_CHECK_LAUNCH() B200_CUDA(cudaGetLastError())
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

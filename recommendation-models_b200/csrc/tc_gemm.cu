@@ -20,8 +20,8 @@ static int pick_bn(int N) {
 }
 
 template <class AP, class BP, class Sched, class Ep>
-static int launch(int M, int N, int bn, int n_stride, int n_valid, int n_tiles, int splits, Sched sched,
-                  AP ap, BP bp, Ep ep, int passes, cudaStream_t st) {
+static int launch(const char* name, int M, int N, int bn, int n_stride, int n_valid, int n_tiles, int splits,
+                  Sched sched, AP ap, BP bp, Ep ep, int passes, cudaStream_t st) {
   if (M <= 0 || N <= 0) return B200REC_OK;
   dim3 grid(n_tiles, cdiv(M, BM), splits);
   const int kc = passes == 3 ? KC_PRECISE : 0;
@@ -32,7 +32,7 @@ static int launch(int M, int N, int bn, int n_stride, int n_valid, int n_tiles, 
       B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       attr_done = true;
     }
-    B200_LAUNCH(k, grid, THREADS, SMEM_BYTES, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, ep);
+    B200_LAUNCH_NAMED(name, k, grid, THREADS, SMEM_BYTES, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, ep);
   } else {
     auto k = gemm_tc_kernel<AP, BP, Sched, Ep, 1>;
     static bool attr_done = false;
@@ -40,7 +40,7 @@ static int launch(int M, int N, int bn, int n_stride, int n_valid, int n_tiles, 
       B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       attr_done = true;
     }
-    B200_LAUNCH(k, grid, THREADS, SMEM_BYTES, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, ep);
+    B200_LAUNCH_NAMED(name, k, grid, THREADS, SMEM_BYTES, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, ep);
   }
   B200_CHECK_LAUNCH();
   return B200REC_OK;
@@ -59,7 +59,7 @@ int tc_linear_fwd(int M, int N, int K, const float* x, const float* w, const flo
   KPlain s{0, K, K};
   RowProd<4, KPlain> ap{x, K, M, BM, (K % 4 == 0) && aligned16(x)};
   RowProd<8, KPlain> bp{w, K, N, bn, (K % 4 == 0) && aligned16(w)};
-  return launch(M, N, bn, bn, bn, cdiv(N, bn), 1, s, ap, bp, tc::EpBiasAct{y, N, b, relu}, passes, st);
+  return launch("tc_linear_fwd", M, N, bn, bn, bn, cdiv(N, bn), 1, s, ap, bp, tc::EpBiasAct{y, N, b, relu}, passes, st);
 }
 
 // PNN product layer: h = relu(prev + ip Wp^T + c0)
@@ -69,7 +69,7 @@ int tc_pnn_lp_fwd(int B, int P, int O, const float* ip, const float* wp, const f
   KPlain s{0, P, P};
   RowProd<4, KPlain> ap{ip, P, B, BM, (P % 4 == 0) && aligned16(ip)};
   RowProd<8, KPlain> bp{wp, P, O, bn, (P % 4 == 0) && aligned16(wp)};
-  return launch(B, O, bn, bn, bn, cdiv(O, bn), 1, s, ap, bp, tc::EpAddBiasRelu2{h, O, prev, c0}, passes, st);
+  return launch("tc_pnn_lp_fwd", B, O, bn, bn, bn, cdiv(O, bn), 1, s, ap, bp, tc::EpAddBiasRelu2{h, O, prev, c0}, passes, st);
 }
 
 // gx[M,K] = (gy[M,N] W[N,K]) (* mask > 0) (+ gx)
@@ -79,7 +79,7 @@ int tc_linear_bwd_input(int M, int N, int K, const float* gy, const float* w, co
   KPlain s{0, N, N};
   RowProd<4, KPlain> ap{gy, N, M, BM, (N % 4 == 0) && aligned16(gy)};
   ColProd<256, KPlain> bp{w, K, K, bn};   // B(k_out, n) = W[n*K + k_out]
-  return launch(M, K, bn, bn, bn, cdiv(K, bn), 1, s, ap, bp, tc::EpMaskAcc{gx, K, mask, K, accumulate},
+  return launch("tc_linear_dx", M, K, bn, bn, bn, cdiv(K, bn), 1, s, ap, bp, tc::EpMaskAcc{gx, K, mask, K, accumulate},
                 passes, st);
 }
 
@@ -101,7 +101,7 @@ int tc_linear_bwd_params(int M, int N, int K, const float* x, const float* gy, f
   KPlain s{0, M, k_chunk};
   ColProd<128, KPlain> ap{gy, N, N, BM};  // A(n, m) = gy[m*N + n]
   ColProd<256, KPlain> bp{x, K, K, bn};   // B(k, m) = x[m*K + k]
-  B200_TRY(launch(N, K, bn, bn, bn, cdiv(K, bn), splits, s, ap, bp, tc::EpPartial{ws, MN, K}, passes, st));
+  B200_TRY(launch("tc_linear_dW", N, K, bn, bn, bn, cdiv(K, bn), splits, s, ap, bp, tc::EpPartial{ws, MN, K}, passes, st));
   B200_TRY(splitk_reduce(ws, splits, MN, scale, accumulate, gw, st));
   if (gb) B200_TRY(colsum(M, N, gy, scale, accumulate, gb, ws + (size_t)splits * MN, st));
   return B200REC_OK;
@@ -119,7 +119,7 @@ int tc_cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x
   KCin s{F, H, 0};
   CinZProd ap{x0, x_in, R, (H % 4 == 0) && aligned16(x_in)};
   RowProd<8, KCin> bp{W, (long long)F * H, C, bn, (H % 4 == 0) && aligned16(W)};
-  return launch(R, C, bn, bn, bn, cdiv(C, bn), 1, s, ap, bp, tc::EpBiasAct{x_out, C, b, true}, passes, st);
+  return launch("tc_cin_fwd", R, C, bn, bn, bn, cdiv(C, bn), 1, s, ap, bp, tc::EpBiasAct{x_out, C, b, true}, passes, st);
 }
 
 // layer backward (gy already ReLU-masked):
@@ -145,7 +145,7 @@ int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x
     KPlain s{0, R, k_chunk};
     CinZtProd ap{x0, x_in, F, H};
     ColProd<256, KPlain> bp{gy, C, C, bn};   // B(c, r) = gy[r*C + c]
-    B200_TRY(launch(FH, C, bn, bn, bn, cdiv(C, bn), splits, s, ap, bp, tc::EpPartialT{ws, MN, FH}, passes, st));
+    B200_TRY(launch("tc_cin_dW", FH, C, bn, bn, bn, cdiv(C, bn), splits, s, ap, bp, tc::EpPartialT{ws, MN, FH}, passes, st));
     B200_TRY(splitk_reduce(ws, splits, MN, 1.0f, false, gW, st));
     B200_TRY(colsum(R, C, gy, 1.0f, false, gb, ws + (size_t)splits * MN, st));
   }
@@ -154,14 +154,14 @@ int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x
     KPlain s{0, C, C};
     RowProd<4, KPlain> ap{gy, C, R, BM, (C % 4 == 0) && aligned16(gy)};
     ColProd<256, KPlain> bp{W, FH, FH, bn};   // B(n = i*H + j, c) = W[c*FH + n]
-    B200_TRY(launch(R, FH, bn, H, H, F, 1, s, ap, bp, tc::EpRowDot{x_in, H, gx0, F}, passes, st));
+    B200_TRY(launch("tc_cin_dx0", R, FH, bn, H, H, F, 1, s, ap, bp, tc::EpRowDot{x_in, H, gx0, F}, passes, st));
   }
   {  // ---- gx_in[r, j] = sum_{(i,c)} (x0[r,i] gy[r,c]) W[c, i*H + j]
     const int bn = pick_bn(H);
     KCin s{F, C, H};
     CinZProd ap{x0, gy, R, (C % 4 == 0) && aligned16(gy)};
     ColProd<256, KCin> bp{W, FH, H, bn};      // B(j, (i,c)) = W[c*FH + i*H + j]; tile rows bounded by H
-    B200_TRY(launch(R, H, bn, bn, bn, cdiv(H, bn), 1, s, ap, bp, tc::EpMaskAcc{gx_in, H, nullptr, 0, gx_in_acc},
+    B200_TRY(launch("tc_cin_dx", R, H, bn, bn, bn, cdiv(H, bn), 1, s, ap, bp, tc::EpMaskAcc{gx_in, H, nullptr, 0, gx_in_acc},
                     passes, st));
   }
   return B200REC_OK;
