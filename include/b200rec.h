@@ -198,9 +198,31 @@ int b200rec_step_gathered_dev(b200rec_model_t m, int batch_size, float* emb, flo
 /* makeEmbeddingGrad / makeWeightsGrad on DEVICE buffers (the owner-side reduce of a row-sharded
  * table): sort + in-order segment sums of (feats[nnz], emb_grad[nnz*dim], w_grad[nnz]) into
  * unique_out / emb_out / w_out (sized for nnz) and *n_unique_dev.  Uses the handle's workspace. */
-int b200rec_segsum_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, const int* feats,
-                       const float* emb_grad, const float* w_grad, int* unique_out, float* emb_out,
-                       float* w_out, int* n_unique_dev, void* stream);
+int b200rec_segsum_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
+                       const int* feats, const float* emb_grad, const float* w_grad, int* unique_out,
+                       float* emb_out, float* w_out, int* n_unique_dev, void* stream);
+
+/* ---- row-sharded table: the PS pull / push as NCCL all-to-all of fixed-capacity slot buffers -------
+ * The Angel PS range-shards the matrices over PS nodes (ColumnRangePartitioner,
+ * rec/model/ParRecModel.scala:77,81,98,116); workers pull rows (:174-177,193-196) and push gradients
+ * (:247-250,261-264).  Here GPU `owner(id) = (id + id / period) % world` holds row `id / world`.
+ * The collectives themselves are issued by the host (torch.distributed / NCCL) between these calls. */
+/* Fill a shard: local row q of `rank` holds the hash-initialised values of its global id. */
+int b200rec_table_init_uniform_sharded(b200rec_table_t t, uint64_t seed, float lo, float hi, int rank,
+                                       int world, int64_t period);
+/* Plan the exchange of one batch: send_ids[world*cap] = local rows grouped by owner in non-zero order
+ * (-1 padding); dst[nnz] = slot of non-zero i; *overflow |= 1 if a bucket exceeds cap. */
+int b200rec_shard_plan_dev(b200rec_model_t m, int64_t nnz, int world, int64_t period, int cap,
+                           const int* feats, int* send_ids, int* dst, int* overflow, void* stream);
+/* Owner-side gather of received slot ids (negative = padding -> zero rows). */
+int b200rec_table_lookup_padded_dev(b200rec_table_t t, int64_t n, const int* local_rows,
+                                    float* embedding_out, float* weights_out, void* stream);
+/* forward + backward where the rows of non-zero i are rows_emb[slots[i]] / rows_w[slots[i]] (the
+ * buffers the all-to-all returned) and its gradients are written to grad_*_slots[slots[i]] (the
+ * buffers the next all-to-all sends to the owners).  Dense gradients / loss stay in the handle. */
+int b200rec_step_rows_dev(b200rec_model_t m, int batch_size, const int* slots, const float* rows_emb,
+                          const float* rows_w, int64_t n_rows, const float* targets,
+                          float* grad_emb_slots, float* grad_w_slots, void* stream);
 /* Plain SGD on the touched rows: E[id] -= lr * G[id], w[id] -= lr * gw[id] (rec/optim/
  * AsyncSGD.scala:10-31 applies the pushed gradient on the PS; textbook form, parity unpinned). */
 int b200rec_table_apply_sgd_dev(b200rec_table_t t, int64_t n_unique_cap, const int* n_unique,

@@ -835,22 +835,88 @@ int b200rec_step_gathered_dev(b200rec_model_t m, int batch_size, float* emb, flo
   B200_GUARD_END
 }
 
-int b200rec_segsum_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, const int* feats,
-                       const float* emb_grad, const float* w_grad, int* unique_out, float* emb_out,
-                       float* w_out, int* n_unique_dev, void* stream) {
+int b200rec_segsum_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
+                       const int* feats, const float* emb_grad, const float* w_grad, int* unique_out,
+                       float* emb_out, float* w_out, int* n_unique_dev, void* stream) {
   B200_GUARD_BEGIN
   B200_REQUIRE(m && n_unique_dev && unique_out, B200REC_ERR_ARG, "NULL argument");
   B200_REQUIRE(nnz >= 0 && nnz < (1LL << 31), B200REC_ERR_ARG, "bad nnz");
   B200_TRY(use_device(m->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
   SegSum a;
-  a.n = nnz; a.K = dim > 0 ? dim : 4; a.key_bits = key_bits > 0 ? key_bits : 31;
+  a.n = nnz; a.K = dim > 0 ? dim : 4; a.key_bits = drop_pad ? 32 : (key_bits > 0 ? key_bits : 31);
+  a.drop_pad = drop_pad != 0;
   a.feats = feats; a.dE = dim > 0 ? emb_grad : nullptr; a.dw = w_grad;
   a.unique = unique_out; a.G = dim > 0 ? emb_out : nullptr; a.gw = w_out;
   a.n_unique = n_unique_dev;
   B200_TRY(segsum_sort(m->seg, a, st));
   if (a.dE || a.dw) B200_TRY(segsum_reduce(m->seg, a, st));
   return B200REC_OK;
+  B200_GUARD_END
+}
+
+// ---- row-sharded table ------------------------------------------------------------------
+int b200rec_table_init_uniform_sharded(b200rec_table_t t, uint64_t seed, float lo, float hi, int rank,
+                                       int world, int64_t period) {
+  B200_REQUIRE(t, B200REC_ERR_ARG, "NULL table");
+  B200_REQUIRE(world >= 1 && rank >= 0 && rank < world, B200REC_ERR_ARG, "bad rank %d / world %d", rank, world);
+  B200_REQUIRE(period >= world && period % world == 0, B200REC_ERR_ARG,
+               "shard period must be a positive multiple of the world size");
+  B200_TRY(use_device(t->device));
+  B200_TRY(table_init_uniform_sharded(t->emb.as<float>(), t->w.as<float>(), t->rows, t->dim ? t->dim : 1,
+                                      seed, lo, hi, rank, world, period, t->stream));
+  B200_CUDA(cudaStreamSynchronize(t->stream));
+  return B200REC_OK;
+}
+
+int b200rec_table_lookup_padded_dev(b200rec_table_t t, int64_t n, const int* local_rows,
+                                    float* embedding_out, float* weights_out, void* stream) {
+  B200_REQUIRE(t, B200REC_ERR_ARG, "NULL table");
+  B200_REQUIRE(n >= 0 && (local_rows || n == 0), B200REC_ERR_ARG, "bad ids");
+  B200_TRY(use_device(t->device));
+  return lookup_rows_padded(t->rows, t->dim ? t->dim : 4, n, local_rows, t->emb.as<float>(),
+                            t->w.as<float>(), t->dim ? embedding_out : nullptr, weights_out,
+                            t->err.as<int>(), stream ? (cudaStream_t)stream : t->stream);
+}
+
+int b200rec_shard_plan_dev(b200rec_model_t m, int64_t nnz, int world, int64_t period, int cap,
+                           const int* feats, int* send_ids, int* dst, int* overflow, void* stream) {
+  B200_GUARD_BEGIN
+  B200_REQUIRE(m && send_ids && dst && overflow, B200REC_ERR_ARG, "NULL argument");
+  B200_REQUIRE(nnz >= 0 && nnz < (1LL << 31) && cap > 0, B200REC_ERR_ARG, "bad sizes");
+  B200_REQUIRE(feats || nnz == 0, B200REC_ERR_ARG, "feats is NULL");
+  B200_TRY(use_device(m->device));
+  return shard_plan(m->plan, nnz, world, period, cap, feats, send_ids, dst, overflow,
+                    stream ? (cudaStream_t)stream : m->stream);
+  B200_GUARD_END
+}
+
+int b200rec_step_rows_dev(b200rec_model_t m, int batch_size, const int* slots, const float* rows_emb,
+                          const float* rows_w, int64_t n_rows, const float* targets,
+                          float* grad_emb_slots, float* grad_w_slots, void* stream) {
+  B200_GUARD_BEGIN
+  B200_REQUIRE(m && slots && rows_w && targets && grad_w_slots, B200REC_ERR_ARG, "NULL argument");
+  B200_REQUIRE(m->params_set, B200REC_ERR_STATE, "b200rec_model_set_params must be called before a step");
+  B200_REQUIRE(batch_size > 0 && m->F > 0, B200REC_ERR_ARG, "batchSize and nFields must be positive");
+  B200_REQUIRE((rows_emb && grad_emb_slots) || m->kind == B200REC_LR, B200REC_ERR_ARG, "NULL row buffers");
+  B200_TRY(use_device(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+  const long long nnz = (long long)batch_size * m->F;
+  float* scal = m->scal.as<float>();
+  m->last_B = batch_size; m->last_nnz = nnz;
+  RunArgs a;
+  a.B = batch_size; a.nnz = nnz;
+  a.feats = slots; a.table_emb = rows_emb ? rows_emb : rows_w; a.table_w = rows_w; a.table_rows = n_rows;
+  a.bias = m->p_bias.as<float>();
+  a.mats = m->mats_len ? m->p_mats.as<float>() : nullptr;
+  a.targets = targets;
+  a.dw_out = grad_w_slots;
+  a.dE_out = m->kind == B200REC_LR ? nullptr : grad_emb_slots;
+  a.out_slot = slots;
+  a.dbias_out = scal + 1;
+  a.gmats_out = m->gmats.as<float>();
+  a.loss_out = scal + 0;
+  return m->run(a, st);
   B200_GUARD_END
 }
 

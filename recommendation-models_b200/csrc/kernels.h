@@ -34,6 +34,7 @@ struct SparseBwd {
   const int* index = nullptr;     // [B*F] or nullptr (canonical)
   float* dE = nullptr;            // [B*F*K] out (may alias X)
   float* dw = nullptr;            // [B*F] out
+  const int* out_slot = nullptr;  // sharded path: row i of the gradients goes to slot out_slot[i]
 };
 int sparse_bwd(const SparseBwd& a, cudaStream_t st);
 
@@ -44,6 +45,9 @@ int scatter_bwd(int B, int n_out, long long n, const int* index, const float* go
                 int* err, cudaStream_t st);
 int lookup_rows(long long rows, int K, long long n, const int* feats, const float* table,
                 const float* wtable, float* emb_out, float* w_out, int* err, cudaStream_t st);
+// same with negative ids allowed (exchange padding): their output rows are zero
+int lookup_rows_padded(long long rows, int K, long long n, const int* feats, const float* table,
+                       const float* wtable, float* emb_out, float* w_out, int* err, cudaStream_t st);
 // nn/Gather.scala / nn/DotProduct2.scala
 int pair_gather_fwd(int B, int F, int P, int K, const float* in, const int* rows, const int* cols,
                     float* row_out, float* col_out, cudaStream_t st);
@@ -71,11 +75,27 @@ struct SegSum {
   float* G = nullptr;             // [n,K] out (first U rows valid)
   float* gw = nullptr;            // [n]   out
   int* n_unique = nullptr;        // device int out
+  bool drop_pad = false;          // keys equal to -1 (exchange padding) form no segment
 };
 // sort half (depends only on feats: can run on a side stream while the dense math runs)
 int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st);
 // reduce half (needs dE / dw)
 int segsum_reduce(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st);
+// ---------------------------------------------------------------- shard.cu (row-sharded table) --
+// owner(id) = (id + id / period) % world, local row = id / world (period is a multiple of world, so
+// the `world` consecutive ids of a block rotate over the ranks: a bijection id <-> (owner, row)).
+struct ShardPlanWorkspace {
+  DevBuf keys, keys_sorted, vals, perm, offsets, cub_tmp;
+  int reserve(long long n);
+  void release();
+};
+// send_ids[world*cap]: local row ids grouped by owner in slot order (-1 = padding);
+// dst[n]: slot (owner*cap + position) of non-zero i; overflow[0] |= 1 when a bucket exceeds cap.
+int shard_plan(ShardPlanWorkspace& ws, long long n, int world, long long period, int cap,
+               const int* feats, int* send_ids, int* dst, int* overflow, cudaStream_t st);
+int table_init_uniform_sharded(float* table, float* wtable, long long rows, int K, uint64_t seed,
+                               float lo, float hi, int rank, int world, long long period,
+                               cudaStream_t st);
 int apply_sgd(int K, long long cap, const int* n_unique, const int* unique, const float* G,
               const float* gw, float lr, float* table, float* wtable, cudaStream_t st);
 

@@ -133,6 +133,7 @@ void b200rec_model_s::destroy() {
   for (auto& b : acts) b.release();
   for (auto& b : xl) b.release();
   seg.release();
+  plan.release();
   if (h_scal) cudaFreeHost(h_scal);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
@@ -428,7 +429,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   SparseBwd sb;
   sb.B = B; sb.F = has_emb ? F : (int)(B ? nnz / B : 0); sb.K = has_emb ? K : 0;
   sb.X = Xp; sb.S = second_order ? S.as<float>() : nullptr; sb.dX = dxd; sb.dlogit = dlg;
-  sb.index = a.index; sb.dE = has_emb ? a.dE_out : nullptr; sb.dw = a.dw_out;
+  sb.index = a.index; sb.dE = has_emb ? a.dE_out : nullptr; sb.dw = a.dw_out; sb.out_slot = a.out_slot;
   if (!has_emb && !canonical) {
     B200_TRY(scatter_bwd(B, 1, nnz, a.index, dlg, a.dw_out, err, st));
   } else {

@@ -38,6 +38,7 @@ struct RunArgs {
   float* dbias_out = nullptr;  // [1]
   float* gmats_out = nullptr;  // [mats_len]
   float* loss_out = nullptr;   // [1]
+  const int* out_slot = nullptr;  // sharded path: per-nnz gradients are written to these slots
 };
 
 }  // namespace b200rec
@@ -74,6 +75,7 @@ struct b200rec_model_s {
   DevBuf ip, gip, pre, hbuf;
   std::vector<DevBuf> acts, xl;
   b200rec::SegSumWorkspace seg;
+  b200rec::ShardPlanWorkspace plan;
 
   int init(int kind, int F, int K, const int* fc, int n_fc, const int* cin, int n_cin, int depth,
            int device);

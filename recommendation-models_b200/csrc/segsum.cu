@@ -60,7 +60,7 @@ __global__ void head_flag_kernel(long long n, const unsigned* keys, int* flags) 
 
 // seg_idx[i] = 1-based segment number of sorted position i (inclusive scan of the head flags)
 __global__ void seg_heads_kernel(long long n, const unsigned* keys, const int* seg_idx,
-                                 int* seg_start, int* unique, int* n_unique) {
+                                 int* seg_start, int* unique, int* n_unique, bool drop_pad) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int s = seg_idx[i];
@@ -69,7 +69,8 @@ __global__ void seg_heads_kernel(long long n, const unsigned* keys, const int* s
     unique[s - 1] = (int)keys[i];
   }
   if (i == n - 1) {
-    *n_unique = s;
+    // exchange padding (key 0xffffffff) sorts last: its segment is not a feature id
+    *n_unique = (drop_pad && keys[i] == 0xffffffffu) ? s - 1 : s;
     seg_start[s] = (int)n;
   }
 }
@@ -103,7 +104,7 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
   if (tl_prof) tl_prof->end(st);
   g_launches.fetch_add(2, std::memory_order_relaxed);
   B200_LAUNCH(seg_heads_kernel, cdiv(n, 256), 256, 0, st, (long long)n, keys_sorted, seg_idx,
-              ws.seg_start.as<int>(), a.unique, a.n_unique);
+              ws.seg_start.as<int>(), a.unique, a.n_unique, a.drop_pad);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }

@@ -205,10 +205,11 @@ __global__ void __launch_bounds__(256) emb_grad_kernel(SparseBwd a, long long n_
       g.x = fmaf(c, s.x - v.x, g.x); g.y = fmaf(c, s.y - v.y, g.y);
       g.z = fmaf(c, s.z - v.z, g.z); g.w = fmaf(c, s.w - v.w, g.w);
     }
-    st_f4(a.dE + row * K + sub * 4, g);
+    const long long orow = a.out_slot ? (long long)a.out_slot[row] : row;
+    st_f4(a.dE + orow * K + sub * 4, g);
     if (sub == 0 && a.dw) {
       const int bi = a.index ? a.index[row] : b;
-      a.dw[row] = __ldg(a.dlogit + bi);
+      a.dw[orow] = __ldg(a.dlogit + bi);
     }
   }
 }
@@ -222,23 +223,24 @@ __global__ void __launch_bounds__(256) emb_grad_generic_kernel(SparseBwd a, long
     const int b = (int)(row / F);
     float g = a.dX ? a.dX[t] : 0.f;
     if (a.S) g = fmaf(a.dlogit[b] / (float)K, a.S[(long long)b * K + k] - a.X[t], g);
-    a.dE[t] = g;
-    if (k == 0 && a.dw) a.dw[row] = a.dlogit[a.index ? a.index[row] : b];
+    const long long orow = a.out_slot ? (long long)a.out_slot[row] : row;
+    a.dE[orow * K + k] = g;
+    if (k == 0 && a.dw) a.dw[orow] = a.dlogit[a.index ? a.index[row] : b];
   }
 }
 
 __global__ void dw_only_kernel(long long n, int F, const int* index, const float* dlogit,
-                               float* dw) {
+                               const int* out_slot, float* dw) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
-    dw[i] = dlogit[index ? index[i] : (int)(i / F)];
+    dw[out_slot ? out_slot[i] : i] = dlogit[index ? index[i] : (int)(i / F)];
 }
 
 int sparse_bwd(const SparseBwd& a, cudaStream_t st) {
   const long long rows = (long long)a.B * a.F;
   if (rows <= 0) return B200REC_OK;
   if (!a.dE) {  // LR: only the first-order gradient
-    B200_LAUNCH(dw_only_kernel, cdiv(rows, 256), 256, 0, st, rows, a.F, a.index, a.dlogit, a.dw);
+    B200_LAUNCH(dw_only_kernel, cdiv(rows, 256), 256, 0, st, rows, a.F, a.index, a.dlogit, a.out_slot, a.dw);
     B200_CHECK_LAUNCH();
     return B200REC_OK;
   }
@@ -261,6 +263,7 @@ int sparse_bwd(const SparseBwd& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // Plain lookup (makeEmbeddings / makeWeights): bit-exact copies.
 // ------------------------------------------------------------------------------------------------
+template <bool PAD>
 __global__ void __launch_bounds__(256) lookup_kernel(long long rows, int K, long long n,
                                                      const int* feats, const float* table,
                                                      const float* wtable, float* emb_out,
@@ -272,6 +275,11 @@ __global__ void __launch_bounds__(256) lookup_kernel(long long rows, int K, long
     const long long i = t / kv;
     const int sub = (int)(t - i * kv);
     long long id = feats[i];
+    if (PAD && id < 0) {  // exchange padding: zero row
+      if (emb_out) st_f4(emb_out + i * K + sub * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (sub == 0 && w_out) w_out[i] = 0.f;
+      continue;
+    }
     if (id < 0 || id >= rows) {
       if (err) atomicOr(err, DEV_BAD_ID);
       id = 0;
@@ -281,6 +289,7 @@ __global__ void __launch_bounds__(256) lookup_kernel(long long rows, int K, long
   }
 }
 
+template <bool PAD>
 __global__ void lookup_generic_kernel(long long rows, int K, long long n, const int* feats,
                                       const float* table, const float* wtable, float* emb_out,
                                       float* w_out, int* err) {
@@ -289,6 +298,11 @@ __global__ void lookup_generic_kernel(long long rows, int K, long long n, const 
     const long long i = t / K;
     const int k = (int)(t - i * K);
     long long id = feats[i];
+    if (PAD && id < 0) {
+      if (emb_out) emb_out[t] = 0.f;
+      if (k == 0 && w_out) w_out[i] = 0.f;
+      continue;
+    }
     if (id < 0 || id >= rows) {
       if (err) atomicOr(err, DEV_BAD_ID);
       id = 0;
@@ -298,22 +312,33 @@ __global__ void lookup_generic_kernel(long long rows, int K, long long n, const 
   }
 }
 
-int lookup_rows(long long rows, int K, long long n, const int* feats, const float* table,
-                const float* wtable, float* emb_out, float* w_out, int* err, cudaStream_t st) {
+template <bool PAD>
+static int lookup_rows_impl(long long rows, int K, long long n, const int* feats, const float* table,
+                            const float* wtable, float* emb_out, float* w_out, int* err,
+                            cudaStream_t st) {
   if (n <= 0) return B200REC_OK;
   if (K % 4 == 0) {
     int grid = cdiv(n * (K / 4), 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    B200_LAUNCH(lookup_kernel, grid, 256, 0, st, rows, K, n, feats, table, wtable, emb_out, w_out,
-                err);
+    B200_LAUNCH(lookup_kernel<PAD>, grid, 256, 0, st, rows, K, n, feats, table, wtable, emb_out,
+                w_out, err);
   } else {
     int grid = cdiv(n * K, 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    B200_LAUNCH(lookup_generic_kernel, grid, 256, 0, st, rows, K, n, feats, table, wtable,
+    B200_LAUNCH(lookup_generic_kernel<PAD>, grid, 256, 0, st, rows, K, n, feats, table, wtable,
                 emb_out, w_out, err);
   }
   B200_CHECK_LAUNCH();
   return B200REC_OK;
+}
+int lookup_rows(long long rows, int K, long long n, const int* feats, const float* table,
+                const float* wtable, float* emb_out, float* w_out, int* err, cudaStream_t st) {
+  return lookup_rows_impl<false>(rows, K, n, feats, table, wtable, emb_out, w_out, err, st);
+}
+int lookup_rows_padded(long long rows, int K, long long n, const int* feats, const float* table,
+                       const float* wtable, float* emb_out, float* w_out, int* err,
+                       cudaStream_t st) {
+  return lookup_rows_impl<true>(rows, K, n, feats, table, wtable, emb_out, w_out, err, st);
 }
 
 // ------------------------------------------------------------------------------------------------

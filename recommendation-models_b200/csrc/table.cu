@@ -39,6 +39,37 @@ __global__ void __launch_bounds__(256) table_init_kernel(float* table, float* wt
   }
 }
 
+// local row q of rank g holds global id q*world + ((g - (q*world)/period) mod world)   (shard.cu)
+__global__ void __launch_bounds__(256) table_init_sharded_kernel(float* table, float* wtable,
+                                                                 long long rows, int K, uint64_t seed,
+                                                                 float lo, float span, int rank,
+                                                                 int world, long long period) {
+  const long long n = rows * K;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long q = t / K;
+    const int k = (int)(t - q * K);
+    const long long base = q * world;
+    long long tt = ((long long)rank - (base / period)) % world;
+    if (tt < 0) tt += world;
+    const uint64_t g = (uint64_t)(base + tt);
+    table[t] = hash_uniform(seed, g * (uint64_t)K + (uint64_t)k, lo, span);
+    if (k == 0 && wtable) wtable[q] = hash_uniform(seed + 1, g, lo, span);
+  }
+}
+
+int table_init_uniform_sharded(float* table, float* wtable, long long rows, int K, uint64_t seed,
+                               float lo, float hi, int rank, int world, long long period,
+                               cudaStream_t st) {
+  if (rows <= 0) return B200REC_OK;
+  int grid = cdiv(rows * K, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  B200_LAUNCH(table_init_sharded_kernel, grid, 256, 0, st, table, wtable, rows, K, seed, lo, hi - lo,
+              rank, world, period);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
 int table_init_uniform(float* table, float* wtable, long long rows, int K, uint64_t seed, float lo,
                        float hi, long long row_offset, long long row_stride, cudaStream_t st) {
   if (rows <= 0) return B200REC_OK;

@@ -1,0 +1,303 @@
+"""Row-sharded embedding table across the GPUs of one box: the PS pull / push of the reference as
+NCCL all-to-all exchanges, dense parameters data-parallel with an NCCL allreduce.
+
+Mirrors rec/model/ParRecModel.scala (under /root/reference/src/main/scala/io/yaochi/recommendation):
+  :77,81,98,116   ColumnRangePartitioner -- the table is partitioned by feature id over PS nodes
+  :174-177,193-196 pullEmbeddings        -> ids to owners, rows back          (two all-to-all)
+  :247-250,261-264 pushEmbedding         -> per-nnz gradients to owners       (one all-to-all), owner-side
+                                            sorted-index segmented scatter-add (makeEmbeddingGrad :316-328)
+  :198-199,266-267 pull / push of `mats` -> replicated dense params, allreduce(sum) of their gradients
+Semantics: the reference is asynchronous (fire-and-forget pushes); here every rank computes the mean
+loss of ITS batch and the owners sum what arrives -- equal to `world` sequential reference pushes
+computed from one parameter snapshot.
+
+`ShardedParRecModel` holds only orchestration; the arithmetic is behind an `ops` object:
+`GpuOps` (libb200rec through the C ABI, torch tensors only as device memory) in production, and a
+numpy stand-in in tests/ so the exchange logic runs under gloo on CPU with world_size 2.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class ShardSpec:
+    """owner(id) = (id + id // period) % world ; local row = id // world  (csrc/shard.cu)."""
+
+    def __init__(self, rows_global, world, rank, period=None):
+        self.rows_global, self.world, self.rank = int(rows_global), int(world), int(rank)
+        if period is None:
+            period = max(world, (self.rows_global // 39 // world) * world)
+        assert period >= world and period % world == 0
+        self.period = int(period)
+        self.rows_local = (self.rows_global + world - 1) // world
+
+    def owner(self, ids):
+        ids = np.asarray(ids, np.int64)
+        return ((ids + ids // self.period) % self.world).astype(np.int64)
+
+    def local_row(self, ids):
+        return np.asarray(ids, np.int64) // self.world
+
+    def global_id(self, rank, q):
+        q = np.asarray(q, np.int64)
+        base = q * self.world
+        return base + (rank - base // self.period) % self.world
+
+
+class GpuOps:
+    """The device half of one rank: C-ABI calls on torch-owned device buffers."""
+
+    def __init__(self, pkg, model, table, spec, batch, cap, torch, device):
+        self.pkg, self.model, self.table, self.spec = pkg, model, table, spec
+        self.torch, self.device = torch, device
+        self.F, self.K = model.nFields, model.embeddingDim
+        self.B, self.cap = batch, cap
+        self.lib = L.lib()
+        sp = C.c_void_p()
+        L.check(self.lib.b200rec_model_stream(model.handle, C.byref(sp)))
+        self.stream_ptr = sp.value
+        self.stream = torch.cuda.ExternalStream(sp.value, device=device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        self.n_unique = torch.zeros(1, dtype=torch.int32, device=device)
+        # dense gradient views of the handle's buffers (for the allreduce)
+        ptrs = [C.c_void_p() for _ in range(7)]
+        L.check(self.lib.b200rec_step_result_ptrs(model.handle, *[C.byref(p) for p in ptrs]))
+        self._loss_ptr, self._bias_grad_ptr, self._mats_grad_ptr = ptrs[0].value, ptrs[5].value, ptrs[6].value
+
+    def empty(self, n, dtype):
+        return self.torch.empty(n, dtype=dtype, device=self.device)
+
+    @property
+    def int32(self):
+        return self.torch.int32
+
+    @property
+    def float32(self):
+        return self.torch.float32
+
+    def wrap(self, ptr, n):
+        """torch view of `n` floats at a raw device pointer owned by the library."""
+        class _Arr:
+            __cuda_array_interface__ = dict(shape=(n,), typestr="<f4", data=(ptr, False), version=2)
+        return self.torch.as_tensor(_Arr(), device=self.device)
+
+    def dense_grads(self):
+        n = self.model.matsLen()
+        return self.wrap(self._bias_grad_ptr, 1), (self.wrap(self._mats_grad_ptr, n) if n else None)
+
+    def loss(self):
+        return self.wrap(self._loss_ptr, 1)
+
+    def plan(self, feats, send_ids, dst):
+        L.check(self.lib.b200rec_shard_plan_dev(self.model.handle, feats.numel(), self.spec.world,
+                                                self.spec.period, self.cap, feats.data_ptr(),
+                                                send_ids.data_ptr(), dst.data_ptr(),
+                                                self.overflow.data_ptr(), self.stream_ptr))
+
+    def lookup(self, recv_ids, rows, w):
+        L.check(self.lib.b200rec_table_lookup_padded_dev(self.table.handle, recv_ids.numel(),
+                                                         recv_ids.data_ptr(), rows.data_ptr(),
+                                                         w.data_ptr(), self.stream_ptr))
+
+    def step_rows(self, dst, rows, w, targets, grad_rows, grad_w):
+        L.check(self.lib.b200rec_step_rows_dev(self.model.handle, self.B, dst.data_ptr(), rows.data_ptr(),
+                                               w.data_ptr(), w.numel(), targets.data_ptr(),
+                                               grad_rows.data_ptr(), grad_w.data_ptr(), self.stream_ptr))
+
+    def segsum(self, recv_ids, grad_rows, grad_w, unique, G, gw):
+        L.check(self.lib.b200rec_segsum_dev(self.model.handle, self.K, recv_ids.numel(), 32, 1,
+                                            recv_ids.data_ptr(), grad_rows.data_ptr(), grad_w.data_ptr(),
+                                            unique.data_ptr(), G.data_ptr(), gw.data_ptr(),
+                                            self.n_unique.data_ptr(), self.stream_ptr))
+
+    def apply_sgd(self, unique, G, gw, lr):
+        L.check(self.lib.b200rec_table_apply_sgd_dev(self.table.handle, unique.numel(),
+                                                     self.n_unique.data_ptr(), unique.data_ptr(),
+                                                     G.data_ptr(), gw.data_ptr(), lr, self.stream_ptr))
+
+    def stream_ctx(self):
+        return self.torch.cuda.stream(self.stream)
+
+
+class ShardedParRecModel:
+    """optimize() over a row-sharded table.  `dist` is torch.distributed (nccl on GPUs, gloo in the
+    CPU tests); `ops` does the arithmetic."""
+
+    def __init__(self, ops, dist, spec, batch, n_fields, dim, cap=None, group=None):
+        self.ops, self.dist, self.spec, self.group = ops, dist, spec, group
+        self.B, self.F, self.K = batch, n_fields, dim
+        N, G = batch * n_fields, spec.world
+        # capacity of one (source, owner) bucket: the mean N/G plus 25 % + 1024 slack; overflow is flagged
+        self.cap = cap or int(N / G * 1.25) + 1024
+        n = G * self.cap
+        e = ops.empty
+        self.send_ids, self.recv_ids, self.dst = e(n, ops.int32), e(n, ops.int32), e(N, ops.int32)
+        self.rows, self.w = e(n * dim, ops.float32), e(n, ops.float32)              # owner side, gathered
+        self.got_rows, self.got_w = e(n * dim, ops.float32), e(n, ops.float32)      # back at the requester
+        self.grad_rows, self.grad_w = e(n * dim, ops.float32), e(n, ops.float32)    # per-nnz grads, slot layout
+        self.recv_grad_rows, self.recv_grad_w = e(n * dim, ops.float32), e(n, ops.float32)
+        self.unique, self.G, self.gw = e(n, ops.int32), e(n * dim, ops.float32), e(n, ops.float32)
+
+    def _a2a(self, out, inp):
+        self.dist.all_to_all_single(out, inp, group=self.group)
+
+    def optimize(self, feats, targets, lr=None):
+        """One step: feats int32[B*F] (global ids), targets float32[B], both on the ops' device.
+        Afterwards unique / G / gw hold this rank's OWNED distinct local rows and their summed
+        gradients, and the dense gradients are allreduced."""
+        o = self.ops
+        with o.stream_ctx():
+            o.plan(feats, self.send_ids, self.dst)                       # bucket ids by owner
+            self._a2a(self.recv_ids, self.send_ids)                      # pull request  (ids -> owners)
+            o.lookup(self.recv_ids, self.rows, self.w)                   # owner-side gather
+            self._a2a(self.got_rows, self.rows)                          # rows back
+            self._a2a(self.got_w, self.w)
+            o.step_rows(self.dst, self.got_rows, self.got_w, targets, self.grad_rows, self.grad_w)
+            gb, gm = o.dense_grads()
+            work = [self.dist.all_reduce(gb, group=self.group, async_op=True)]
+            if gm is not None:
+                work.append(self.dist.all_reduce(gm, group=self.group, async_op=True))
+            self._a2a(self.recv_grad_rows, self.grad_rows)               # push  (grads -> owners)
+            self._a2a(self.recv_grad_w, self.grad_w)
+            o.segsum(self.recv_ids, self.recv_grad_rows, self.recv_grad_w, self.unique, self.G, self.gw)
+            for wk in work:
+                wk.wait()
+            if lr is not None:
+                o.apply_sgd(self.unique, self.G, self.gw, lr)
+
+
+# ------------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1, launched by torchrun): weak scaling, per-GPU batch fixed
+# ------------------------------------------------------------------------------------------------------
+def bench(args, pkg):
+    import json
+    import os
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    import bench as B
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    synth = pkg.synth
+    kind, fc, cin, depth = B.MODELS[args.model]
+    F, K = B.F, B.K
+    batch, rows = args.batch, args.rows
+    spec = ShardSpec(rows, world, rank)
+    model = pkg.make_model(kind, F, K, fc, cin, depth, device=local)
+    if args.gemm_mode is not None:
+        model.setGemmMode(args.gemm_mode)
+    table = pkg.EmbeddingTable(spec.rows_local, K if kind != "lr" else 0, device=local)
+    L.check(L.lib().b200rec_table_init_uniform_sharded(table.handle, B.SEED_PARAMS, -0.05, 0.05, rank, world,
+                                                       spec.period))
+    ps = pkg.ParRecModel(model, table)
+    ps.setParams(np.array([0.1], np.float32), synth.init_mats(B.SEED_PARAMS, model.getMatsSize()))
+    ops = GpuOps(pkg, model, table, spec, batch, None, torch, dev)
+    sh = ShardedParRecModel(ops, dist, spec, batch, F, K)
+    ops.cap = sh.cap
+    W, Ksteps = args.warmup, args.steps
+    nb = min(W + Ksteps, 32)
+    # every rank draws its own batches: global step index = s * world + rank
+    batches = [synth.make_feats(B.SEED_DATA, s * world + rank, batch, F, rows)[1] for s in range(nb)]
+    dev_b = [(torch.from_numpy(f).to(dev), torch.from_numpy(synth.make_targets(B.SEED_DATA, f, batch, F)).to(dev))
+             for f in batches]
+    for i in range(W):
+        sh.optimize(*dev_b[i % nb])
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = B.ClockSampler(local)
+    clocks.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = pkg.launch_count()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(ops.stream)
+    for i in range(Ksteps):
+        sh.optimize(*dev_b[(W + i) % nb])
+    e1.record(ops.stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = pkg.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ovf = ops.overflow.clone()
+    dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
+
+    # end to end: ids + labels from pinned host memory every step, loss back to the host every step
+    pin = [(torch.from_numpy(f).pin_memory(), torch.from_numpy(synth.make_targets(B.SEED_DATA, f, batch, F)).pin_memory())
+           for f in batches]
+    d_f, d_t = torch.empty(batch * F, dtype=torch.int32, device=dev), torch.empty(batch, dtype=torch.float32, device=dev)
+    h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def host_step(i):
+        f, t = pin[i % nb]
+        with ops.stream_ctx():
+            d_f.copy_(f, non_blocking=True)
+            d_t.copy_(t, non_blocking=True)
+        sh.optimize(d_f, d_t)
+        with ops.stream_ctx():
+            h_loss.copy_(ops.loss(), non_blocking=True)
+        ops.stream.synchronize()
+        return float(h_loss[0])
+
+    for i in range(3):
+        host_step(i)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    last = 0.0
+    for i in range(Ksteps):
+        last = host_step(W + i)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    clk = clocks.stop()
+
+    # per-kernel pass on rank 0 (own kernels only; NCCL kernels are not in this list)
+    L.profile_begin()
+    for i in range(min(Ksteps, 10)):
+        sh.optimize(*dev_b[(W + i) % nb])
+    prof = L.profile_end()
+    dist.barrier()
+    if rank == 0:
+        nsteps = min(Ksteps, 10)
+        by_phase = {}
+        for tag, name, cnt, t in prof:
+            by_phase[tag] = by_phase.get(tag, 0.0) + t / nsteps
+        n_slots = world * sh.cap
+        out = {
+            "metric": "train samples/sec (fwd+bwd)", "value": round(batch * world * Ksteps / (ms_total * 1e-3), 1),
+            "unit": "samples/s", "n_gpus": world, "steps": Ksteps, "warmup": W,
+            "ms_per_step": round(ms_total / Ksteps, 5), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.model} k={K} F={F} fc={fc} cin={cin} depth={depth} per-GPU batch={batch} "
+                                   f"table_rows={rows} row-sharded over {world} GPUs (BASELINE configs[2]/[4])",
+                       "global_batch": batch * world, "parallelism": f"table row-sharded x{world} (NCCL all-to-all), "
+                       f"dense dp{world} (NCCL allreduce)", "bucket_capacity": sh.cap,
+                       "bucket_overflow": int(ovf.item()),
+                       "l2": "table shard > L2; new ids every step; no explicit flush", "gemm_mode": args.gemm_mode},
+            "clocks": clk,
+            "e2e": {"value": round(batch * world * Ksteps / float(e2e.item()), 1), "unit": "samples/s",
+                    "h2d_bytes_per_step": batch * F * 4 + batch * 4, "d2h_bytes_per_step": 4,
+                    "call": "ShardedParRecModel.optimize (pinned host ids + labels in, loss out), per rank",
+                    "last_loss": round(last, 6)},
+            "gpu_launches": int(launches),
+            "exchange_bytes_per_gpu_per_step": {"ids": n_slots * 4, "rows_back": n_slots * (K + 1) * 4,
+                                                "grads": n_slots * (K + 1) * 4,
+                                                "dense_allreduce": (model.matsLen() + 1) * 4},
+            "kernels_rank0_ms_per_step": {k: round(v, 5) for k, v in sorted(by_phase.items(), key=lambda kv: -kv[1])},
+        }
+        print(json.dumps(out))
+    model.close()
+    table.close()
+    dist.destroy_process_group()
