@@ -185,7 +185,9 @@ int b200rec_model_param_ptrs(b200rec_model_t m, float** bias, float** mats);
  *  loss; n_unique; unique[U]; emb_grad[U*K]; w_grad[U]; bias_grad[1]; mats_grad[mats_len]. */
 int b200rec_step_results(b200rec_model_t m, float* loss, int64_t* n_unique, int* unique,
                          float* emb_grad, float* w_grad, float* bias_grad, float* mats_grad);
-/* Device pointers of the same (valid until the next step on this handle). */
+/* Device pointers of the same (valid until the next step on this handle).  mats_grad points at
+ * mats_len + 1 floats: the bias gradient is repeated at mats_grad[mats_len] so one allreduce covers
+ * all dense gradients. */
 int b200rec_step_result_ptrs(b200rec_model_t m, float** loss, int** n_unique, int** unique,
                              float** emb_grad, float** w_grad, float** bias_grad,
                              float** mats_grad);
@@ -201,6 +203,15 @@ int b200rec_step_gathered_dev(b200rec_model_t m, int batch_size, float* emb, flo
 int b200rec_segsum_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
                        const int* feats, const float* emb_grad, const float* w_grad, int* unique_out,
                        float* emb_out, float* w_out, int* n_unique_dev, void* stream);
+
+/* The two halves of b200rec_segsum_dev, for overlap: the sort needs only the ids and runs on the
+ * handle's side stream forked from `stream`; the reduce joins it.  Pass the same arguments to both. */
+int b200rec_segsum_sort_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
+                            const int* feats, int* unique_out, int* n_unique_dev, void* stream);
+int b200rec_segsum_reduce_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
+                              const int* feats, const float* emb_grad, const float* w_grad,
+                              int* unique_out, float* emb_out, float* w_out, int* n_unique_dev,
+                              void* stream);
 
 /* ---- row-sharded table: the PS pull / push as NCCL all-to-all of fixed-capacity slot buffers -------
  * The Angel PS range-shards the matrices over PS nodes (ColumnRangePartitioner,

@@ -64,6 +64,8 @@ SIGNATURES = {
     "b200rec_step_nnz_grad_ptrs": [vp, C.POINTER(vp), C.POINTER(vp)],
     "b200rec_step_gathered_dev": [vp, C.c_int, vp, vp, vp, vp],
     "b200rec_segsum_dev": [vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp],
+    "b200rec_segsum_sort_dev": [vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp],
+    "b200rec_segsum_reduce_dev": [vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp],
     "b200rec_table_init_uniform_sharded": [vp, C.c_uint64, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int64],
     "b200rec_shard_plan_dev": [vp, C.c_int64, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp, vp],
     "b200rec_table_lookup_padded_dev": [vp, C.c_int64, vp, vp, vp, vp],

@@ -855,6 +855,54 @@ int b200rec_segsum_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, in
   B200_GUARD_END
 }
 
+// The two halves of b200rec_segsum_dev for overlap: the sort depends only on the ids, so the owner
+// runs it on the handle's side stream (forked from `stream`) while the dense math runs; the reduce
+// joins it.  Same arguments in both calls.
+static int fill_segsum(Model* m, int dim, int64_t nnz, int key_bits, int drop_pad, const int* feats,
+                       const float* emb_grad, const float* w_grad, int* unique_out, float* emb_out,
+                       float* w_out, int* n_unique_dev, SegSum& a) {
+  B200_REQUIRE(m && n_unique_dev && unique_out, B200REC_ERR_ARG, "NULL argument");
+  B200_REQUIRE(nnz >= 0 && nnz < (1LL << 31), B200REC_ERR_ARG, "bad nnz");
+  a.n = nnz; a.K = dim > 0 ? dim : 4; a.key_bits = drop_pad ? 32 : (key_bits > 0 ? key_bits : 31);
+  a.drop_pad = drop_pad != 0;
+  a.feats = feats; a.dE = dim > 0 ? emb_grad : nullptr; a.dw = w_grad;
+  a.unique = unique_out; a.G = dim > 0 ? emb_out : nullptr; a.gw = w_out;
+  a.n_unique = n_unique_dev;
+  return B200REC_OK;
+}
+
+int b200rec_segsum_sort_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
+                            const int* feats, int* unique_out, int* n_unique_dev, void* stream) {
+  B200_GUARD_BEGIN
+  SegSum a;
+  B200_TRY(fill_segsum(m, dim, nnz, key_bits, drop_pad, feats, nullptr, nullptr, unique_out, nullptr,
+                       nullptr, n_unique_dev, a));
+  B200_TRY(use_device(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+  B200_CUDA(cudaEventRecord(m->ev_fork, st));
+  B200_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+  B200_TRY(segsum_sort(m->seg, a, m->side));
+  B200_CUDA(cudaEventRecord(m->ev_join, m->side));
+  return B200REC_OK;
+  B200_GUARD_END
+}
+
+int b200rec_segsum_reduce_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
+                              const int* feats, const float* emb_grad, const float* w_grad,
+                              int* unique_out, float* emb_out, float* w_out, int* n_unique_dev,
+                              void* stream) {
+  B200_GUARD_BEGIN
+  SegSum a;
+  B200_TRY(fill_segsum(m, dim, nnz, key_bits, drop_pad, feats, emb_grad, w_grad, unique_out, emb_out,
+                       w_out, n_unique_dev, a));
+  B200_TRY(use_device(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+  B200_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
+  if (a.dE || a.dw) B200_TRY(segsum_reduce(m->seg, a, st));
+  return B200REC_OK;
+  B200_GUARD_END
+}
+
 // ---- row-sharded table ------------------------------------------------------------------
 int b200rec_table_init_uniform_sharded(b200rec_table_t t, uint64_t seed, float lo, float hi, int rank,
                                        int world, int64_t period) {

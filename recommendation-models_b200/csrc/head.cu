@@ -43,13 +43,15 @@ __global__ void __launch_bounds__(256) head_kernel(Head h, float* part) {
   }
 }
 
-__global__ void head_finish_kernel(int nparts, int B, const float* part, float* loss, float* dbias) {
+__global__ void head_finish_kernel(int nparts, int B, const float* part, float* loss, float* dbias,
+                                   float* dbias2) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double a = 0.0;  // BCECriterion accumulates the two dot products in a double
     float c = 0.f;
     for (int i = 0; i < nparts; ++i) { a += (double)part[2 * i]; c += part[2 * i + 1]; }
     if (loss) loss[0] = (float)(-a / (double)B);
     if (dbias) dbias[0] = c;
+    if (dbias2) dbias2[0] = c;
   }
 }
 
@@ -59,7 +61,7 @@ int head_run(const Head& h, DevBuf& scratch, cudaStream_t st) {
   B200_TRY(scratch.reserve((size_t)blocks * 2 * sizeof(float)));
   B200_LAUNCH(head_kernel, blocks, 256, 0, st, h, scratch.as<float>());
   if (h.targets)
-    B200_LAUNCH(head_finish_kernel, 1, 32, 0, st, blocks, h.B, scratch.as<float>(), h.loss, h.dbias);
+    B200_LAUNCH(head_finish_kernel, 1, 32, 0, st, blocks, h.B, scratch.as<float>(), h.loss, h.dbias, h.dbias2);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }

@@ -136,6 +136,7 @@ struct Head {
   float* dlogit = nullptr;         // [B]
   float* loss = nullptr;           // [1]
   float* dbias = nullptr;          // [1]
+  float* dbias2 = nullptr;         // second copy, adjacent to the mats gradient (one allreduce)
 };
 int head_run(const Head& h, DevBuf& scratch, cudaStream_t st);
 

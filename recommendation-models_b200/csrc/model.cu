@@ -117,7 +117,7 @@ int b200rec_model_s::init(int kind_, int F_, int K_, const int* fc_, int n_fc, c
   B200_CUDA(cudaMemset(scal.p, 0, 64));
   B200_TRY(p_bias.reserve(4));
   B200_TRY(p_mats.reserve((size_t)(mats_len > 0 ? mats_len : 1) * 4));
-  B200_TRY(gmats.reserve((size_t)(mats_len > 0 ? mats_len : 1) * 4));
+  B200_TRY(gmats.reserve((size_t)(mats_len + 1) * 4));  // + the bias gradient at the end
   return B200REC_OK;
 }
 
@@ -351,6 +351,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   h.dlogit = dlogit.as<float>();
   h.loss = a.loss_out;
   h.dbias = a.dbias_out;
+  if (a.gmats_out == gmats.as<float>()) h.dbias2 = gmats.as<float>() + mats_len;  // [mats grad | bias grad]
   B200_TRY(head_run(h, scratch, st));
   if (!train) return B200REC_OK;
 

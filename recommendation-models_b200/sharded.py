@@ -86,8 +86,8 @@ class GpuOps:
         return self.torch.as_tensor(_Arr(), device=self.device)
 
     def dense_grads(self):
-        n = self.model.matsLen()
-        return self.wrap(self._bias_grad_ptr, 1), (self.wrap(self._mats_grad_ptr, n) if n else None)
+        """[mats gradient | bias gradient] as ONE tensor (the library keeps them adjacent)."""
+        return self.wrap(self._mats_grad_ptr, self.model.matsLen() + 1)
 
     def loss(self):
         return self.wrap(self._loss_ptr, 1)
@@ -108,11 +108,17 @@ class GpuOps:
                                                w.data_ptr(), w.numel(), targets.data_ptr(),
                                                grad_rows.data_ptr(), grad_w.data_ptr(), self.stream_ptr))
 
+    def segsum_sort(self, recv_ids, unique):
+        """Owner-side sort of the received ids on the side stream (overlaps the dense math)."""
+        L.check(self.lib.b200rec_segsum_sort_dev(self.model.handle, self.K, recv_ids.numel(), 32, 1,
+                                                 recv_ids.data_ptr(), unique.data_ptr(),
+                                                 self.n_unique.data_ptr(), self.stream_ptr))
+
     def segsum(self, recv_ids, grad_rows, grad_w, unique, G, gw):
-        L.check(self.lib.b200rec_segsum_dev(self.model.handle, self.K, recv_ids.numel(), 32, 1,
-                                            recv_ids.data_ptr(), grad_rows.data_ptr(), grad_w.data_ptr(),
-                                            unique.data_ptr(), G.data_ptr(), gw.data_ptr(),
-                                            self.n_unique.data_ptr(), self.stream_ptr))
+        L.check(self.lib.b200rec_segsum_reduce_dev(self.model.handle, self.K, recv_ids.numel(), 32, 1,
+                                                   recv_ids.data_ptr(), grad_rows.data_ptr(),
+                                                   grad_w.data_ptr(), unique.data_ptr(), G.data_ptr(),
+                                                   gw.data_ptr(), self.n_unique.data_ptr(), self.stream_ptr))
 
     def apply_sgd(self, unique, G, gw, lr):
         L.check(self.lib.b200rec_table_apply_sgd_dev(self.table.handle, unique.numel(),
@@ -153,14 +159,12 @@ class ShardedParRecModel:
         with o.stream_ctx():
             o.plan(feats, self.send_ids, self.dst)                       # bucket ids by owner
             self._a2a(self.recv_ids, self.send_ids)                      # pull request  (ids -> owners)
+            o.segsum_sort(self.recv_ids, self.unique)                    # owner-side sort, side stream
             o.lookup(self.recv_ids, self.rows, self.w)                   # owner-side gather
             self._a2a(self.got_rows, self.rows)                          # rows back
             self._a2a(self.got_w, self.w)
             o.step_rows(self.dst, self.got_rows, self.got_w, targets, self.grad_rows, self.grad_w)
-            gb, gm = o.dense_grads()
-            work = [self.dist.all_reduce(gb, group=self.group, async_op=True)]
-            if gm is not None:
-                work.append(self.dist.all_reduce(gm, group=self.group, async_op=True))
+            work = [self.dist.all_reduce(o.dense_grads(), group=self.group, async_op=True)]
             self._a2a(self.recv_grad_rows, self.grad_rows)               # push  (grads -> owners)
             self._a2a(self.recv_grad_w, self.grad_w)
             o.segsum(self.recv_ids, self.recv_grad_rows, self.recv_grad_w, self.unique, self.G, self.gw)
@@ -176,6 +180,7 @@ class ShardedParRecModel:
 def bench(args, pkg):
     import json
     import os
+    import sys
     import time
 
     import torch
@@ -297,7 +302,11 @@ def bench(args, pkg):
                                                 "dense_allreduce": (model.matsLen() + 1) * 4},
             "kernels_rank0_ms_per_step": {k: round(v, 5) for k, v in sorted(by_phase.items(), key=lambda kv: -kv[1])},
         }
-        print(json.dumps(out))
-    model.close()
-    table.close()
+        print(json.dumps(out), flush=True)
+    # torch's caching allocator still holds blocks last used on the library's stream; leave the teardown
+    # to process exit instead of destroying that stream under it
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)

@@ -33,8 +33,7 @@ class NumpyOps:
         self.wt = synth.wtable_rows(SEED_PARAMS, gid)
         self.model = refport.Model(KIND, F, K, FC, CIN)
         self.mats = synth.init_mats(SEED_PARAMS, self.model.mats_size())
-        self.gb = torch.zeros(1)
-        self.gm = torch.zeros(self.mats.size)
+        self.dense = torch.zeros(self.mats.size + 1)   # [mats grad | bias grad], like the library
         self.n_unique = 0
         self.int32, self.float32 = torch.int32, torch.float32
 
@@ -76,11 +75,14 @@ class NumpyOps:
         self.loss = self.model.backward(B, index, wn, bias, emb, mats, targets.numpy())
         grad_rows.numpy().reshape(-1, K)[d] = emb.reshape(-1, K)
         grad_w.numpy()[d] = wn
-        self.gb.numpy()[:] = bias
-        self.gm.numpy()[:] = mats
+        self.dense.numpy()[:-1] = mats
+        self.dense.numpy()[-1] = bias[0]
 
     def dense_grads(self):
-        return self.gb, self.gm
+        return self.dense
+
+    def segsum_sort(self, recv_ids, unique):
+        pass
 
     def segsum(self, recv_ids, grad_rows, grad_w, unique, G, gw):
         ids = recv_ids.numpy()
@@ -153,8 +155,8 @@ def run(rank, world, backend, device=None):
     uniq = sh.unique[:U].cpu().numpy()
     G = sh.G[:U * K].cpu().numpy().reshape(U, K)
     gw = sh.gw[:U].cpu().numpy()
-    gb, gm = ops.dense_grads()
-    gb, gm = float(gb.cpu()[0]), gm.cpu().numpy()
+    dense = ops.dense_grads().cpu().numpy()
+    gb, gm = float(dense[-1]), dense[:-1]
     tot_e, tot_w, egm, egb, losses = expected(synth, refport, spec)
     # ids this rank owns, ascending local row
     owned = sorted(fid for fid in tot_e if spec.owner([fid])[0] == rank)
@@ -196,3 +198,5 @@ if __name__ == "__main__":
     print(f"rank {rank}/{world}: sharded step ok, {u} owned distinct rows", flush=True)
     dist.barrier()
     dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
