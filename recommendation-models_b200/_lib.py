@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200rec.so")
+LIB_PATH = os.environ.get("B200REC_LIB") or os.path.join(HERE, "libb200rec.so")
 
 OK, ERR_ARG, ERR_SHAPE, ERR_INDEX, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 KINDS = {"lr": 0, "fm": 1, "deepfm": 2, "xdeepfm": 3, "dcn": 4, "pnn": 5}

@@ -46,6 +46,16 @@ def _compile(src, force, hdr_m):
     return obj, True
 
 
+def build_trace():
+    """Debug variant with the in-kernel pipeline timeline (tc_gemm.cuh: B200_TC_TRACE)."""
+    out = os.path.join(HERE, "libb200rec_trace.so")
+    cmd = [NVCC, *FLAGS, "-DB200_TC_TRACE", "-shared", "-o", out, *_sources()]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    return out
+
+
 def build(force=False, verbose=True):
     os.makedirs(OBJ, exist_ok=True)
     hdr_m = _deps_mtime()
@@ -66,4 +76,7 @@ def build(force=False, verbose=True):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    if "--trace" in sys.argv:
+        print(build_trace())
+    else:
+        build(force="--force" in sys.argv)

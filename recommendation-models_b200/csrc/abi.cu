@@ -30,6 +30,7 @@ void set_error(const char* fmt, ...) {
 int g_default_gemm_mode = 1;  // 3xTF32 tcgen05 wherever a tensor-core kernel exists
 thread_local Prof* tl_prof = nullptr;
 thread_local const char* tl_tag = nullptr;
+thread_local DevBuf* tl_pack = nullptr;
 
 void Prof::begin(const char* name, cudaStream_t st) {
   if (n >= kMax) return;
@@ -982,7 +983,8 @@ int b200rec_table_apply_sgd_dev(b200rec_table_t t, int64_t n_unique_cap, const i
 // Host arrays in/out; one call = upload, kernel(s), download on the calling thread's stream.
 struct OpCtx {
   cudaStream_t st = cudaStreamPerThread;
-  ScopedBuf err;
+  ScopedBuf err, pack;
+  PackScope pack_scope{&pack};
   int init() {
     B200_TRY(err.reserve(16));
     B200_CUDA(cudaMemsetAsync(err.p, 0, 16, st));

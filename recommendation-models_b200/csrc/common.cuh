@@ -51,6 +51,14 @@ struct Prof {
 };
 extern thread_local Prof* tl_prof;
 extern thread_local const char* tl_tag;
+struct DevBuf;
+// weight-pack scratch of the handle / call that is currently running on this thread (tc_gemm.cu)
+extern thread_local DevBuf* tl_pack;
+struct PackScope {
+  DevBuf* prev;
+  explicit PackScope(DevBuf* b) : prev(tl_pack) { tl_pack = b; }
+  ~PackScope() { tl_pack = prev; }
+};
 struct ProfTag {  // names the phase the following launches belong to
   const char* prev;
   explicit ProfTag(const char* t) : prev(tl_tag) { tl_tag = t; }

@@ -58,25 +58,43 @@ __global__ void colsum_stage1(int M, int N, const float* g, int rows_per_chunk, 
   if (n >= N) return;
   const int r0 = c * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
   float s = 0.f;
-  for (int r = r0; r < r1; ++r) s += g[(long long)r * N + n];
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {  // 8 independent loads in flight, added in row order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = g[(long long)(r + u) * N + n];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; r < r1; ++r) s += g[(long long)r * N + n];
   part[(long long)c * N + n] = s;
 }
+// one warp per column: lanes stride over the chunks, then a fixed xor tree (deterministic)
 __global__ void colsum_stage2(int N, int chunks, const float* part, float scale, bool accumulate,
                               float* out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (n >= N) return;
   float s = 0.f;
-  for (int c = 0; c < chunks; ++c) s += part[(long long)c * N + n];
-  s *= scale;
-  out[n] = accumulate ? out[n] + s : s;
+  for (int c = lane; c < chunks; c += 32) s += part[(long long)c * N + n];
+  s = warp_sum(s);
+  if (lane == 0) {
+    s *= scale;
+    out[n] = accumulate ? out[n] + s : s;
+  }
 }
 
 int colsum(int M, int N, const float* g, float scale, bool accumulate, float* out, float* part,
            cudaStream_t st) {
-  const int chunks = 64;
+  // row chunks of >= 32 rows, at most COLSUM_CHUNKS of them: enough CTAs to pull HBM bandwidth
+  int chunks = M / 32;
+  if (chunks > COLSUM_CHUNKS) chunks = COLSUM_CHUNKS;
+  if (chunks < 1) chunks = 1;
+  const int rows_per_chunk = cdiv(M, chunks);
+  chunks = cdiv(M, rows_per_chunk);
   dim3 g1(cdiv(N, 128), chunks);
-  B200_LAUNCH(colsum_stage1, g1, 128, 0, st, M, N, g, cdiv(M, chunks), part);
-  B200_LAUNCH(colsum_stage2, cdiv(N, 128), 128, 0, st, N, chunks, part, scale, accumulate, out);
+  B200_LAUNCH(colsum_stage1, g1, 128, 0, st, M, N, g, rows_per_chunk, part);
+  B200_LAUNCH(colsum_stage2, cdiv((long long)N * 32, 256), 256, 0, st, N, chunks, part, scale, accumulate, out);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -89,7 +107,7 @@ int linear_bwd_params(int M, int N, int K, const float* x, const float* gy, floa
   // gw[N,K] = gy^T x : output N x K, contraction over the batch M
   const int splits = pick_splits(N, K, M);
   const long long MN = (long long)N * K;
-  B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)64 * N) * sizeof(float)));
+  B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)COLSUM_CHUNKS * N) * sizeof(float)));
   float* ws = scratch.as<float>();
   B200_TRY(gemm_simt(N, K, M, splits, ColMajorOp{gy, N}, ColMajorOp{x, K}, EpPartial{ws, MN, K},
                      st));
@@ -155,12 +173,16 @@ __global__ void wcolsum_stage1(int M, int K, const float* d, const float* x, int
 }
 int wcolsum(int M, int K, const float* d, const float* x, int ldx, float* gw, DevBuf& scratch,
             cudaStream_t st) {
-  const int chunks = 64;
+  int chunks = M / 32;
+  if (chunks > COLSUM_CHUNKS) chunks = COLSUM_CHUNKS;
+  if (chunks < 1) chunks = 1;
+  const int rows_per_chunk = cdiv(M, chunks);
+  chunks = cdiv(M, rows_per_chunk);
   B200_TRY(scratch.reserve((size_t)chunks * K * sizeof(float)));
   float* part = scratch.as<float>();
   dim3 g1(cdiv(K, 128), chunks);
-  B200_LAUNCH(wcolsum_stage1, g1, 128, 0, st, M, K, d, x, ldx, cdiv(M, chunks), part);
-  B200_LAUNCH(colsum_stage2, cdiv(K, 128), 128, 0, st, K, chunks, part, 1.0f, false, gw);
+  B200_LAUNCH(wcolsum_stage1, g1, 128, 0, st, M, K, d, x, ldx, rows_per_chunk, part);
+  B200_LAUNCH(colsum_stage2, cdiv((long long)K * 32, 256), 256, 0, st, K, chunks, part, 1.0f, false, gw);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }

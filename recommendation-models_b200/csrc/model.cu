@@ -127,7 +127,7 @@ void b200rec_model_s::destroy() {
   if (side) cudaStreamSynchronize(side);
   DevBuf* bufs[] = {&p_bias, &p_mats, &gmats, &scal, &d_feats, &d_targets, &d_index, &X, &wnz, &S,
                     &first, &second, &branch, &preds, &dlogit, &dXd, &dw, &gA, &gB, &scratch,
-                    &uniq, &G, &gwU, &x0, &gx0, &gy, &gnA, &gnB, &pooled, &gpooled, &xL, &s_cross,
+                    &uniq, &G, &gwU, &wpack, &x0, &gx0, &gy, &gnA, &gnB, &pooled, &gpooled, &xL, &s_cross,
                     &g_xL, &ip, &gip, &pre, &hbuf, &stage_a, &stage_b};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : acts) b.release();
@@ -238,6 +238,7 @@ int b200rec_model_s::mlp_head_backward(int B, const float* x_in, const float* ma
 
 // ---- the whole forward (+ backward) on device buffers -------------------------------------------
 int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
+  PackScope pack_scope(&wpack);
   const int B = a.B;
   const long long nnz = a.nnz;
   const bool train = a.targets != nullptr;

@@ -69,7 +69,7 @@ struct b200rec_model_s {
   DevBuf p_bias, p_mats, gmats, scal;
   DevBuf d_feats, d_targets, d_index, stage_a, stage_b;
   DevBuf X, wnz, S, first, second, branch, preds, dlogit, dXd, dw, gA, gB, scratch;
-  DevBuf uniq, G, gwU;
+  DevBuf uniq, G, gwU, wpack;
   DevBuf x0, gx0, gy, gnA, gnB, pooled, gpooled;
   DevBuf xL, s_cross, g_xL;
   DevBuf ip, gip, pre, hbuf;

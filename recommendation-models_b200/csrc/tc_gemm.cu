@@ -19,34 +19,72 @@ static int pick_bn(int N) {
   return bn < 16 ? 16 : bn;
 }
 
-template <class AP, class BP, class Sched, class Ep>
-static int launch(const char* name, int M, int N, int bn, int n_stride, int n_valid, int n_tiles, int splits,
-                  Sched sched, AP ap, BP bp, Ep ep, int passes, cudaStream_t st) {
-  if (M <= 0 || N <= 0) return B200REC_OK;
-  dim3 grid(n_tiles, cdiv(M, BM), splits);
+template <class AP, class BP, class Sched, class Ep, bool PACKED>
+static int launch_ws(const char* name, dim3 grid, int smem, int M, int N, int bn, int n_stride, int n_valid,
+                     Sched sched, AP ap, BP bp, const char* blob, Ep ep, int passes, cudaStream_t st) {
   const int kc = passes == 3 ? KC_PRECISE : 0;
+  const int smem_max = ws_smem_bytes(PACKED, PACKED ? 208 : 256);
   if (passes == 3) {
-    auto k = gemm_tc_kernel<AP, BP, Sched, Ep, 3>;
+    auto k = gemm_ws_kernel<AP, BP, Sched, Ep, 3, PACKED>;
     static bool attr_done = false;
     if (!attr_done) {
-      B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       attr_done = true;
     }
-    B200_LAUNCH_NAMED(name, k, grid, THREADS, SMEM_BYTES, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, ep);
+    B200_LAUNCH_NAMED(name, k, grid, WS_THREADS, smem, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, blob, ep);
   } else {
-    auto k = gemm_tc_kernel<AP, BP, Sched, Ep, 1>;
+    auto k = gemm_ws_kernel<AP, BP, Sched, Ep, 1, PACKED>;
     static bool attr_done = false;
     if (!attr_done) {
-      B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       attr_done = true;
     }
-    B200_LAUNCH_NAMED(name, k, grid, THREADS, SMEM_BYTES, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, ep);
+    B200_LAUNCH_NAMED(name, k, grid, WS_THREADS, smem, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, blob, ep);
   }
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }
 
+// both operands produced by the CTA's producer warps (activation x activation contractions)
+template <class AP, class BP, class Sched, class Ep>
+static int launch(const char* name, int M, int N, int bn, int n_stride, int n_valid, int n_tiles, int splits,
+                  Sched sched, AP ap, BP bp, Ep ep, int passes, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return B200REC_OK;
+  dim3 grid(n_tiles, cdiv(M, BM), splits);
+  return launch_ws<AP, BP, Sched, Ep, false>(name, grid, ws_smem_bytes(false, bn), M, N, bn, n_stride, n_valid,
+                                             sched, ap, bp, nullptr, ep, passes, st);
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// the 4x4 register-transpose path of ColProd needs 16-B aligned rows of 4
+static bool colvec(const float* p, long long ld, int rows_total) {
+  return ld % 4 == 0 && rows_total % 4 == 0 && aligned16(p);
+}
+
+// widest tile <= 208 (3-deep B ring fits) that splits N evenly
+static int pick_bn_packed(int N) {
+  const int tiles = (N + 207) / 208;
+  int bn = round16((N + tiles - 1) / tiles);
+  return bn < 16 ? 16 : bn;
+}
+
+// pack the weight operand into stage images, then run the bulk-copy GEMM on it
+template <class AP, class BP, class Sched, class Ep>
+static int launch_packed(const char* name, int M, int N, int bn, int n_stride, int n_valid, int n_tiles,
+                         int nkb, Sched sched, AP ap, BP bp, Ep ep, int passes, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return B200REC_OK;
+  B200_REQUIRE(tl_pack, B200REC_ERR_STATE, "no weight-pack buffer bound to this thread");
+  const size_t blob_bytes = (size_t)n_tiles * nkb * 2 * bn * 128;
+  B200_TRY(tl_pack->reserve(blob_bytes));
+  char* blob = tl_pack->as<char>();
+  {
+    dim3 pg(n_tiles, nkb < 64 ? nkb : 64);
+    B200_LAUNCH_NAMED("tc_pack_weights", (pack_b_kernel<BP, Sched>), pg, THREADS, 0, st, bn, n_stride, sched, bp, blob);
+  }
+  dim3 grid(n_tiles, cdiv(M, BM), 1);
+  return launch_ws<AP, BP, Sched, Ep, true>(name, grid, ws_smem_bytes(true, bn), M, N, bn, n_stride, n_valid,
+                                            sched, ap, bp, (const char*)blob, ep, passes, st);
+}
 
 }  // namespace tc
 
@@ -55,32 +93,34 @@ using namespace tc;
 // y[M,N] = act(x[M,K] W[N,K]^T + b)
 int tc_linear_fwd(int M, int N, int K, const float* x, const float* w, const float* b, bool relu,
                   float* y, int passes, cudaStream_t st) {
-  const int bn = pick_bn(N);
+  const int bn = pick_bn_packed(N);
   KPlain s{0, K, K};
   RowProd<4, KPlain> ap{x, K, M, BM, (K % 4 == 0) && aligned16(x)};
   RowProd<8, KPlain> bp{w, K, N, bn, (K % 4 == 0) && aligned16(w)};
-  return launch("tc_linear_fwd", M, N, bn, bn, bn, cdiv(N, bn), 1, s, ap, bp, tc::EpBiasAct{y, N, b, relu}, passes, st);
+  return launch_packed("tc_linear_fwd", M, N, bn, bn, bn, cdiv(N, bn), cdiv(K, BK), s, ap, bp,
+                       tc::EpBiasAct{y, N, b, relu}, passes, st);
 }
 
 // PNN product layer: h = relu(prev + ip Wp^T + c0)
 int tc_pnn_lp_fwd(int B, int P, int O, const float* ip, const float* wp, const float* prev,
                   const float* c0, float* h, int passes, cudaStream_t st) {
-  const int bn = pick_bn(O);
+  const int bn = pick_bn_packed(O);
   KPlain s{0, P, P};
   RowProd<4, KPlain> ap{ip, P, B, BM, (P % 4 == 0) && aligned16(ip)};
   RowProd<8, KPlain> bp{wp, P, O, bn, (P % 4 == 0) && aligned16(wp)};
-  return launch("tc_pnn_lp_fwd", B, O, bn, bn, bn, cdiv(O, bn), 1, s, ap, bp, tc::EpAddBiasRelu2{h, O, prev, c0}, passes, st);
+  return launch_packed("tc_pnn_lp_fwd", B, O, bn, bn, bn, cdiv(O, bn), cdiv(P, BK), s, ap, bp,
+                       tc::EpAddBiasRelu2{h, O, prev, c0}, passes, st);
 }
 
 // gx[M,K] = (gy[M,N] W[N,K]) (* mask > 0) (+ gx)
 int tc_linear_bwd_input(int M, int N, int K, const float* gy, const float* w, const float* mask,
                         float* gx, bool accumulate, int passes, cudaStream_t st) {
-  const int bn = pick_bn(K);
+  const int bn = pick_bn_packed(K);
   KPlain s{0, N, N};
   RowProd<4, KPlain> ap{gy, N, M, BM, (N % 4 == 0) && aligned16(gy)};
-  ColProd<256, KPlain> bp{w, K, K, bn};   // B(k_out, n) = W[n*K + k_out]
-  return launch("tc_linear_dx", M, K, bn, bn, bn, cdiv(K, bn), 1, s, ap, bp, tc::EpMaskAcc{gx, K, mask, K, accumulate},
-                passes, st);
+  ColProd<256, KPlain> bp{w, K, K, bn, colvec(w, K, K)};   // B(k_out, n) = W[n*K + k_out]
+  return launch_packed("tc_linear_dx", M, K, bn, bn, bn, cdiv(K, bn), cdiv(N, BK), s, ap, bp,
+                       tc::EpMaskAcc{gx, K, mask, K, accumulate}, passes, st);
 }
 
 // gw[N,K] (+)= scale * gy[M,N]^T x[M,K]  (split-K over the batch, fixed-order reduce) ; gb likewise
@@ -96,11 +136,11 @@ int tc_linear_bwd_params(int M, int N, int K, const float* x, const float* gy, f
   int k_chunk = ((cdiv(M, splits) + BK - 1) / BK) * BK;
   splits = cdiv(M, k_chunk);
   const long long MN = (long long)N * K;
-  B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)64 * N) * sizeof(float)));
+  B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)COLSUM_CHUNKS * N) * sizeof(float)));
   float* ws = scratch.as<float>();
   KPlain s{0, M, k_chunk};
-  ColProd<128, KPlain> ap{gy, N, N, BM};  // A(n, m) = gy[m*N + n]
-  ColProd<256, KPlain> bp{x, K, K, bn};   // B(k, m) = x[m*K + k]
+  ColProd<128, KPlain> ap{gy, N, N, BM, colvec(gy, N, N)};  // A(n, m) = gy[m*N + n]
+  ColProd<256, KPlain> bp{x, K, K, bn, colvec(x, K, K)};   // B(k, m) = x[m*K + k]
   B200_TRY(launch("tc_linear_dW", N, K, bn, bn, bn, cdiv(K, bn), splits, s, ap, bp, tc::EpPartial{ws, MN, K}, passes, st));
   B200_TRY(splitk_reduce(ws, splits, MN, scale, accumulate, gw, st));
   if (gb) B200_TRY(colsum(M, N, gy, scale, accumulate, gb, ws + (size_t)splits * MN, st));
@@ -109,17 +149,18 @@ int tc_linear_bwd_params(int M, int N, int K, const float* x, const float* gy, f
 
 // ---- CIN --------------------------------------------------------------------------------------------
 bool tc_cin_supported(int F, int H, int C) {
-  return F <= CinZProd::MAX_F && H <= MAX_BN && C >= 1;
+  return F >= 1 && H >= 1 && H <= 208 && C >= 1;   // dx0 runs one N tile per field: H must fit a 208-wide tile
 }
 
 // x_out[r,c] = relu(sum_{i,j} x0[r,i] x_in[r,j] W[c, i*H+j] + b[c])
 int tc_cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
                      const float* b, float* x_out, int passes, cudaStream_t st) {
-  const int bn = pick_bn(C);
-  KCin s{F, H, 0};
-  CinZProd ap{x0, x_in, R, (H % 4 == 0) && aligned16(x_in)};
+  const int bn = pick_bn_packed(C);
+  KCin s{F, H, 0, H};
+  CinZProd ap{x0, x_in, R, (H % 4 == 0) && aligned16(x_in), false};
   RowProd<8, KCin> bp{W, (long long)F * H, C, bn, (H % 4 == 0) && aligned16(W)};
-  return launch("tc_cin_fwd", R, C, bn, bn, bn, cdiv(C, bn), 1, s, ap, bp, tc::EpBiasAct{x_out, C, b, true}, passes, st);
+  return launch_packed("tc_cin_fwd", R, C, bn, bn, bn, cdiv(C, bn), F * cdiv(H, BK), s, ap, bp,
+                       tc::EpBiasAct{x_out, C, b, true}, passes, st);
 }
 
 // layer backward (gy already ReLU-masked):
@@ -140,31 +181,39 @@ int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x
     int k_chunk = ((cdiv(R, splits) + BK - 1) / BK) * BK;
     splits = cdiv(R, k_chunk);
     const long long MN = (long long)C * FH;
-    B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)64 * C) * sizeof(float)));
+    B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)COLSUM_CHUNKS * C) * sizeof(float)));
     float* ws = scratch.as<float>();
     KPlain s{0, R, k_chunk};
-    CinZtProd ap{x0, x_in, F, H};
-    ColProd<256, KPlain> bp{gy, C, C, bn};   // B(c, r) = gy[r*C + c]
+    CinZtProd ap{x0, x_in, F, H, (H % 4 == 0) && aligned16(x_in)};
+    ColProd<256, KPlain> bp{gy, C, C, bn, colvec(gy, C, C)};   // B(c, r) = gy[r*C + c]
     B200_TRY(launch("tc_cin_dW", FH, C, bn, bn, bn, cdiv(C, bn), splits, s, ap, bp, tc::EpPartialT{ws, MN, FH}, passes, st));
     B200_TRY(splitk_reduce(ws, splits, MN, 1.0f, false, gW, st));
     B200_TRY(colsum(R, C, gy, 1.0f, false, gb, ws + (size_t)splits * MN, st));
   }
   {  // ---- gx0: per field i, T_i[r, j] = sum_c gy[r,c] W[c, i*H + j];  gx0[r,i] += <T_i[r,:], x_in[r,:]>
+     //      (one N tile per field: full-width MMAs; T = dZ stays in TMEM, the x tile is staged in smem)
     const int bn = round16(H);
     KPlain s{0, C, C};
     RowProd<4, KPlain> ap{gy, C, R, BM, (C % 4 == 0) && aligned16(gy)};
-    ColProd<256, KPlain> bp{W, FH, FH, bn};   // B(n = i*H + j, c) = W[c*FH + n]
-    B200_TRY(launch("tc_cin_dx0", R, FH, bn, H, H, F, 1, s, ap, bp, tc::EpRowDot{x_in, H, gx0, F}, passes, st));
+    ColProd<256, KPlain> bp{W, FH, FH, bn, colvec(W, FH, FH) && H % 4 == 0};   // B(n = i*H + j, c) = W[c*FH + n]
+    B200_TRY(launch_packed("tc_cin_dx0", R, FH, bn, H, H, F, cdiv(C, BK), s, ap, bp, tc::EpRowDot{x_in, H, gx0, F},
+                           passes, st));
   }
   {  // ---- gx_in[r, j] = sum_{(i,c)} (x0[r,i] gy[r,c]) W[c, i*H + j]
-    const int bn = pick_bn(H);
-    KCin s{F, C, H};
-    CinZProd ap{x0, gy, R, (C % 4 == 0) && aligned16(gy)};
-    ColProd<256, KCin> bp{W, FH, H, bn};      // B(j, (i,c)) = W[c*FH + i*H + j]; tile rows bounded by H
-    B200_TRY(launch("tc_cin_dx", R, H, bn, bn, bn, cdiv(H, bn), 1, s, ap, bp, tc::EpMaskAcc{gx_in, H, nullptr, 0, gx_in_acc},
-                    passes, st));
+    const int bn = pick_bn_packed(H);
+    KCin s{F, C, H, C};
+    CinZProd ap{x0, gy, R, (C % 4 == 0) && aligned16(gy), false};
+    ColProd<256, KCin> bp{W, FH, H, bn, colvec(W, FH, H) && H % 4 == 0};   // B(j, (i,c)) = W[c*FH + i*H + j]
+    B200_TRY(launch_packed("tc_cin_dx", R, H, bn, bn, bn, cdiv(H, bn), F * cdiv(C, BK), s, ap, bp,
+                           tc::EpMaskAcc{gx_in, H, nullptr, 0, gx_in_acc}, passes, st));
   }
   return B200REC_OK;
 }
 
 }  // namespace b200rec
+
+#ifdef B200_TC_TRACE
+extern "C" int b200rec_debug_tc_trace(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, b200rec::tc::g_tc_trace, sizeof(long long) * (size_t)n);
+}
+#endif

@@ -16,14 +16,16 @@
 // and D += Ahi*Bhi + Alo*Bhi + Ahi*Blo: the dropped lo*lo term is 2^-22 relative.  The producers
 // write both parts, so the split costs two ALU ops per element and no extra memory pass.
 //
-// Structure (one CTA = one 128 x BN output tile, BN <= 256, 256 threads, 1 CTA / SM):
-//   * 2-stage ring of {A_hi, A_lo, B_hi, B_lo} tiles, 128 B (32 fp32) of K per row per stage
-//   * all 8 warps produce stage s (global -> registers one stage ahead -> split -> swizzled STS),
-//     fence.proxy.async, __syncthreads; one elected thread issues up to 4 K-steps x 3 passes of
-//     tcgen05.mma.cta_group::1.kind::tf32 and tcgen05.commit's the stage's "empty" mbarrier;
-//     production of stage s+1 overlaps the MMAs of stage s (the tensor core runs asynchronously)
-//   * epilogue: tcgen05.ld 32x32b.x16 (thread = accumulator row), functor, vectorised stores.
+// Structure (one CTA = one 128 x BN output tile, BN <= 256, 1 CTA / SM, warp-specialised; see
+// gemm_ws_kernel below): a 2-stage ring of {A_hi, A_lo} tiles filled by 8 producer warps
+// (global -> registers one or two stages ahead -> split -> swizzled STS, 128 B = 32 fp32 of K per
+// row per stage), a B ring that is either filled by the same warps or -- for weight operands --
+// fetched as pre-packed stage images with cp.async.bulk, and one MMA thread issuing up to
+// 4 K-steps x 3 passes of tcgen05.mma.cta_group::1.kind::tf32 per stage; mbarriers only, no
+// __syncthreads in the main loop; epilogue tcgen05.ld 32x32b.x16 (thread = accumulator row).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200rec {
@@ -40,8 +42,6 @@ constexpr int TMEM_S = 256;
 constexpr int A_TILE_BYTES = BM * 128;        // 16 KB
 constexpr int B_TILE_BYTES = MAX_BN * 128;    // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 KB
-constexpr int EXTRA_BYTES = 24 * 1024;        // producer scratch (CIN keeps its x0 tile here)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EXTRA_BYTES + 1024 /*align*/ + 64 /*barriers*/;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -50,17 +50,36 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  // a pipeline bug must fail the launch, not hang the GPU: trap after ~2 s of waiting
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
+  if (mbar_try(bar, parity)) return;   // fast path: no clock reads
+  if (mbar_try(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, no tensor map), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -209,8 +228,9 @@ struct KPlain {  // kb-th block of [k_begin, k_end); split-K over blockIdx.z
 // Stages walk j-blocks of 32 in the OUTER loop and i in the INNER loop, so the producer keeps its
 // x[r, j-block] segment in registers across all F fields (x is read once, not F times).
 struct KCin {
-  int F, H;   // H = width of the second factor (x^{l-1} in the forward, dY in the dx GEMM)
+  int F, H;   // F = length of the first factor, H = width of the second factor
   int Hp;     // dx GEMM only: row stride of field i inside W's columns (= H_{l-1})
+  long long KS;  // row-major B: offset of first-factor index i along the contraction (H fwd, F*H dx0)
   __device__ __forceinline__ KCin for_split(int) const { return *this; }
   __device__ __forceinline__ int njb() const { return (H + BK - 1) / BK; }
   __device__ __forceinline__ int nkb() const { return F * njb(); }
@@ -218,7 +238,7 @@ struct KCin {
   __device__ __forceinline__ int jb(int kb) const { return kb / F; }
   __device__ __forceinline__ int kvalid(int kb) const { return min(BK, H - jb(kb) * BK); }
   // forward: W[c, i*H + j]  (row-major over the contraction)
-  __device__ __forceinline__ long long row_koff(int kb) const { return (long long)fi(kb) * H + jb(kb) * BK; }
+  __device__ __forceinline__ long long row_koff(int kb) const { return (long long)fi(kb) * KS + jb(kb) * BK; }
   // dx: B(n = j', k = (i, c)) = W[c, i*Hp + j']  ->  [k][n] matrix with row stride ld = F*Hp
   __device__ __forceinline__ long long col_off(int kb, long long ld) const {
     return (long long)jb(kb) * BK * ld + (long long)fi(kb) * Hp;
@@ -238,8 +258,18 @@ struct RowProd {
   Sched s;
   int row0, tid;
   float4 reg[MAXT];
+  float4 reg2[MAXT];   // second prefetch slot (packed-B kernel: loads fly two stages ahead)
+  template <int SLOT> __device__ __forceinline__ void prefetch2(int kb) {
+    if constexpr (SLOT == 1) load(kb, reg2); else load(kb, reg);
+  }
+  template <int SLOT> __device__ __forceinline__ void store2(int, char* hi, char* lo) {
+    if constexpr (SLOT == 1) put(reg2, hi, lo); else put(reg, hi, lo);
+  }
+  static constexpr int DIST = 2;
   __device__ __forceinline__ void init(char*, int r0, int t) { row0 = r0; tid = t; }
-  __device__ __forceinline__ void prefetch(int kb) {
+  __device__ __forceinline__ void prefetch(int kb) { load(kb, reg); }
+  __device__ __forceinline__ void store(int, char* hi, char* lo) { put(reg, hi, lo); }
+  __device__ __forceinline__ void load(int kb, float4 (&dst)[MAXT]) {
     const int kv = s.kvalid(kb);
     const long long ko = s.row_koff(kb);
 #pragma unroll
@@ -258,31 +288,58 @@ struct RowProd {
           if (4 * c + 3 < kv) v.w = __ldg(src + 3);
         }
       }
-      reg[t] = v;
+      dst[t] = v;
     }
   }
-  __device__ __forceinline__ void store(int, char* hi, char* lo) {
+  __device__ __forceinline__ void put(const float4 (&src)[MAXT], char* hi, char* lo) {
 #pragma unroll
     for (int t = 0; t < MAXT; ++t) {
       const int q = tid + t * THREADS;
       const int r = q >> 3, c = q & 7;
-      if (r < tile_rows) split_store(hi, lo, swz(r, c), reg[t]);
+      if (r < tile_rows) split_store(hi, lo, swz(r, c), src[t]);
     }
   }
 };
 
 // value(r, kk) = p[sched.col_off(kb, ld) + kk * ld + r]    (tile rows contiguous in memory: the
 // producer transposes while it stores).  ROWS = 128 or 256 (power of two >= tile rows).
+// vec path (ld % 4 == 0, 16-B aligned, rows_total % 4 == 0): a thread loads a 4 (kk) x 4 (rows) block
+// with four 128-bit loads and transposes it in registers into the four rows' 16-B chunks -- 4x fewer
+// load instructions than the element-wise path.
 template <int ROWS, class Sched>
 struct ColProd {
-  static constexpr int MAXT = ROWS * 8 / THREADS;
-  const float* p; long long ld; int rows_total; int tile_rows;
+  static constexpr int MAXT = ROWS * 8 / THREADS;   // float4 registers per thread per stage
+  static constexpr int NIT = ROWS * 2 / THREADS;    // vec path: 4x4 blocks per thread
+  const float* p; long long ld; int rows_total; int tile_rows; bool vec;
   Sched s;
   int row0, tid;
   float4 reg[MAXT];
+  static constexpr int DIST = 1;
+  template <int SLOT> __device__ __forceinline__ void prefetch2(int kb) { prefetch(kb); }
+  template <int SLOT> __device__ __forceinline__ void store2(int kb, char* hi, char* lo) { store(kb, hi, lo); }
   __device__ __forceinline__ void init(char*, int r0, int t) { row0 = r0; tid = t; }
   __device__ __forceinline__ void prefetch(int kb) {
     const int kv = s.kvalid(kb);
+    if (vec) {
+#pragma unroll
+      for (int t = 0; t < NIT; ++t) {
+        const int q = tid + t * THREADS;
+        const int c = q & 7, rg = q >> 3;
+        const int r = 4 * rg;
+        const bool rok = r < tile_rows && row0 + r < rows_total;
+        const float* src = p + s.col_off(kb, ld) + row0 + r;
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          v[u] = (rok && 4 * c + u < kv) ? __ldg(reinterpret_cast<const float4*>(src + (long long)(4 * c + u) * ld))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        reg[4 * t + 0] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+        reg[4 * t + 1] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+        reg[4 * t + 2] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+        reg[4 * t + 3] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+      }
+      return;
+    }
     const int r = tid & (ROWS - 1);
     const bool rok = r < tile_rows && row0 + r < rows_total;
     const float* src = p + s.col_off(kb, ld) + row0 + r;
@@ -300,6 +357,18 @@ struct ColProd {
     }
   }
   __device__ __forceinline__ void store(int, char* hi, char* lo) {
+    if (vec) {
+#pragma unroll
+      for (int t = 0; t < NIT; ++t) {
+        const int q = tid + t * THREADS;
+        const int c = q & 7, r = 4 * (q >> 3);
+        if (r < tile_rows) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_store(hi, lo, swz(r + e, c), reg[4 * t + e]);
+        }
+      }
+      return;
+    }
     const int r = tid & (ROWS - 1);
     if (r >= tile_rows) return;
 #pragma unroll
@@ -315,15 +384,19 @@ struct ColProd {
 // j-block lives in registers across the F inner stages.
 struct CinZProd {
   const float* x0; const float* x; int R; bool vec;   // vec: H % 4 == 0 (16-B aligned x rows)
+  bool x0_in_smem;                                     // false: no scratch smem (packed-B kernel)
   KCin s;
   int row0, tid;
   float* x0s;
   float4 xr[4];
   float x0v[4];
-  static constexpr int MAX_F = EXTRA_BYTES / (BM * 4);
+  static constexpr int DIST = 1;
+  template <int SLOT> __device__ __forceinline__ void prefetch2(int kb) { prefetch(kb); }
+  template <int SLOT> __device__ __forceinline__ void store2(int kb, char* hi, char* lo) { store(kb, hi, lo); }
   __device__ __forceinline__ void init(char* extra, int r0, int t) {
     row0 = r0; tid = t;
     x0s = reinterpret_cast<float*>(extra);
+    if (x0_in_smem)
     for (int idx = tid; idx < BM * s.F; idx += THREADS) {
       const int r = idx / s.F, i = idx - r * s.F;
       x0s[idx] = (row0 + r < R) ? __ldg(x0 + (long long)(row0 + r) * s.F + i) : 0.f;
@@ -354,7 +427,11 @@ struct CinZProd {
       }
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) x0v[t] = x0s[((tid >> 3) + 32 * t) * s.F + i];
+    for (int t = 0; t < 4; ++t) {
+      const int r = (tid >> 3) + 32 * t;
+      x0v[t] = x0_in_smem ? x0s[r * s.F + i]
+                          : (row0 + r < R ? __ldg(x0 + (long long)(row0 + r) * s.F + i) : 0.f);
+    }
   }
   __device__ __forceinline__ void store(int, char* hi, char* lo) {
 #pragma unroll
@@ -368,21 +445,46 @@ struct CinZProd {
 };
 
 // Z^T as the A operand of the weight-gradient GEMM:  A(m = (i, j), k = r) = x0[r, i] * x[r, j]
+// vec path (H % 4 == 0): a thread owns 4 consecutive m (= 4 consecutive j of one field) x 4 rows r:
+// four 128-bit loads of x, four scalar loads of x0, a register transpose, four 16-B chunk stores.
 struct CinZtProd {
-  const float* x0; const float* x; int F, H;
+  const float* x0; const float* x; int F, H; bool vec;
   KPlain s;
   int tid, im, jm;
   bool valid;
   float4 reg[4];
+  static constexpr int DIST = 1;
+  template <int SLOT> __device__ __forceinline__ void prefetch2(int kb) { prefetch(kb); }
+  template <int SLOT> __device__ __forceinline__ void store2(int kb, char* hi, char* lo) { store(kb, hi, lo); }
   __device__ __forceinline__ void init(char*, int r0, int t) {
     tid = t;
-    const int m = r0 + (t & 127);
+    const int m = vec ? r0 + 4 * (t >> 3) : r0 + (t & 127);
     valid = m < F * H;
     im = valid ? m / H : 0;
     jm = valid ? m - im * H : 0;
   }
   __device__ __forceinline__ void prefetch(int kb) {
     const int k0 = s.k0(kb);
+    if (vec) {
+      const int c = tid & 7;
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long r = k0 + 4 * c + u;
+        if (valid && r < s.k_end) {
+          const float a = __ldg(x0 + r * F + im);
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * H + jm));
+          v[u] = make_float4(a * xv.x, a * xv.y, a * xv.z, a * xv.w);
+        } else {
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      reg[0] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+      reg[1] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+      reg[2] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+      reg[3] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+      return;
+    }
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int c = (tid >> 7) + 2 * t;
@@ -396,6 +498,12 @@ struct CinZtProd {
     }
   }
   __device__ __forceinline__ void store(int, char* hi, char* lo) {
+    if (vec) {
+      const int c = tid & 7, r = 4 * (tid >> 3);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_store(hi, lo, swz(r + e, c), reg[e]);
+      return;
+    }
 #pragma unroll
     for (int t = 0; t < 4; ++t) split_store(hi, lo, swz(tid & 127, (tid >> 7) + 2 * t), reg[t]);
   }
@@ -474,153 +582,275 @@ struct EpAddBiasRelu2 {  // PNN: h = relu(prev + acc + c0)   (ProductEncoder.sca
       }
   }
 };
-// CIN input gradient w.r.t. x0:  out[m, tile] += sum_n acc[m, n] * x[m, n]   (one N tile per field)
+// CIN input gradient w.r.t. x0:  out[m, tile] += sum_n acc[m, n] * x[m, n]   (one N tile per field).
+// The CTA's x tile [128 x ncols] is staged in shared memory with coalesced loads (row stride ncols+1:
+// thread = row reads are then bank-conflict free); dZ = gy W never leaves TMEM.
 struct EpRowDot {
   const float* x; long long ldx; float* out; long long ldo;
   static constexpr bool kRowReduce = true;
-  __device__ __forceinline__ float dot(int m, int nl0, const float* v, int nv) const {
+  __device__ __forceinline__ void load_tile(float* xs, int m0, int M, int ncols, int tid) const {
+    const int stride = ncols + 1;
+    for (int idx = tid; idx < BM * ncols; idx += THREADS) {
+      const int r = idx / ncols, j = idx - r * ncols;
+      xs[r * stride + j] = (m0 + r < M) ? __ldg(x + (long long)(m0 + r) * ldx + j) : 0.f;
+    }
+  }
+  __device__ __forceinline__ float dot(const float* xs, int ncols, int rl, int nl0, const float* v, int nv) const {
     float s = 0.f;
-    const float* xr = x + (long long)m * ldx + nl0;
+    const float* xr = xs + rl * (ncols + 1) + nl0;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-      if (i < nv) s = fmaf(v[i], __ldg(xr + i), s);
+      if (i < nv) s = fmaf(v[i], xr[i], s);
     return s;
   }
   __device__ __forceinline__ void finish(int m, int tile, float s) const { out[(long long)m * ldo + tile] += s; }
 };
 
+// ====================================================================================================
+// Packed-B variant.  Wherever the B operand is a WEIGHT matrix (Linear forward / gradInput, CIN
+// forward, CIN dx0 / dx), it is split into hi / lo and laid out ONCE per step by pack_b_kernel as the
+// exact shared-memory images of the GEMM's stages: blob[(n_tile * nkb + kb)] = {hi image, lo image},
+// each bn x 128 B, already SWIZZLE_128B.  The GEMM then fetches a whole B stage with two
+// cp.async.bulk copies issued by one thread into a 3-deep ring (2-deep when bn > 208), completion by
+// mbarrier transaction count -- no registers, no ALU, and the copy of stage kb+1 is in flight for two
+// MMA stages.  The A operand stays software-produced (generated CIN outer product, or activations
+// split on the fly with loads two stages ahead).
+// ====================================================================================================
+constexpr int TCB_A_BYTES = STAGES * 2 * A_TILE_BYTES;   // 64 KB
+__host__ __device__ inline int tcb_nb(int bn) { return bn <= 208 ? 3 : 2; }
+__host__ __device__ inline int tcb_smem_bytes(int bn) {
+  return 1024 + TCB_A_BYTES + tcb_nb(bn) * 2 * bn * 128 + 128;
+}
 
-// ---- the kernel ---------------------------------------------------------------------------------------
-// grid = (n_tiles, m_tiles, splits).  Tile n covers columns [n * n_stride, n * n_stride + n_valid).
-template <class AP, class BP, class Sched, class Ep, int PASSES>
-__global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sched, AP ap, BP bp,
-               Ep ep) {
-  // kc > 0: the tensor core accumulates at most kc K-blocks (kc * 32 of K) into the TMEM chunk
-  // accumulator P; every chunk is then added into the running sum S (TMEM columns 256..) by the
-  // CUDA cores with round-to-nearest.  tcgen05.mma's own accumulation truncates toward zero, so the
-  // error of one long TMEM accumulation grows linearly with K (5.7e-5 at K = 8192, measured); chunked
-  // it stays at the fp32-blocked-sum level.  kc = 0: plain single accumulation.
+template <class BP, class Sched>
+__global__ void __launch_bounds__(THREADS) pack_b_kernel(int bn, int n_stride, Sched sched, BP bp, char* blob) {
+  const int nkb = sched.nkb();
+  const int tile = blockIdx.x;
+  bp.s = sched;
+  bp.init(nullptr, tile * n_stride, threadIdx.x);
+  for (int kb = blockIdx.y; kb < nkb; kb += gridDim.y) {
+    char* hi = blob + ((size_t)tile * nkb + kb) * (size_t)(2 * bn * 128);
+    bp.prefetch(kb);
+    bp.store(kb, hi, hi + bn * 128);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Warp-specialised kernel (the one the launchers use).  9 warps:
+//   warp 0      : one thread issues tcgen05.mma (<= 4 K-steps x 3 passes per stage) and commits the
+//                 stage's "empty" mbarrier; it never touches operand data
+//   warps 1..8  : 256 producer threads fill the A stage (and the B stage when B is not packed),
+//                 arrive on the stage's "full" mbarrier, and run up to STAGES ahead of the tensor
+//                 core -- there is no __syncthreads in the main loop.  Producer thread 0 also issues
+//                 the cp.async.bulk copies of packed B stages.  At every accumulation-chunk boundary
+//                 the producers add the TMEM chunk accumulator P into the running sum S (RN) and
+//                 release the MMA warp through the "drained" mbarrier.  They are the epilogue warps.
+// barriers: full[0..1] (256 arrivals), empty[0..1] (tcgen05.commit), bfull[0..2] (tx bytes), drained.
+// ----------------------------------------------------------------------------------------------------
+constexpr int WS_THREADS = 32 + THREADS;
+#ifdef B200_TC_TRACE
+// debug timeline of CTA (0,0,0): [role][kb][slot] clock64 stamps (built only into libb200rec_trace.so)
+__device__ long long g_tc_trace[3 * 512 * 4];
+#define TC_TRACE(role, kb, slot)                                                          \
+  do {                                                                                    \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (kb) < 512)              \
+      g_tc_trace[((role) * 512 + (kb)) * 4 + (slot)] = clock64();                         \
+  } while (0)
+#else
+#define TC_TRACE(role, kb, slot) do {} while (0)
+#endif
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__host__ __device__ inline int ws_nb(bool packed, int bn) { return packed ? tcb_nb(bn) : 2; }
+__host__ __device__ inline int ws_smem_bytes(bool packed, int bn) {
+  return 1024 + TCB_A_BYTES + ws_nb(packed, bn) * 2 * bn * 128 + 128;
+}
+
+template <class AP, class BP, class Sched, class Ep, int PASSES, bool PACKED>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sched, AP ap, BP bp,
+               const char* __restrict__ bblob, Ep ep) {
   extern __shared__ char smem_raw[];
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  char* extra = base + STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(extra + EXTRA_BYTES);   // stage[0], stage[1] drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NB = ws_nb(PACKED, bn);
+  const int b_stage = 2 * bn * 128;
+  char* bbase = base + TCB_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bbase + NB * b_stage);
+  const uint32_t bar_full = smem_u32(&bars[0]);    // +8*st
+  const uint32_t bar_empty = smem_u32(&bars[2]);   // +8*st
+  const uint32_t bar_bfull = smem_u32(&bars[4]);   // +8*sb
+  const uint32_t bar_drained = smem_u32(&bars[7]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM;
   const int n0 = blockIdx.x * n_stride;
   const Sched s = sched.for_split(blockIdx.z);
-  ap.s = s;
-  bp.s = s;
+  const int nkb = s.nkb();
 
-  if (tid == 0) {
-    mbar_init(smem_u32(&bars[0]), 1);
-    mbar_init(smem_u32(&bars[1]), 1);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, THREADS); mbar_init(bar_full + 8, THREADS);
+    mbar_init(bar_empty, 1); mbar_init(bar_empty + 8, 1);
+    mbar_init(bar_bfull, 1); mbar_init(bar_bfull + 8, 1); mbar_init(bar_bfull + 16, 1);
+    mbar_init(bar_drained, THREADS);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-  ap.init(extra, m0, tid);
-  bp.init(extra, n0, tid);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t idesc = make_idesc(bn);
-  const int nkb = s.nkb();
 
-  if (nkb > 0) {
-    ap.prefetch(0);
-    bp.prefetch(0);
-  }
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int st = kb & 1;
-    char* a_hi = base + st * STAGE_BYTES;
-    char* a_lo = a_hi + A_TILE_BYTES;
-    char* b_hi = a_lo + A_TILE_BYTES;
-    char* b_lo = b_hi + B_TILE_BYTES;
-    // the MMAs that read this stage two iterations ago must have drained
-    if (kb >= STAGES) mbar_wait(smem_u32(&bars[st]), ((kb >> 1) - 1) & 1);
-    ap.store(kb, a_hi, a_lo);
-    bp.store(kb, b_hi, b_lo);
-    if (kb + 1 < nkb) {  // next stage's global loads fly while the tensor core works
-      ap.prefetch(kb + 1);
-      bp.prefetch(kb + 1);
+  if (warp == 0) {
+    // ===================================== MMA issuer =====================================
+    // elect.sync (not `lane == 0`): ptxas then knows a single thread runs the block and keeps the
+    // descriptors / TMEM address in uniform registers instead of re-broadcasting them per MMA
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    if (leader) {
+      const uint32_t idesc = make_idesc(bn);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb & 1, sb = kb % NB;
+        const bool chunk_start = kc > 0 ? (kb % kc == 0) : (kb == 0);
+        TC_TRACE(0, kb, 0);
+        if (kc > 0 && chunk_start && kb > 0) mbar_wait(bar_drained, ((kb / kc) - 1) & 1);
+        mbar_wait(bar_full + 8 * st, (kb >> 1) & 1);
+        TC_TRACE(0, kb, 1);
+        if (PACKED) mbar_wait(bar_bfull + 8 * sb, (kb / NB) & 1);
+        TC_TRACE(0, kb, 2);
+        tc_fence_after();
+        char* a_hi = base + st * 2 * A_TILE_BYTES;
+        char* b_hi = bbase + sb * b_stage;
+        const uint64_t dah = make_desc(smem_u32(a_hi)), dal = make_desc(smem_u32(a_hi + A_TILE_BYTES));
+        const uint64_t dbh = make_desc(smem_u32(b_hi)), dbl = make_desc(smem_u32(b_hi + bn * 128));
+        const int ksteps = (s.kvalid(kb) + UK - 1) / UK;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4);
+          mma_tf32(tmem, dah + adv, dbh + adv, idesc, (!chunk_start || ks != 0) ? 1u : 0u);
+          if (PASSES == 3) {
+            mma_tf32(tmem, dal + adv, dbh + adv, idesc, 1u);
+            mma_tf32(tmem, dah + adv, dbl + adv, idesc, 1u);
+          }
+        }
+        mma_commit(bar_empty + 8 * st);
+        TC_TRACE(0, kb, 3);
+      }
     }
-    const bool chunk_start = kc > 0 ? (kb % kc == 0) : (kb == 0);
-    if (kc > 0 && chunk_start && kb > 0) {
-      // the previous chunk ended with stage kb-1: wait for its MMAs, then S (+)= P
-      mbar_wait(smem_u32(&bars[st ^ 1]), ((kb - 1) >> 1) & 1);
-      tc_fence_after();
-      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-      for (int ch = warp >> 2; ch * 16 < bn; ch += 2) {
-        uint32_t p[16], q[16];
-        tmem_ld16_nowait(tmem + lane_addr + ch * 16, p);
-        if (kb > kc) {
-          tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, q);
-          tmem_wait_ld2(p, q);
+  } else {
+    // ===================================== producers =====================================
+    const int tid = threadIdx.x - 32;
+    const int pw = warp - 1;               // 0..7
+    ap.s = s;
+    ap.init(nullptr, m0, tid);
+    if (!PACKED) {
+      bp.s = s;
+      bp.init(nullptr, n0, tid);
+    }
+    const char* myblob = bblob + (size_t)blockIdx.x * nkb * b_stage;
+    auto issue_b = [&](int kb) {
+      const int sb = kb % NB;
+      mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)b_stage);
+      bulk_g2s(smem_u32(bbase + sb * b_stage), myblob + (size_t)kb * b_stage, (uint32_t)b_stage,
+               bar_bfull + 8 * sb);
+    };
+    if (PACKED && tid == 0)
+      for (int kb = 0; kb < NB && kb < nkb; ++kb) issue_b(kb);
+    if (nkb > 0) {
+      ap.template prefetch2<0>(0);
+      if (!PACKED) bp.prefetch(0);
+    }
+    if (AP::DIST == 2 && nkb > 1) ap.template prefetch2<1>(1);
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+
+    auto stage = [&](auto slot_tag, int kb) {
+      constexpr int P = decltype(slot_tag)::value;
+      char* a_hi = base + P * 2 * A_TILE_BYTES;
+      if (tid == 0) TC_TRACE(1, kb, 0);
+      if (kb >= STAGES) {
+        mbar_wait(bar_empty + 8 * P, ((kb >> 1) - 1) & 1);     // MMA(kb-2) drained: stage P is free
+        if (PACKED && tid == 0 && kb - 2 + NB < nkb) issue_b(kb - 2 + NB);
+      }
+      if (tid == 0) TC_TRACE(1, kb, 1);
+      ap.template store2<P>(kb, a_hi, a_hi + A_TILE_BYTES);
+      if (tid == 0) TC_TRACE(1, kb, 2);
+      if (!PACKED) {
+        char* b_hi = bbase + P * b_stage;
+        bp.store(kb, b_hi, b_hi + bn * 128);
+        if (kb + 1 < nkb) bp.prefetch(kb + 1);
+      }
+      if (kb + AP::DIST < nkb) ap.template prefetch2<(AP::DIST == 2 ? P : 1 - P)>(kb + AP::DIST);
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * P);
+      if (tid == 0) TC_TRACE(1, kb, 3);
+      if (kc > 0 && kb > 0 && kb % kc == 0) {
+        // the previous accumulation chunk ended with stage kb-1: S (+)= P, then release the MMA warp
+        mbar_wait(bar_empty + 8 * (P ^ 1), ((kb - 1) >> 1) & 1);
+        tc_fence_after();
+        for (int ch = pw >> 2; ch * 16 < bn; ch += 2) {
+          uint32_t p[16], q[16];
+          tmem_ld16_nowait(tmem + lane_addr + ch * 16, p);
+          if (kb > kc) {
+            tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, q);
+            tmem_wait_ld2(p, q);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) p[i] = __float_as_uint(__uint_as_float(p[i]) + __uint_as_float(q[i]));
-        } else {
-          tmem_wait_ld1(p);
+            for (int i = 0; i < 16; ++i) p[i] = __float_as_uint(__uint_as_float(p[i]) + __uint_as_float(q[i]));
+          } else {
+            tmem_wait_ld1(p);
+          }
+          tmem_st16(tmem + lane_addr + TMEM_S + ch * 16, p);
         }
-        tmem_st16(tmem + lane_addr + TMEM_S + ch * 16, p);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_drained);
+        if (tid == 0) TC_TRACE(2, kb, 0);
       }
-      tmem_wait_st();
+    };
+    for (int kb0 = 0; kb0 < nkb; kb0 += 2) {
+      stage(std::integral_constant<int, 0>{}, kb0);
+      if (kb0 + 1 < nkb) stage(std::integral_constant<int, 1>{}, kb0 + 1);
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const int ksteps = (s.kvalid(kb) + UK - 1) / UK;
-      const uint64_t dah = make_desc(smem_u32(a_hi)), dal = make_desc(smem_u32(a_lo));
-      const uint64_t dbh = make_desc(smem_u32(b_hi)), dbl = make_desc(smem_u32(b_lo));
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4);  // 32 B per K-step inside the swizzle row
-        mma_tf32(tmem, dah + adv, dbh + adv, idesc, (!chunk_start || ks != 0) ? 1u : 0u);
-        if (PASSES == 3) {
-          mma_tf32(tmem, dal + adv, dbh + adv, idesc, 1u);
-          mma_tf32(tmem, dah + adv, dbl + adv, idesc, 1u);
-        }
-      }
-      mma_commit(smem_u32(&bars[st]));
-    }
-  }
 
-  // ---- epilogue: thread = accumulator row (TMEM lane), 16 columns per tcgen05.ld ------------------
-  if (nkb > 0) {
-    mbar_wait(smem_u32(&bars[(nkb - 1) & 1]), ((nkb - 1) >> 1) & 1);
-    tc_fence_after();
-    const bool add_s = kc > 0 && nkb > kc;   // result = S + P (the last chunk is still in P)
-    const int lane_base = (warp & 3) * 32;
-    const int row = m0 + lane_base + lane;
-    const int ncols = min(n_valid, N - n0);
-    float v[16];
-    if constexpr (Ep::kRowReduce) {
-      if (warp < 4) {
+    // ---- epilogue: thread = accumulator row (TMEM lane), 16 columns per tcgen05.ld ----------------
+    if (nkb > 0) {
+      mbar_wait(bar_empty + 8 * ((nkb - 1) & 1), ((nkb - 1) >> 1) & 1);
+      tc_fence_after();
+      const bool add_s = kc > 0 && nkb > kc;   // result = S + P (the last chunk is still in P)
+      const int row = m0 + (warp & 3) * 32 + lane;
+      const int ncols = min(n_valid, N - n0);
+      float v[16];
+      if constexpr (Ep::kRowReduce) {
+        // x tile -> shared memory (the B ring is free now), then thread = row dots; the two column
+        // halves of a row are reduced by different warps and combined through shared memory
+        float* xs = reinterpret_cast<float*>(bbase);
+        ep.load_tile(xs, m0, M, ncols, tid);
+        asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
+        const int rl = (warp & 3) * 32 + lane;
         float acc = 0.f;
-        for (int ch = 0; ch * 16 < ncols; ++ch) {
-          tmem_ld16(tmem + ((uint32_t)lane_base << 16) + ch * 16, v);
+        for (int ch = pw >> 2; ch * 16 < ncols; ch += 2) {
+          tmem_ld16(tmem + lane_addr + ch * 16, v);
           if (add_s) {
             float sv[16];
-            tmem_ld16(tmem + ((uint32_t)lane_base << 16) + TMEM_S + ch * 16, sv);
+            tmem_ld16(tmem + lane_addr + TMEM_S + ch * 16, sv);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += sv[i];
           }
-          if (row < M) acc += ep.dot(row, ch * 16, v, min(16, ncols - ch * 16));
+          acc += ep.dot(xs, ncols, rl, ch * 16, v, min(16, ncols - ch * 16));
         }
-        if (row < M) ep.finish(row, blockIdx.x, acc);
-      }
-    } else {
-      for (int ch = warp >> 2; ch * 16 < ncols; ch += 2) {
-        tmem_ld16(tmem + ((uint32_t)lane_base << 16) + ch * 16, v);
-        if (add_s) {
-          float sv[16];
-          tmem_ld16(tmem + ((uint32_t)lane_base << 16) + TMEM_S + ch * 16, sv);
+        float* red = reinterpret_cast<float*>(base);   // A stage 0 is free now
+        if (pw >= 4) red[(warp & 3) * 32 + lane] = acc;
+        asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
+        if (pw < 4 && row < M) ep.finish(row, blockIdx.x, acc + red[(warp & 3) * 32 + lane]);
+      } else {
+        for (int ch = pw >> 2; ch * 16 < ncols; ch += 2) {
+          tmem_ld16(tmem + lane_addr + ch * 16, v);
+          if (add_s) {
+            float sv[16];
+            tmem_ld16(tmem + lane_addr + TMEM_S + ch * 16, sv);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += sv[i];
+            for (int i = 0; i < 16; ++i) v[i] += sv[i];
+          }
+          if (row < M) ep(row, n0 + ch * 16, v, min(16, ncols - ch * 16), blockIdx.z);
         }
-        if (row < M) ep(row, n0 + ch * 16, v, min(16, ncols - ch * 16), blockIdx.z);
       }
     }
   }

@@ -190,6 +190,8 @@ def bench(args, pkg):
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is set; keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
     dist.init_process_group("nccl", device_id=dev)
     synth = pkg.synth
     kind, fc, cin, depth = B.MODELS[args.model]

@@ -1,0 +1,44 @@
+"""Pipeline timeline of the tcgen05 GEMM (CTA 0) from the trace build: B200REC_LIB=.../libb200rec_trace.so"""
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as g
+pkg = g.load_package()
+lib = pkg.lib()
+rng = np.random.default_rng(0)
+
+def dump(title, nkb):
+    buf = (C.c_longlong * (3 * 512 * 4))()
+    lib.b200rec_debug_tc_trace(buf, 3 * 512 * 4)
+    a = np.array(buf, dtype=np.int64).reshape(3, 512, 4)
+    t0 = a[0, 0, 0]
+    print("==", title, "nkb", nkb)
+    print(" kb | MMA: start  full  bfull  issued | PROD: start  waited  stored  arrived | drained")
+    for kb in range(min(nkb, 24)):
+        m, p = a[0, kb] - t0, a[1, kb] - t0
+        d = a[2, kb, 0] - t0 if a[2, kb, 0] else 0
+        print(f"{kb:3d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d} | {p[0]:7d} {p[1]:7d} {p[2]:7d} {p[3]:7d} | {d:7d}")
+    m = a[0, :nkb] - t0
+    print(" mean stage period (MMA issued->issued):", float(np.diff(m[:, 3]).mean()) if nkb > 1 else 0)
+
+B, I, O = 1024, 624, 400
+x = rng.standard_normal((B, I)).astype(np.float32)
+w = (rng.standard_normal((O, I)) / np.sqrt(I)).astype(np.float32)
+lin = pkg.Linear(I, O, False, w)
+lin.updateOutput(x)
+dump("linear fwd 1024x624x400", (I + 31) // 32)
+gy = rng.standard_normal((B, O)).astype(np.float32)
+lin.updateGradInput(x, gy)
+dump("linear dx", (O + 31) // 32)
+lin.accGradParameters(x, gy)
+dump("linear dW (split-K)", 8)
+# CIN forward through a tiny xdeepfm forward
+F, K = 39, 16
+m = pkg.make_model("xdeepfm", F, K, [16], [200, 200])
+Bm = 64
+n = Bm * F
+from oracle import refport
+mats = pkg.synth.init_mats(1, refport.mats_size("xdeepfm", F, K, [16], [200, 200]))
+m.forward(Bm, np.repeat(np.arange(Bm, dtype=np.int32), F), rng.standard_normal(n).astype(np.float32),
+          np.zeros(1, np.float32), rng.standard_normal(n * K).astype(np.float32), mats)
+dump("cin fwd layer 2 (H=200)", 39 * 7)
