@@ -172,6 +172,8 @@ def run_b200(args):
     model = pkg.make_model(kind, F, K, fc, cin, depth, device=local)
     if args.gemm_mode is not None:
         model.setGemmMode(args.gemm_mode)
+    if args.no_graph:
+        L.check(L.lib().b200rec_model_set_graph(model.handle, 0))
     table = pkg.EmbeddingTable(rows, K if kind != "lr" else 0, device=local)
     table.init_uniform(SEED_PARAMS)
     mats = synth.init_mats(SEED_PARAMS, model.getMatsSize())
@@ -286,7 +288,7 @@ def run_b200(args):
                                f"table_rows={rows} (BASELINE configs[{ {'deepfm': 1, 'xdeepfm': 2}.get(args.model, 3)}])",
                    "global_batch": B, "ids": "power-law, one per field, new batch every step",
                    "l2": f"table {rows * K * 4 / 1e6:.0f} MB > 126 MB L2; distinct ids per step; no explicit flush",
-                   "parallelism": "1 GPU", "gemm_mode": args.gemm_mode, "seed_data": SEED_DATA,
+                   "parallelism": "1 GPU", "gemm_mode": args.gemm_mode, "cuda_graph": not args.no_graph, "seed_data": SEED_DATA,
                    "seed_params": SEED_PARAMS, "distinct_ids_last_step": U},
         "clocks": clk,
         "e2e": {"value": round(B * Ksteps / e2e_s, 1), "unit": "samples/s", "h2d_bytes_per_step": B * F * 4 + B * 4,
@@ -391,6 +393,7 @@ def main():
     ap.add_argument("--rows", type=int, default=39 * (1 << 18))
     ap.add_argument("--gemm-mode", type=int, default=None, help="0 fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of the CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -173,6 +173,9 @@ int b200rec_step(b200rec_model_t m, b200rec_table_t t, int batch_size,
 /* Same with DEVICE ids / targets; no host synchronisation; loss stays in the handle. */
 int b200rec_step_dev(b200rec_model_t m, b200rec_table_t t, int batch_size,
                      const int* feats, const float* targets, void* stream);
+/* The training step replays as a CUDA graph after one eager warm-up per (batch size, table); 0 turns
+ * that off (plain stream launches). */
+int b200rec_model_set_graph(b200rec_model_t m, int enabled);
 /* Predict: preds[B] = sigmoid(logit) (ParRecModel.predict :519-533). */
 int b200rec_predict(b200rec_model_t m, b200rec_table_t t, int batch_size,
                     const int* feats, float* preds);

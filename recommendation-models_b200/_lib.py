@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200rec_model_set_params": [vp, vp, vp],
     "b200rec_model_get_params": [vp, vp, vp],
     "b200rec_model_param_ptrs": [vp, C.POINTER(vp), C.POINTER(vp)],
+    "b200rec_model_set_graph": [vp, C.c_int],
     "b200rec_step": [vp, vp, C.c_int, vp, vp, c_float_p],
     "b200rec_step_dev": [vp, vp, C.c_int, vp, vp, vp],
     "b200rec_predict": [vp, vp, C.c_int, vp, vp],

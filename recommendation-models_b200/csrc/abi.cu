@@ -704,14 +704,71 @@ static int step_on_device(Model* m, Table* t, int B, const int* feats, const flo
   return B200REC_OK;
 }
 
+// The resident training step as a CUDA graph: the ~45 dependent launches of one step replay with
+// sub-microsecond gaps instead of a stream launch each.  Inputs are staged at fixed addresses
+// (d_feats / d_targets), the first step of a configuration runs eagerly (it sizes every workspace and
+// sets kernel attributes), the second is captured (both streams: the sort fork/join becomes graph
+// edges), later ones replay.  Any capture failure falls back to eager launches for good.
+static int step_train_graphed(Model* m, Table* t, int B, const int* feats, const float* targets,
+                              cudaStream_t st) {
+  const long long nnz = (long long)B * m->F;
+  B200_TRY(m->d_feats.reserve((size_t)nnz * sizeof(int)));
+  B200_TRY(m->d_targets.reserve((size_t)B * sizeof(float)));
+  if (feats != m->d_feats.as<int>())
+    B200_CUDA(cudaMemcpyAsync(m->d_feats.p, feats, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (targets != m->d_targets.as<float>())
+    B200_CUDA(cudaMemcpyAsync(m->d_targets.p, targets, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const int* f = m->d_feats.as<int>();
+  const float* tg = m->d_targets.as<float>();
+  if (!m->graph_enabled || tl_prof) return step_on_device(m, t, B, f, tg, nullptr, st);
+  const bool match = m->graph_exec && m->graph_B == B && m->graph_table == (const void*)t &&
+                     m->graph_mode == m->gemm_mode;
+  if (!match) {
+    if (m->graph_warm_B != B) {  // eager warm-up: allocations and attribute calls happen here
+      m->graph_warm_B = B;
+      if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+      return step_on_device(m, t, B, f, tg, nullptr, st);
+    }
+    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const long long l0 = g_launches.load();
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int s = B200REC_OK;
+    if (ok) {
+      s = step_on_device(m, t, B, f, tg, nullptr, st);
+      ok = cudaStreamEndCapture(st, &graph) == cudaSuccess && s == B200REC_OK && graph;
+    }
+    if (ok) ok = cudaGraphInstantiate(&m->graph_exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      m->graph_enabled = false;
+      m->graph_exec = nullptr;
+      return step_on_device(m, t, B, f, tg, nullptr, st);
+    }
+    m->graph_nodes = (int)(g_launches.load() - l0);   // launches recorded, not executed, by the capture
+    g_launches.fetch_sub(m->graph_nodes);
+    m->graph_B = B; m->graph_table = (const void*)t; m->graph_mode = m->gemm_mode;
+    m->last_B = B; m->last_nnz = nnz;
+  }
+  B200_CUDA(cudaGraphLaunch(m->graph_exec, st));
+  g_launches.fetch_add(m->graph_nodes, std::memory_order_relaxed);
+  return B200REC_OK;
+}
+
+int b200rec_model_set_graph(b200rec_model_t m, int enabled) {
+  B200_REQUIRE(m, B200REC_ERR_ARG, "NULL model");
+  m->graph_enabled = enabled != 0;
+  return B200REC_OK;
+}
+
 int b200rec_step_dev(b200rec_model_t m, b200rec_table_t t, int batch_size, const int* feats,
                      const float* targets, void* stream) {
   B200_GUARD_BEGIN
   B200_TRY(check_step_args(m, t, batch_size));
   B200_REQUIRE(feats && targets, B200REC_ERR_ARG, "NULL argument");
   B200_TRY(use_device(m->device));
-  return step_on_device(m, t, batch_size, feats, targets, nullptr,
-                        stream ? (cudaStream_t)stream : m->stream);
+  return step_train_graphed(m, t, batch_size, feats, targets, stream ? (cudaStream_t)stream : m->stream);
   B200_GUARD_END
 }
 
@@ -725,7 +782,7 @@ int b200rec_step(b200rec_model_t m, b200rec_table_t t, int batch_size, const int
   const long long nnz = (long long)batch_size * m->F;
   B200_TRY(upload(m->d_feats, feats, (size_t)nnz * sizeof(int), st));
   B200_TRY(upload(m->d_targets, targets, (size_t)batch_size * sizeof(float), st));
-  B200_TRY(step_on_device(m, t, batch_size, m->d_feats.as<int>(), m->d_targets.as<float>(), nullptr, st));
+  B200_TRY(step_train_graphed(m, t, batch_size, m->d_feats.as<int>(), m->d_targets.as<float>(), st));
   B200_TRY(download(m->h_scal, m->scal.p, 8 * sizeof(float), st));
   B200_CUDA(cudaStreamSynchronize(st));
   B200_TRY(dev_status(((int*)m->h_scal)[4], batch_size, t->rows));

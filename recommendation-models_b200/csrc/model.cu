@@ -134,6 +134,8 @@ void b200rec_model_s::destroy() {
   for (auto& b : xl) b.release();
   seg.release();
   plan.release();
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  graph_exec = nullptr;
   if (h_scal) cudaFreeHost(h_scal);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);

@@ -62,6 +62,11 @@ struct b200rec_model_s {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* h_scal = nullptr;  // pinned 16 words: loss, dbias, n_unique, -, err, sorted
   bool params_set = false;
+  // CUDA graph of the resident step (one per (B, table, gemm_mode)); captured after one eager warm-up
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_B = 0, graph_mode = -1, graph_nodes = 0, graph_warm_B = 0;
+  const void* graph_table = nullptr;
+  bool graph_enabled = true;
   int gemm_mode = 0;  // 0 fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32 tcgen05
   int last_B = 0;
   long long last_nnz = 0;

@@ -163,9 +163,12 @@ __global__ void __launch_bounds__(256) segsum_long_kernel(const int* seg_start,
                                                           const float* dw, float* G, float* gw,
                                                           const int* long_list,
                                                           const int* long_count) {
+  // One warp per hot id.  Rows are LOADED 32/LPR x UNR at a time (all loads of a batch in flight,
+  // the positions of the next batch prefetched meanwhile) and ADDED strictly in non-zero order
+  // through shuffles, so the result equals the reference's sequential hash-map accumulation.
   constexpr int K = 4 * LPR;
   constexpr int RPW = 32 / LPR;
-  constexpr int UNR = 4;
+  constexpr int UNR = 8;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR, slot = lane / LPR;
   const int n_long = *long_count;
@@ -177,6 +180,12 @@ __global__ void __launch_bounds__(256) segsum_long_kernel(const int* seg_start,
     const int len = seg_start[seg + 1] - start;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float aw = 0.f;
+    unsigned pnext[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = u * RPW + slot;
+      pnext[u] = j < len ? perm[start + j] : 0u;
+    }
     for (int base = 0; base < len; base += RPW * UNR) {
       float4 v[UNR];
       float w[UNR];
@@ -186,10 +195,15 @@ __global__ void __launch_bounds__(256) segsum_long_kernel(const int* seg_start,
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         w[u] = 0.f;
         if (j < len) {
-          const long long p = perm[start + j];
+          const long long p = pnext[u];
           if (dE) v[u] = ldg_f4(dE + p * K + sub * 4);
           if (dw && sub == 0) w[u] = __ldg(dw + p);
         }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {  // positions of the next batch: their latency hides under the fold
+        const int j = base + RPW * UNR + u * RPW + slot;
+        pnext[u] = j < len ? perm[start + j] : 0u;
       }
       // fold the RPW*UNR rows into the accumulator strictly in order (all lanes keep a copy)
 #pragma unroll

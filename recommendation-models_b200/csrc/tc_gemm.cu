@@ -55,6 +55,9 @@ static int launch(const char* name, int M, int N, int bn, int n_stride, int n_va
                                              sched, ap, bp, nullptr, ep, passes, st);
 }
 
+static KCin make_kcin(int F, int H, int Hp, long long KS) {
+  return KCin{F, H, Hp, KS, (unsigned)((0x100000000ULL + (unsigned)F - 1) / (unsigned)F)};
+}
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 // the 4x4 register-transpose path of ColProd needs 16-B aligned rows of 4
 static bool colvec(const float* p, long long ld, int rows_total) {
@@ -156,7 +159,7 @@ bool tc_cin_supported(int F, int H, int C) {
 int tc_cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
                      const float* b, float* x_out, int passes, cudaStream_t st) {
   const int bn = pick_bn_packed(C);
-  KCin s{F, H, 0, H};
+  KCin s = make_kcin(F, H, 0, H);
   CinZProd ap{x0, x_in, R, (H % 4 == 0) && aligned16(x_in), false};
   RowProd<8, KCin> bp{W, (long long)F * H, C, bn, (H % 4 == 0) && aligned16(W)};
   return launch_packed("tc_cin_fwd", R, C, bn, bn, bn, cdiv(C, bn), F * cdiv(H, BK), s, ap, bp,
@@ -201,7 +204,7 @@ int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x
   }
   {  // ---- gx_in[r, j] = sum_{(i,c)} (x0[r,i] gy[r,c]) W[c, i*H + j]
     const int bn = pick_bn_packed(H);
-    KCin s{F, C, H, C};
+    KCin s = make_kcin(F, C, H, C);
     CinZProd ap{x0, gy, R, (C % 4 == 0) && aligned16(gy), false};
     ColProd<256, KCin> bp{W, FH, H, bn, colvec(W, FH, H) && H % 4 == 0};   // B(j, (i,c)) = W[c*FH + i*H + j]
     B200_TRY(launch_packed("tc_cin_dx", R, H, bn, bn, bn, cdiv(H, bn), F * cdiv(C, BK), s, ap, bp,

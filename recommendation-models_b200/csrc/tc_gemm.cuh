@@ -231,11 +231,12 @@ struct KCin {
   int F, H;   // F = length of the first factor, H = width of the second factor
   int Hp;     // dx GEMM only: row stride of field i inside W's columns (= H_{l-1})
   long long KS;  // row-major B: offset of first-factor index i along the contraction (H fwd, F*H dx0)
+  unsigned magicF;  // ceil(2^32 / F): kb / F == __umulhi(kb, magicF) while kb * F < 2^32 (host: make_kcin)
   __device__ __forceinline__ KCin for_split(int) const { return *this; }
   __device__ __forceinline__ int njb() const { return (H + BK - 1) / BK; }
   __device__ __forceinline__ int nkb() const { return F * njb(); }
-  __device__ __forceinline__ int fi(int kb) const { return kb % F; }
-  __device__ __forceinline__ int jb(int kb) const { return kb / F; }
+  __device__ __forceinline__ int jb(int kb) const { return (int)__umulhi((unsigned)kb, magicF); }
+  __device__ __forceinline__ int fi(int kb) const { return kb - jb(kb) * F; }
   __device__ __forceinline__ int kvalid(int kb) const { return min(BK, H - jb(kb) * BK); }
   // forward: W[c, i*H + j]  (row-major over the contraction)
   __device__ __forceinline__ long long row_koff(int kb) const { return (long long)fi(kb) * KS + jb(kb) * BK; }
@@ -668,7 +669,7 @@ __host__ __device__ inline int ws_smem_bytes(bool packed, int bn) {
 }
 
 template <class AP, class BP, class Sched, class Ep, int PASSES, bool PACKED>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+__global__ void __launch_bounds__(WS_THREADS, 1)   // registers are granted per 4 warps: 9 warps -> cap 168
 gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sched, AP ap, BP bp,
                const char* __restrict__ bblob, Ep ep) {
   extern __shared__ char smem_raw[];
@@ -709,14 +710,15 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     if (leader) {
       const uint32_t idesc = make_idesc(bn);
+      int sb = 0, bphase = 0, cpos = 0, cidx = 0;   // B ring slot / its phase, position in / index of the chunk
       for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb & 1, sb = kb % NB;
-        const bool chunk_start = kc > 0 ? (kb % kc == 0) : (kb == 0);
+        const int st = kb & 1;
+        const bool chunk_start = kc > 0 ? (cpos == 0) : (kb == 0);
         TC_TRACE(0, kb, 0);
-        if (kc > 0 && chunk_start && kb > 0) mbar_wait(bar_drained, ((kb / kc) - 1) & 1);
+        if (kc > 0 && chunk_start && kb > 0) mbar_wait(bar_drained, (cidx - 1) & 1);
         mbar_wait(bar_full + 8 * st, (kb >> 1) & 1);
         TC_TRACE(0, kb, 1);
-        if (PACKED) mbar_wait(bar_bfull + 8 * sb, (kb / NB) & 1);
+        if (PACKED) mbar_wait(bar_bfull + 8 * sb, bphase);
         TC_TRACE(0, kb, 2);
         tc_fence_after();
         char* a_hi = base + st * 2 * A_TILE_BYTES;
@@ -734,6 +736,8 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         }
         mma_commit(bar_empty + 8 * st);
         TC_TRACE(0, kb, 3);
+        if (++sb == NB) { sb = 0; bphase ^= 1; }
+        if (kc > 0 && ++cpos == kc) { cpos = 0; ++cidx; }
       }
     }
   } else {
@@ -762,6 +766,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
     if (AP::DIST == 2 && nkb > 1) ap.template prefetch2<1>(1);
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
 
+    int pcpos = 0;   // position of stage kb inside its accumulation chunk
     auto stage = [&](auto slot_tag, int kb) {
       constexpr int P = decltype(slot_tag)::value;
       char* a_hi = base + P * 2 * A_TILE_BYTES;
@@ -782,28 +787,50 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * P);
       if (tid == 0) TC_TRACE(1, kb, 3);
-      if (kc > 0 && kb > 0 && kb % kc == 0) {
-        // the previous accumulation chunk ended with stage kb-1: S (+)= P, then release the MMA warp
+      if (kc > 0 && kb > 0 && pcpos == 0) {
+        // Stage kb (just produced, so the MMA warp can start it the moment it is released) opens a new
+        // accumulation chunk; the previous one ended with stage kb-1.  Once its MMAs have drained:
+        // S (+)= P with round-to-nearest, then release the MMA warp.  All TMEM
+        // loads of a group of chunks are issued before the first wait (fewer TMEM round trips).
         mbar_wait(bar_empty + 8 * (P ^ 1), ((kb - 1) >> 1) & 1);
         tc_fence_after();
-        for (int ch = pw >> 2; ch * 16 < bn; ch += 2) {
-          uint32_t p[16], q[16];
-          tmem_ld16_nowait(tmem + lane_addr + ch * 16, p);
-          if (kb > kc) {
-            tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, q);
-            tmem_wait_ld2(p, q);
+        const bool have_s = kb > kc;
+        const int ch0 = pw >> 2;
+        constexpr int DG = PACKED ? 2 : 1;   // chunks per TMEM round trip (register budget)
+#pragma unroll 1
+        for (int grp = 0; grp < 8 / DG; ++grp) {
+          if ((ch0 + 2 * DG * grp) * 16 >= bn) break;
+          uint32_t p[DG][16], q[DG][16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) p[i] = __float_as_uint(__uint_as_float(p[i]) + __uint_as_float(q[i]));
-          } else {
-            tmem_wait_ld1(p);
+          for (int i = 0; i < DG; ++i) {
+            const int ch = ch0 + 2 * (grp * DG + i);
+            if (ch * 16 < bn) {
+              tmem_ld16_nowait(tmem + lane_addr + ch * 16, p[i]);
+              if (have_s) tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, q[i]);
+            }
           }
-          tmem_st16(tmem + lane_addr + TMEM_S + ch * 16, p);
+#pragma unroll
+          for (int i = 0; i < DG; ++i) {
+            const int ch = ch0 + 2 * (grp * DG + i);
+            if (ch * 16 < bn) {
+              if (have_s) {
+                tmem_wait_ld2(p[i], q[i]);
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  p[i][e] = __float_as_uint(__uint_as_float(p[i][e]) + __uint_as_float(q[i][e]));
+              } else {
+                tmem_wait_ld1(p[i]);
+              }
+              tmem_st16(tmem + lane_addr + TMEM_S + ch * 16, p[i]);
+            }
+          }
         }
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(bar_drained);
         if (tid == 0) TC_TRACE(2, kb, 0);
       }
+      if (kc > 0 && ++pcpos == kc) pcpos = 0;
     };
     for (int kb0 = 0; kb0 < nkb; kb0 += 2) {
       stage(std::integral_constant<int, 0>{}, kb0);

@@ -77,3 +77,42 @@ def test_step_needs_params_and_valid_ids(gpu_pkg):
     with pytest.raises(ValueError):
         ps.optimize(feats, np.zeros(B, np.float32))
     model.close(); table.close()
+
+
+@pytest.mark.parametrize("name", ["fm", "deepfm"])
+def test_step_graph_replay(gpu_pkg, name):
+    """The resident step is captured into a CUDA graph after one eager warm-up; replays with new ids
+    must give the results of a fresh eager step (and of the oracle)."""
+    synth = gpu_pkg.synth
+    cfg = CONFIGS[name]
+    F, K, rows, B = 39, 16, 39 * 300, 128
+    model = gpu_pkg.make_model(name, F, K, cfg.get("fc_dims", ()))
+    table = gpu_pkg.EmbeddingTable(rows, K)
+    table.init_uniform(42, -0.3, 0.3)
+    mats = synth.init_mats(7, model.getMatsSize())
+    bias = np.array([0.1], np.float32)
+    ps = gpu_pkg.ParRecModel(model, table)
+    ps.setParams(bias, mats)
+    o = refport.Model(name, F, K, cfg.get("fc_dims", ()))
+    o64 = refport.Model(name, F, K, cfg.get("fc_dims", ()), dtype=np.float64)
+    for step in range(4):     # step 0 eager, step 1 captured, steps 2-3 replayed
+        _, cand = synth.make_feats(99, step, 4 * B, F, rows)
+        ce = synth.table_rows(42, cand, K, -0.3, 0.3).reshape(-1)
+        cw = synth.wtable_rows(42, cand, -0.3, 0.3)
+        cidx = np.repeat(np.arange(4 * B, dtype=np.int32), F)
+        index, _, _, ids = away_from_kinks(o64, 4 * B, F, K, cidx, cw, bias, ce, mats if mats.size else None, keep=B)
+        feats = np.ascontiguousarray(cand.reshape(4 * B, F)[ids].reshape(-1))
+        targets = synth.make_targets(99, feats, B, F)
+        loss = ps.optimize(feats, targets) / B
+        res = ps.stepResults()
+        emb = synth.table_rows(42, feats, K, -0.3, 0.3).reshape(-1)
+        w = synth.wtable_rows(42, feats, -0.3, 0.3)
+        ob, om = bias.copy(), (mats.copy() if mats.size else None)
+        oloss = o.backward(B, index, w, ob, emb, om, targets)
+        assert abs(loss - oloss) <= 1e-5 * abs(oloss), step
+        uids, G = refport.make_embedding_grad(emb, feats, K)
+        assert np.array_equal(res["unique"], uids), step
+        assert_close(res["emb_grad"], G, what=f"emb_grad step {step}", rtol=2e-5)
+        if om is not None:
+            assert_close(res["mats_grad"], om, what=f"mats_grad step {step}", rtol=2e-5)
+    model.close(); table.close()
