@@ -48,6 +48,14 @@ enum b200rec_status {
   B200REC_ERR_NOMEM = -6
 };
 
+/* rec/optim/OptimUtils.scala:5-12 ("sgd" | "momentum" | "adagrad" | "adam") */
+enum b200rec_optimizer {
+  B200REC_OPT_SGD = 0,       /* AsyncSGD.scala:10-31      1 slot                             */
+  B200REC_OPT_MOMENTUM = 1,  /* AsyncMomentum.scala:10-33 2 slots, p1 = momentum (0.9)       */
+  B200REC_OPT_ADAGRAD = 2,   /* AsyncAdagrad.scala:10-33  2 slots, p1 = factor (0.9)         */
+  B200REC_OPT_ADAM = 3       /* AsyncAdam.scala:10-36     3 slots, p1 = gamma (0.99), p2 = beta (0.9) */
+};
+
 /* rec/model/RecModelType.scala:3-9 decides which buffers exist; `kind` implies it. */
 enum b200rec_kind {
   B200REC_LR = 0,       /* rec/model/lr/LR.scala:42-90            BIAS_WEIGHT                 */
@@ -242,6 +250,20 @@ int b200rec_step_rows_dev(b200rec_model_t m, int batch_size, const int* slots, c
 int b200rec_table_apply_sgd_dev(b200rec_table_t t, int64_t n_unique_cap, const int* n_unique,
                                 const int* unique, const float* emb_grad, const float* w_grad,
                                 float lr, void* stream);
+
+/* ---- optimizer step: what the PS does with a pushed gradient ------------------------
+ * rec/optim/Async*.scala hand (gradient, hyper-parameters, slot offset) to Angel PSFs; the PSF
+ * arithmetic is third-party: textbook forms, PARITY UNPINNED (csrc/optim.cu states them).  Optimizer
+ * state ("slots", ParRecModel.scala:75,79,96,115) is allocated inside the handle on first use.
+ * `step` = 1-based update count (Adam bias correction; AsyncAdam.numUpdates).
+ * Touched rows only: unique[U], emb_grad[U*K], w_grad[U] as produced by the step (device pointers). */
+int b200rec_table_apply_optimizer_dev(b200rec_table_t t, int optimizer, float lr, float p1, float p2,
+                                      int64_t step, int64_t n_unique_cap, const int* n_unique,
+                                      const int* unique, const float* emb_grad, const float* w_grad,
+                                      void* stream);
+/* Dense params of the handle (bias, mats) with the gradients of its last step. */
+int b200rec_model_apply_optimizer_dev(b200rec_model_t m, int optimizer, float lr, float p1, float p2,
+                                      int64_t step, void* stream);
 
 /* ---- the reference's own BigDL modules (updateOutput / updateGradInput / accGradParameters) */
 /* nn/Scatter.scala:17-36  output[index[i], :] += input[i, :]  (i ascending; bit-exact order). */

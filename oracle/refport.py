@@ -674,6 +674,39 @@ def make_weights_grad(buf, feats):
 
 
 # ----------------------------------------------------------------------------
+# Optimizers (rec/optim/Async*.scala -> Angel Async*Func PSFs, third-party: textbook forms, unpinned)
+# ----------------------------------------------------------------------------
+def optimizer_update(kind, w, g, state, lr, p1=None, p2=None, step=1, eps=1e-7):
+    """One update of the values `w` (any shape) with gradient `g`; `state` is a dict holding the slots.
+    sgd; momentum (p1 = 0.9); adagrad (p1 = factor 0.9, EMA of g^2); adam (p1 = gamma 0.99, p2 = beta 0.9).
+    fp32 arithmetic like the GPU kernel (csrc/optim.cu)."""
+    f = np.float32
+    w, g = w.astype(f), g.astype(f)
+    lr = f(lr)
+    if kind == "sgd":
+        return w - lr * g
+    if kind == "momentum":
+        mu = f(0.9 if p1 is None else p1)
+        v = mu * state.get("s1", np.zeros_like(w)) + g
+        state["s1"] = v
+        return w - lr * v
+    if kind == "adagrad":
+        fac = f(0.9 if p1 is None else p1)
+        s = fac * state.get("s1", np.zeros_like(w)) + (f(1) - fac) * g * g
+        state["s1"] = s
+        return w - lr * g / (np.sqrt(s) + f(eps))
+    if kind == "adam":
+        gamma, beta = f(0.99 if p1 is None else p1), f(0.9 if p2 is None else p2)
+        m = beta * state.get("s1", np.zeros_like(w)) + (f(1) - beta) * g
+        v = gamma * state.get("s2", np.zeros_like(w)) + (f(1) - gamma) * g * g
+        state["s1"], state["s2"] = m, v
+        c1 = f(1.0 / (1.0 - float(beta) ** step))
+        c2 = f(1.0 / (1.0 - float(gamma) ** step))
+        return w - lr * (m * c1) / (np.sqrt(v * c2) + f(eps))
+    raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------
 # AUC (Angel AUC().calculate, rec/example/DeepFMLocalExample.scala:45-52) -- rank-sum
 # ----------------------------------------------------------------------------
 def auc(targets, preds):

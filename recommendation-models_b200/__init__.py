@@ -11,4 +11,4 @@ from .models import (InternalDCNModel, InternalDeepFMModel, InternalFMModel, Int
                      InternalPNNModel, InternalXDeepFMModel, make_model)
 from .nn import DotProduct2, FirstOrderEncoder, Gather, Linear, Scatter, SecondOrderEncoder
 from .ps import EmbeddingTable, ParRecModel, distinct, scatter_add
-from . import sharded, synth
+from . import data, metrics, sharded, synth

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200REC_LIB") or os.path.join(HERE, "libb200rec.so")
 
 OK, ERR_ARG, ERR_SHAPE, ERR_INDEX, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
+OPTIMIZERS = {"sgd": 0, "momentum": 1, "adagrad": 2, "adam": 3}
 KINDS = {"lr": 0, "fm": 1, "deepfm": 2, "xdeepfm": 3, "dcn": 4, "pnn": 5}
 
 c_int_p = C.POINTER(C.c_int)
@@ -72,6 +73,9 @@ SIGNATURES = {
     "b200rec_table_lookup_padded_dev": [vp, C.c_int64, vp, vp, vp, vp],
     "b200rec_step_rows_dev": [vp, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, vp],
     "b200rec_table_apply_sgd_dev": [vp, C.c_int64, vp, vp, vp, vp, C.c_float, vp],
+    "b200rec_table_apply_optimizer_dev": [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_int64, vp, vp, vp,
+                                          vp, vp],
+    "b200rec_model_apply_optimizer_dev": [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int64, vp],
     "b200rec_scatter_update_output": [C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp, vp],
     "b200rec_scatter_update_grad_input": [C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp, vp],
     "b200rec_gather_update_output": [C.c_int] * 5 + [vp] * 5,

@@ -458,6 +458,7 @@ int b200rec_table_destroy(b200rec_table_t t) {
   if (!t) return B200REC_OK;
   cudaSetDevice(t->device);
   if (t->stream) cudaStreamSynchronize(t->stream);
+  t->s1e.release(); t->s2e.release(); t->s1w.release(); t->s2w.release();
   t->emb.release(); t->w.release(); t->stage_i.release(); t->stage_e.release();
   t->stage_w.release(); t->err.release();
   if (t->stream) cudaStreamDestroy(t->stream);
@@ -1034,6 +1035,61 @@ int b200rec_table_apply_sgd_dev(b200rec_table_t t, int64_t n_unique_cap, const i
   return apply_sgd(t->dim ? t->dim : 1, n_unique_cap, n_unique, unique, t->dim ? emb_grad : nullptr,
                    w_grad, lr, t->emb.as<float>(), t->w.as<float>(),
                    stream ? (cudaStream_t)stream : t->stream);
+}
+
+// ---- optimizer step -----------------------------------------------------------------------------------
+static int zeroed(DevBuf& b, size_t bytes, cudaStream_t st) {
+  if (b.p && b.cap >= bytes) return B200REC_OK;
+  B200_TRY(b.reserve(bytes));
+  B200_CUDA(cudaMemsetAsync(b.p, 0, b.cap, st));
+  return B200REC_OK;
+}
+
+int b200rec_table_apply_optimizer_dev(b200rec_table_t t, int optimizer, float lr, float p1, float p2,
+                                      int64_t step, int64_t n_unique_cap, const int* n_unique,
+                                      const int* unique, const float* emb_grad, const float* w_grad,
+                                      void* stream) {
+  B200_GUARD_BEGIN
+  B200_REQUIRE(t && n_unique && unique, B200REC_ERR_ARG, "NULL argument");
+  B200_REQUIRE(optimizer >= B200REC_OPT_SGD && optimizer <= B200REC_OPT_ADAM, B200REC_ERR_ARG,
+               "unknown optimizer %d (OptimUtils.scala:6-11 raises MatchError)", optimizer);
+  B200_TRY(use_device(t->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : t->stream;
+  const size_t ne = (size_t)t->rows * (t->dim ? t->dim : 1) * sizeof(float), nw = (size_t)t->rows * sizeof(float);
+  if (optimizer != B200REC_OPT_SGD) {
+    B200_TRY(zeroed(t->s1e, ne, st));
+    B200_TRY(zeroed(t->s1w, nw, st));
+  }
+  if (optimizer == B200REC_OPT_ADAM) {
+    B200_TRY(zeroed(t->s2e, ne, st));
+    B200_TRY(zeroed(t->s2w, nw, st));
+  }
+  return opt_rows(optimizer, t->dim ? t->dim : 1, n_unique_cap, n_unique, unique, t->dim ? emb_grad : nullptr,
+                  w_grad, lr, p1, p2, step, t->emb.as<float>(), t->w.as<float>(), t->s1e.as<float>(),
+                  t->s2e.as<float>(), t->s1w.as<float>(), t->s2w.as<float>(), st);
+  B200_GUARD_END
+}
+
+int b200rec_model_apply_optimizer_dev(b200rec_model_t m, int optimizer, float lr, float p1, float p2,
+                                      int64_t step, void* stream) {
+  B200_GUARD_BEGIN
+  B200_REQUIRE(m, B200REC_ERR_ARG, "NULL model");
+  B200_REQUIRE(m->params_set && m->last_B > 0, B200REC_ERR_STATE, "no step has produced gradients yet");
+  B200_REQUIRE(optimizer >= B200REC_OPT_SGD && optimizer <= B200REC_OPT_ADAM, B200REC_ERR_ARG,
+               "unknown optimizer %d", optimizer);
+  B200_TRY(use_device(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+  const size_t n = (size_t)(m->mats_len + 1) * sizeof(float);
+  if (optimizer != B200REC_OPT_SGD) B200_TRY(zeroed(m->s1m, n, st));
+  if (optimizer == B200REC_OPT_ADAM) B200_TRY(zeroed(m->s2m, n, st));
+  if (m->mats_len)
+    B200_TRY(opt_dense(optimizer, m->mats_len, m->gmats.as<float>(), lr, p1, p2, step, m->p_mats.as<float>(),
+                       m->s1m.as<float>(), m->s2m.as<float>(), st));
+  // bias: gradient at gmats[mats_len], slots at s*m[mats_len]
+  return opt_dense(optimizer, 1, m->gmats.as<float>() + m->mats_len, lr, p1, p2, step, m->p_bias.as<float>(),
+                   m->s1m.p ? m->s1m.as<float>() + m->mats_len : nullptr,
+                   m->s2m.p ? m->s2m.as<float>() + m->mats_len : nullptr, st);
+  B200_GUARD_END
 }
 
 // ---- the reference's own BigDL modules -------------------------------------------------------------

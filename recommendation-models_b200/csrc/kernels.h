@@ -99,6 +99,13 @@ int table_init_uniform_sharded(float* table, float* wtable, long long rows, int 
 int apply_sgd(int K, long long cap, const int* n_unique, const int* unique, const float* G,
               const float* gw, float lr, float* table, float* wtable, cudaStream_t st);
 
+// ---------------------------------------------------------------- optim.cu ----------------------
+int opt_rows(int kind, int K, long long cap, const int* n_unique, const int* unique, const float* G,
+             const float* gw, float lr, float p1, float p2, long long step, float* table, float* wtable,
+             float* s1e, float* s2e, float* s1w, float* s2w, cudaStream_t st);
+int opt_dense(int kind, long long n, const float* g, float lr, float p1, float p2, long long step,
+              float* w, float* s1, float* s2, cudaStream_t st);
+
 // ---------------------------------------------------------------- dense.cu (SIMT fp32) --------
 // y[M,N] = act(x[M,K] W[N,K]^T + b[N])   (BigDL Linear + optional ReLU)
 // mode: 0 = fp32 FFMA (SIMT), 1 = 3xTF32 tcgen05, 2 = 1xTF32 tcgen05

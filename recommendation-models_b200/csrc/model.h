@@ -49,6 +49,7 @@ struct b200rec_table_s {
   int device = 0;
   cudaStream_t stream = nullptr;
   b200rec::DevBuf emb, w, stage_i, stage_e, stage_w, err;
+  b200rec::DevBuf s1e, s2e, s1w, s2w;  // optimizer slots (allocated on first use)
 };
 
 struct b200rec_model_s {
@@ -75,6 +76,7 @@ struct b200rec_model_s {
   DevBuf d_feats, d_targets, d_index, stage_a, stage_b;
   DevBuf X, wnz, S, first, second, branch, preds, dlogit, dXd, dw, gA, gB, scratch;
   DevBuf uniq, G, gwU, wpack;
+  DevBuf s1m, s2m;  // optimizer slots of [mats | bias]
   DevBuf x0, gx0, gy, gnA, gnB, pooled, gpooled;
   DevBuf xL, s_cross, g_xL;
   DevBuf ip, gip, pre, hbuf;

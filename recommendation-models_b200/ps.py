@@ -112,6 +112,7 @@ class ParRecModel:
         field per sample, sample-major."""
         feats, targets = L.i32(feats), L.f32(targets)
         B = targets.shape[0]
+        self._last_nnz = feats.shape[0]
         loss = C.c_float(0)
         L.check(L.lib().b200rec_step(self.model.handle, self.table.handle, B, L.ptr(feats),
                                      L.ptr(targets), C.byref(loss)))
@@ -123,6 +124,35 @@ class ParRecModel:
         L.check(L.lib().b200rec_predict(self.model.handle, self.table.handle, batchSize, L.ptr(feats),
                                         L.ptr(preds)))
         return preds
+
+    # ---- optimizer step: rec/optim/OptimUtils.scala:5-12 + Async*.scala defaults -------------------
+    _DEFAULTS = {"sgd": (0.0, 0.0), "momentum": (0.9, 0.0), "adagrad": (0.9, 0.0), "adam": (0.99, 0.9)}
+
+    def applyOptimizer(self, optim, stepSize, p1=None, p2=None):
+        """What the PS does with the pushed gradients (ParRecModel.push* :201-267 -> optim.asycUpdate):
+        update the touched table rows and the dense params in place on the GPU.  `optim` is the
+        reference's name ("sgd" | "momentum" | "adagrad" | "adam"; anything else raises, like the
+        MatchError of OptimUtils.scala:6-11).  Arithmetic: textbook forms, parity unpinned."""
+        name = optim.lower()
+        if name not in L.OPTIMIZERS:
+            raise ValueError(f"unknown optimizer {optim!r}")
+        d1, d2 = self._DEFAULTS[name]
+        p1 = d1 if p1 is None else p1
+        p2 = d2 if p2 is None else p2
+        self._opt_step = getattr(self, "_opt_step", 0) + 1
+        lib, m, t = L.lib(), self.model, self.table
+        ptrs = [C.c_void_p() for _ in range(7)]
+        L.check(lib.b200rec_step_result_ptrs(m.handle, *[C.byref(p) for p in ptrs]))
+        _, n_unique, unique, emb_grad, w_grad, _, _ = [p.value for p in ptrs]
+        sp = C.c_void_p()
+        L.check(lib.b200rec_model_stream(m.handle, C.byref(sp)))
+        cap = self._last_nnz
+        L.check(lib.b200rec_table_apply_optimizer_dev(t.handle, L.OPTIMIZERS[name], stepSize, p1, p2,
+                                                      self._opt_step, cap, n_unique, unique, emb_grad,
+                                                      w_grad, sp))
+        L.check(lib.b200rec_model_apply_optimizer_dev(m.handle, L.OPTIMIZERS[name], stepSize, p1, p2,
+                                                      self._opt_step, sp))
+        L.check(lib.b200rec_model_sync(m.handle))
 
     def stepResults(self):
         """Gradients of the last optimize: dict(loss, unique, emb_grad, w_grad, bias_grad, mats_grad)."""
