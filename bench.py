@@ -393,6 +393,8 @@ def main():
     ap.add_argument("--rows", type=int, default=39 * (1 << 18))
     ap.add_argument("--gemm-mode", type=int, default=None, help="0 fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: NVLink peer-memory exchange fused into the kernels, or NCCL all-to-all")
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of the CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

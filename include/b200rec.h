@@ -244,7 +244,28 @@ int b200rec_table_lookup_padded_dev(b200rec_table_t t, int64_t n, const int* loc
  * buffers the next all-to-all sends to the owners).  Dense gradients / loss stay in the handle. */
 int b200rec_step_rows_dev(b200rec_model_t m, int batch_size, const int* slots, const float* rows_emb,
                           const float* rows_w, int64_t n_rows, const float* targets,
-                          float* grad_emb_slots, float* grad_w_slots, void* stream);
+                          float* grad_emb_slots, float* grad_w_slots, int grads_by_slot, void* stream);
+
+/* ---- the same exchange over NVLink peer memory instead of NCCL ------------------------------------
+ * The id dispatch, the row return and the gradient push are stores into the PEERS' buffers issued by
+ * the producing kernels (fused gather + dispatch); release/acquire flags in peer memory order them
+ * (csrc/p2p.cu).  peer_* are arrays of `world` device pointers, one per rank, to symmetric buffers
+ * (the host maps them, e.g. torch symmetric memory or cudaIpc): ids_in[world*cap] int (double-buffered
+ * by the caller, reset to -1 one step ahead), rows_in[world*cap*K], w_in[world*cap], grad_in, gw_in
+ * (same shapes), flags[3*world] int (zero-initialised).  `step` counts from 1 and must increase. */
+int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, int world, int rank, int64_t period,
+                                 int cap, int step, const int* feats, void* const* peer_ids_in,
+                                 void* const* peer_flags, int* dst, int* overflow, void* stream);
+/* spin (device side) until every rank's flag of `phase` (0 ids, 1 rows, 2 grads) has reached `step` */
+int b200rec_p2p_wait_dev(b200rec_model_t m, const int* flags_local, int phase, int world, int step,
+                         void* stream);
+int b200rec_p2p_gather_dev(b200rec_model_t m, b200rec_table_t t, int world, int rank, int cap, int step,
+                           const int* ids_in, void* const* peer_rows_in, void* const* peer_w_in,
+                           void* const* peer_flags, void* stream);
+int b200rec_p2p_push_grads_dev(b200rec_model_t m, int64_t nnz, int world, int rank, int cap, int step,
+                               const int* dst, const float* emb_grad, const float* w_grad,
+                               void* const* peer_grad_in, void* const* peer_gw_in,
+                               void* const* peer_flags, void* stream);
 /* Plain SGD on the touched rows: E[id] -= lr * G[id], w[id] -= lr * gw[id] (rec/optim/
  * AsyncSGD.scala:10-31 applies the pushed gradient on the PS; textbook form, parity unpinned). */
 int b200rec_table_apply_sgd_dev(b200rec_table_t t, int64_t n_unique_cap, const int* n_unique,

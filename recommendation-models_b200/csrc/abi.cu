@@ -922,7 +922,9 @@ static int fill_segsum(Model* m, int dim, int64_t nnz, int key_bits, int drop_pa
                        float* w_out, int* n_unique_dev, SegSum& a) {
   B200_REQUIRE(m && n_unique_dev && unique_out, B200REC_ERR_ARG, "NULL argument");
   B200_REQUIRE(nnz >= 0 && nnz < (1LL << 31), B200REC_ERR_ARG, "bad nnz");
-  a.n = nnz; a.K = dim > 0 ? dim : 4; a.key_bits = drop_pad ? 32 : (key_bits > 0 ? key_bits : 31);
+  // padding (-1 = all ones) still sorts last when one extra key bit is kept above the ids' bits
+  a.n = nnz; a.K = dim > 0 ? dim : 4;
+  a.key_bits = key_bits > 0 ? (drop_pad ? (key_bits < 31 ? key_bits + 1 : 32) : key_bits) : (drop_pad ? 32 : 31);
   a.drop_pad = drop_pad != 0;
   a.feats = feats; a.dE = dim > 0 ? emb_grad : nullptr; a.dw = w_grad;
   a.unique = unique_out; a.G = dim > 0 ? emb_out : nullptr; a.gw = w_out;
@@ -1000,7 +1002,7 @@ int b200rec_shard_plan_dev(b200rec_model_t m, int64_t nnz, int world, int64_t pe
 
 int b200rec_step_rows_dev(b200rec_model_t m, int batch_size, const int* slots, const float* rows_emb,
                           const float* rows_w, int64_t n_rows, const float* targets,
-                          float* grad_emb_slots, float* grad_w_slots, void* stream) {
+                          float* grad_emb_slots, float* grad_w_slots, int grads_by_slot, void* stream) {
   B200_GUARD_BEGIN
   B200_REQUIRE(m && slots && rows_w && targets && grad_w_slots, B200REC_ERR_ARG, "NULL argument");
   B200_REQUIRE(m->params_set, B200REC_ERR_STATE, "b200rec_model_set_params must be called before a step");
@@ -1019,11 +1021,79 @@ int b200rec_step_rows_dev(b200rec_model_t m, int batch_size, const int* slots, c
   a.targets = targets;
   a.dw_out = grad_w_slots;
   a.dE_out = m->kind == B200REC_LR ? nullptr : grad_emb_slots;
-  a.out_slot = slots;
+  a.out_slot = grads_by_slot ? slots : nullptr;
   a.dbias_out = scal + 1;
   a.gmats_out = m->gmats.as<float>();
   a.loss_out = scal + 0;
   return m->run(a, st);
+  B200_GUARD_END
+}
+
+// ---- NVLink peer-memory exchange (csrc/p2p.cu) -------------------------------------------------------
+static int fill_p2p(Model* m, int world, int rank, int step, void* const* peer_flags, P2P& c) {
+  B200_REQUIRE(m && peer_flags, B200REC_ERR_ARG, "NULL argument");
+  B200_REQUIRE(world >= 1 && world <= P2P_MAX && rank >= 0 && rank < world, B200REC_ERR_ARG,
+               "bad rank %d / world %d (peer exchange supports up to %d GPUs)", rank, world, P2P_MAX);
+  if (!m->p2p_ctr.p) {
+    B200_TRY(m->p2p_ctr.reserve(16));
+    B200_CUDA(cudaMemset(m->p2p_ctr.p, 0, 16));
+  }
+  c.world = world; c.rank = rank; c.step = step;
+  c.block_counter = m->p2p_ctr.as<unsigned>();
+  for (int p = 0; p < world; ++p) c.flags[p] = (int*)peer_flags[p];
+  return B200REC_OK;
+}
+
+int b200rec_p2p_wait_dev(b200rec_model_t m, const int* flags_local, int phase, int world, int step,
+                         void* stream) {
+  B200_REQUIRE(m && flags_local && phase >= 0 && phase < 3, B200REC_ERR_ARG, "bad argument");
+  B200_TRY(use_device(m->device));
+  return p2p_wait(flags_local, phase, world, step, stream ? (cudaStream_t)stream : m->stream);
+}
+
+int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, int world, int rank, int64_t period,
+                                 int cap, int step, const int* feats, void* const* peer_ids_in,
+                                 void* const* peer_flags, int* dst, int* overflow, void* stream) {
+  B200_GUARD_BEGIN
+  P2P c;
+  B200_TRY(fill_p2p(m, world, rank, step, peer_flags, c));
+  B200_REQUIRE(peer_ids_in && dst && overflow && (feats || nnz == 0), B200REC_ERR_ARG, "NULL argument");
+  B200_TRY(use_device(m->device));
+  PeerI ids;
+  for (int p = 0; p < world; ++p) ids.p[p] = (int*)peer_ids_in[p];
+  return p2p_plan(m->plan, nnz, period, cap, feats, dst, overflow, c, ids,
+                  stream ? (cudaStream_t)stream : m->stream);
+  B200_GUARD_END
+}
+
+int b200rec_p2p_gather_dev(b200rec_model_t m, b200rec_table_t t, int world, int rank, int cap, int step,
+                           const int* ids_in, void* const* peer_rows_in, void* const* peer_w_in,
+                           void* const* peer_flags, void* stream) {
+  B200_GUARD_BEGIN
+  P2P c;
+  B200_TRY(fill_p2p(m, world, rank, step, peer_flags, c));
+  B200_REQUIRE(t && ids_in && peer_rows_in && peer_w_in, B200REC_ERR_ARG, "NULL argument");
+  B200_TRY(use_device(m->device));
+  PeerF rows, w;
+  for (int p = 0; p < world; ++p) { rows.p[p] = (float*)peer_rows_in[p]; w.p[p] = (float*)peer_w_in[p]; }
+  return p2p_gather(t->rows, t->dim ? t->dim : 4, cap, ids_in, t->dim ? t->emb.as<float>() : nullptr,
+                    t->w.as<float>(), c, rows, w, t->err.as<int>(), stream ? (cudaStream_t)stream : m->stream);
+  B200_GUARD_END
+}
+
+int b200rec_p2p_push_grads_dev(b200rec_model_t m, int64_t nnz, int world, int rank, int cap, int step,
+                               const int* dst, const float* emb_grad, const float* w_grad,
+                               void* const* peer_grad_in, void* const* peer_gw_in,
+                               void* const* peer_flags, void* stream) {
+  B200_GUARD_BEGIN
+  P2P c;
+  B200_TRY(fill_p2p(m, world, rank, step, peer_flags, c));
+  B200_REQUIRE(dst && w_grad && peer_grad_in && peer_gw_in, B200REC_ERR_ARG, "NULL argument");
+  B200_TRY(use_device(m->device));
+  PeerF g, gw;
+  for (int p = 0; p < world; ++p) { g.p[p] = (float*)peer_grad_in[p]; gw.p[p] = (float*)peer_gw_in[p]; }
+  return p2p_push_grads(nnz, m->kind == B200REC_LR ? 4 : m->K, cap, dst, m->kind == B200REC_LR ? nullptr : emb_grad,
+                        w_grad, c, g, gw, stream ? (cudaStream_t)stream : m->stream);
   B200_GUARD_END
 }
 

@@ -93,6 +93,22 @@ struct ShardPlanWorkspace {
 // dst[n]: slot (owner*cap + position) of non-zero i; overflow[0] |= 1 when a bucket exceeds cap.
 int shard_plan(ShardPlanWorkspace& ws, long long n, int world, long long period, int cap,
                const int* feats, int* send_ids, int* dst, int* overflow, cudaStream_t st);
+// ---------------------------------------------------------------- p2p.cu (NVLink peer exchange) --
+constexpr int P2P_MAX = 8;
+struct PeerI { int* p[P2P_MAX]; };
+struct PeerF { float* p[P2P_MAX]; };
+struct P2P {
+  int world, rank, step;
+  unsigned* block_counter;   // local, zero-initialised; wraps back to 0 through atomicInc
+  int* flags[P2P_MAX];       // every rank's flags[3][world]
+};
+int p2p_wait(const int* flags, int phase, int world, int step, cudaStream_t st);
+int p2p_plan(ShardPlanWorkspace& ws, long long n, long long period, int cap, const int* feats, int* dst,
+             int* overflow, const P2P& c, const PeerI& ids_in, cudaStream_t st);
+int p2p_gather(long long rows, int K, int cap, const int* ids_in, const float* table, const float* wtable,
+               const P2P& c, const PeerF& rows_in, const PeerF& w_in, int* err, cudaStream_t st);
+int p2p_push_grads(long long n, int K, int cap, const int* dst, const float* dE, const float* dw,
+                   const P2P& c, const PeerF& grad_in, const PeerF& gw_in, cudaStream_t st);
 int table_init_uniform_sharded(float* table, float* wtable, long long rows, int K, uint64_t seed,
                                float lo, float hi, int rank, int world, long long period,
                                cudaStream_t st);

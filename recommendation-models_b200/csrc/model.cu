@@ -127,7 +127,7 @@ void b200rec_model_s::destroy() {
   if (side) cudaStreamSynchronize(side);
   DevBuf* bufs[] = {&p_bias, &p_mats, &gmats, &scal, &d_feats, &d_targets, &d_index, &X, &wnz, &S,
                     &first, &second, &branch, &preds, &dlogit, &dXd, &dw, &gA, &gB, &scratch,
-                    &uniq, &G, &gwU, &wpack, &s1m, &s2m, &x0, &gx0, &gy, &gnA, &gnB, &pooled, &gpooled, &xL, &s_cross,
+                    &uniq, &G, &gwU, &wpack, &s1m, &s2m, &p2p_ctr, &x0, &gx0, &gy, &gnA, &gnB, &pooled, &gpooled, &xL, &s_cross,
                     &g_xL, &ip, &gip, &pre, &hbuf, &stage_a, &stage_b};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : acts) b.release();

@@ -77,6 +77,7 @@ struct b200rec_model_s {
   DevBuf X, wnz, S, first, second, branch, preds, dlogit, dXd, dw, gA, gB, scratch;
   DevBuf uniq, G, gwU, wpack;
   DevBuf s1m, s2m;  // optimizer slots of [mats | bias]
+  DevBuf p2p_ctr;   // block-completion counter of the peer-exchange kernels
   DevBuf x0, gx0, gy, gnA, gnB, pooled, gpooled;
   DevBuf xL, s_cross, g_xL;
   DevBuf ip, gip, pre, hbuf;

@@ -12,8 +12,6 @@
 //     send_ids[owner * cap + slot] = local row (or -1 padding)
 // Slot order within an owner is the non-zero order i ascending (stable counting sort), so the
 // owner's in-order segment sum sees a deterministic order: by source rank, then by i.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "kernels.h"
 
 namespace b200rec {
@@ -25,10 +23,6 @@ int ShardPlanWorkspace::reserve(long long n) {
   B200_TRY(vals.reserve(ni * 4));
   B200_TRY(perm.reserve(ni * 4));
   B200_TRY(offsets.reserve(64 * 4));
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
-                                  (const unsigned*)nullptr, (unsigned*)nullptr, (int)ni, 0, 8);
-  B200_TRY(cub_tmp.reserve(bytes + 1024));
   return B200REC_OK;
 }
 void ShardPlanWorkspace::release() {
@@ -36,29 +30,107 @@ void ShardPlanWorkspace::release() {
   cub_tmp.release();
 }
 
-__global__ void shard_owner_kernel(long long n, int world, long long period, const int* feats,
-                                   unsigned* owner, unsigned* iota, int* send_ids, long long n_send) {
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t < n) {
-    const long long id = feats[t];
-    owner[t] = (unsigned)((id + id / period) % world);
-    iota[t] = (unsigned)t;
-  }
-  // the slot buffer starts as all padding
-  for (long long i = t; i < n_send; i += (long long)gridDim.x * blockDim.x) send_ids[i] = -1;
+// ---- stable counting sort of the non-zeros by owner (world <= 32): three tiny kernels ---------------
+// A radix sort of 1..3 key bits is all fixed overhead; here: (1) per-block owner histograms,
+// (2) one block scans them into per-(block, owner) offsets, (3) every block ranks its items per owner
+// with ballots (stable: block order, then thread order) and scatters owner / position to sorted order.
+constexpr int CS_ITEMS = 2048;   // items per block
+constexpr int CS_MAXW = 32;
+
+__device__ __forceinline__ int owner_of(long long id, int world, long long period) {
+  return (int)((id + id / period) % world);
 }
 
-// offsets[o] = first sorted position whose owner >= o  (o = 0..world)
-__global__ void shard_offsets_kernel(long long n, int world, const unsigned* owner_sorted,
-                                     int* offsets) {
-  const int o = threadIdx.x;
-  if (o > world) return;
-  long long lo = 0, hi = n;
-  while (lo < hi) {
-    const long long mid = (lo + hi) >> 1;
-    if (owner_sorted[mid] < (unsigned)o) lo = mid + 1; else hi = mid;
+__global__ void __launch_bounds__(256) shard_hist_kernel(long long n, int world, long long period,
+                                                         const int* feats, int* block_counts,
+                                                         int* send_ids, long long n_send) {
+  __shared__ int cnt[CS_MAXW];
+  if (threadIdx.x < CS_MAXW) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * CS_ITEMS;
+  for (int k = threadIdx.x; k < CS_ITEMS; k += 256) {
+    const long long i = base + k;
+    if (i < n) atomicAdd(&cnt[owner_of(feats[i], world, period)], 1);   // integer counts: order-free
   }
-  offsets[o] = (int)lo;
+  __syncthreads();
+  if (threadIdx.x < world) block_counts[blockIdx.x * world + threadIdx.x] = cnt[threadIdx.x];
+  // the slot buffer starts as all padding
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_send; i += (long long)gridDim.x * 256)
+    send_ids[i] = -1;
+}
+
+// offsets[o] = first sorted position of owner o (o = 0..world); block_counts -> exclusive offsets.
+// The counts are staged in shared memory in chunks (coalesced) so the serial scan runs at smem latency.
+__global__ void __launch_bounds__(256) shard_scan_kernel(int n_blocks, int world, int* block_counts,
+                                                         int* offsets) {
+  constexpr int CHUNK = 4096;            // ints of block_counts per pass
+  __shared__ int buf[CHUNK];
+  __shared__ int tot[CS_MAXW + 1];
+  const int o = threadIdx.x;
+  int run = 0;
+  const int blocks_per_pass = CHUNK / world;
+  for (int b0 = 0; b0 < n_blocks; b0 += blocks_per_pass) {
+    const int nb = min(blocks_per_pass, n_blocks - b0);
+    for (int k = threadIdx.x; k < nb * world; k += 256) buf[k] = block_counts[b0 * world + k];
+    __syncthreads();
+    if (o < world) {
+      for (int b = 0; b < nb; ++b) {
+        const int c = buf[b * world + o];
+        buf[b * world + o] = run;
+        run += c;
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb * world; k += 256) block_counts[b0 * world + k] = buf[k];
+    __syncthreads();
+  }
+  if (o < world) tot[o] = run;
+  __syncthreads();
+  if (o == 0) {
+    int r = 0;
+    for (int k = 0; k < world; ++k) {
+      offsets[k] = r;
+      r += tot[k];
+    }
+    offsets[world] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256) shard_rank_kernel(long long n, int world, long long period,
+                                                         const int* feats, const int* block_offsets,
+                                                         const int* offsets, unsigned* owner_sorted,
+                                                         unsigned* perm) {
+  __shared__ int run[CS_MAXW];            // items of each owner already ranked in this block
+  __shared__ int wcnt[8][CS_MAXW];        // per-warp counts of the current pass
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < CS_MAXW) run[threadIdx.x] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * CS_ITEMS;
+  for (int k0 = 0; k0 < CS_ITEMS; k0 += 256) {
+    const long long i = base + k0 + threadIdx.x;
+    const int o = i < n ? owner_of(feats[i], world, period) : -1;
+    int my_rank = 0;
+    for (int q = 0; q < world; ++q) {
+      const unsigned m = __ballot_sync(0xffffffffu, o == q);
+      if (o == q) my_rank = __popc(m & ((1u << lane) - 1));
+      if (lane == 0) wcnt[warp][q] = __popc(m);
+    }
+    __syncthreads();
+    if (o >= 0) {
+      int before = run[o];
+      for (int w = 0; w < warp; ++w) before += wcnt[w][o];
+      const int pos = offsets[o] + block_offsets[blockIdx.x * world + o] + before + my_rank;
+      owner_sorted[pos] = (unsigned)o;
+      perm[pos] = (unsigned)i;
+    }
+    __syncthreads();
+    if (threadIdx.x < world) {
+      int c = 0;
+      for (int w = 0; w < 8; ++w) c += wcnt[w][threadIdx.x];
+      run[threadIdx.x] += c;
+    }
+    __syncthreads();
+  }
 }
 
 __global__ void shard_place_kernel(long long n, int world, int cap, const int* feats,
@@ -78,34 +150,34 @@ __global__ void shard_place_kernel(long long n, int world, int cap, const int* f
   dst[i] = o * cap + slot;
 }
 
-int shard_plan(ShardPlanWorkspace& ws, long long n, int world, long long period, int cap,
-               const int* feats, int* send_ids, int* dst, int* overflow, cudaStream_t st) {
-  ProfTag tag("shard_plan");
-  B200_REQUIRE(world >= 1 && world <= 32, B200REC_ERR_ARG, "world size %d out of range", world);
+// owner keys -> stable sort -> per-owner offsets (ws.keys_sorted / ws.perm / ws.offsets).  When
+// send_ids is given it is reset to all padding on the way.
+static int shard_sort_impl(ShardPlanWorkspace& ws, long long n, int world, long long period,
+                           const int* feats, int* send_ids, long long n_send, cudaStream_t st) {
+  B200_REQUIRE(world >= 1 && world <= CS_MAXW, B200REC_ERR_ARG, "world size %d out of range", world);
   B200_REQUIRE(period >= world && period % world == 0, B200REC_ERR_ARG,
                "shard period %lld must be a positive multiple of the world size %d", period, world);
   B200_TRY(ws.reserve(n));
-  const long long n_send = (long long)world * cap;
-  const long long cover = n > n_send ? n : n_send;
-  int grid = cdiv(cover, 256);
-  if (grid > 148 * 16) grid = 148 * 16;
-  if (grid < cdiv(n, 256)) grid = cdiv(n, 256);
-  if (grid < 1) grid = 1;
-  B200_LAUNCH(shard_owner_kernel, grid, 256, 0, st, n, world, period, feats, ws.keys.as<unsigned>(),
-              ws.vals.as<unsigned>(), send_ids, n_send);
-  if (n > 0) {
-    size_t tmp = ws.cub_tmp.cap;
-    int bits = 1;
-    while ((1 << bits) < world) ++bits;
-    if (tl_prof) tl_prof->begin("cub::DeviceRadixSort::SortPairs", st);
-    B200_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp.p, tmp, ws.keys.as<unsigned>(),
-                                              ws.keys_sorted.as<unsigned>(), ws.vals.as<unsigned>(),
-                                              ws.perm.as<unsigned>(), (int)n, 0, bits, st));
-    if (tl_prof) tl_prof->end(st);
-    g_launches.fetch_add(3, std::memory_order_relaxed);
-  }
-  B200_LAUNCH(shard_offsets_kernel, 1, 64, 0, st, n, world, ws.keys_sorted.as<unsigned>(),
-              ws.offsets.as<int>());
+  const int n_blocks = cdiv(n > 0 ? n : 1, CS_ITEMS);
+  B200_TRY(ws.keys.reserve((size_t)n_blocks * world * sizeof(int) + 64));   // block counts / offsets
+  int* block_counts = ws.keys.as<int>();
+  B200_LAUNCH(shard_hist_kernel, n_blocks, 256, 0, st, n, world, period, feats, block_counts, send_ids, n_send);
+  B200_LAUNCH(shard_scan_kernel, 1, 256, 0, st, n_blocks, world, block_counts, ws.offsets.as<int>());
+  B200_LAUNCH(shard_rank_kernel, n_blocks, 256, 0, st, n, world, period, feats, block_counts,
+              ws.offsets.as<int>(), ws.keys_sorted.as<unsigned>(), ws.perm.as<unsigned>());
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+int shard_sort(ShardPlanWorkspace& ws, long long n, int world, long long period, const int* feats,
+               cudaStream_t st) {
+  return shard_sort_impl(ws, n, world, period, feats, nullptr, 0, st);
+}
+
+int shard_plan(ShardPlanWorkspace& ws, long long n, int world, long long period, int cap,
+               const int* feats, int* send_ids, int* dst, int* overflow, cudaStream_t st) {
+  ProfTag tag("shard_plan");
+  B200_TRY(shard_sort_impl(ws, n, world, period, feats, send_ids, (long long)world * cap, st));
   if (n > 0)
     B200_LAUNCH(shard_place_kernel, cdiv(n, 256), 256, 0, st, n, world, cap, feats,
                 ws.keys_sorted.as<unsigned>(), ws.perm.as<unsigned>(), ws.offsets.as<int>(), send_ids,

@@ -61,6 +61,7 @@ class GpuOps:
         L.check(self.lib.b200rec_model_stream(model.handle, C.byref(sp)))
         self.stream_ptr = sp.value
         self.stream = torch.cuda.ExternalStream(sp.value, device=device)
+        self.key_bits = max(1, int(spec.rows_local - 1).bit_length())   # bits of a local row id
         self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
         self.n_unique = torch.zeros(1, dtype=torch.int32, device=device)
         # dense gradient views of the handle's buffers (for the allreduce)
@@ -106,16 +107,16 @@ class GpuOps:
     def step_rows(self, dst, rows, w, targets, grad_rows, grad_w):
         L.check(self.lib.b200rec_step_rows_dev(self.model.handle, self.B, dst.data_ptr(), rows.data_ptr(),
                                                w.data_ptr(), w.numel(), targets.data_ptr(),
-                                               grad_rows.data_ptr(), grad_w.data_ptr(), self.stream_ptr))
+                                               grad_rows.data_ptr(), grad_w.data_ptr(), 1, self.stream_ptr))
 
     def segsum_sort(self, recv_ids, unique):
         """Owner-side sort of the received ids on the side stream (overlaps the dense math)."""
-        L.check(self.lib.b200rec_segsum_sort_dev(self.model.handle, self.K, recv_ids.numel(), 32, 1,
+        L.check(self.lib.b200rec_segsum_sort_dev(self.model.handle, self.K, recv_ids.numel(), self.key_bits, 1,
                                                  recv_ids.data_ptr(), unique.data_ptr(),
                                                  self.n_unique.data_ptr(), self.stream_ptr))
 
     def segsum(self, recv_ids, grad_rows, grad_w, unique, G, gw):
-        L.check(self.lib.b200rec_segsum_reduce_dev(self.model.handle, self.K, recv_ids.numel(), 32, 1,
+        L.check(self.lib.b200rec_segsum_reduce_dev(self.model.handle, self.K, recv_ids.numel(), self.key_bits, 1,
                                                    recv_ids.data_ptr(), grad_rows.data_ptr(),
                                                    grad_w.data_ptr(), unique.data_ptr(), G.data_ptr(),
                                                    gw.data_ptr(), self.n_unique.data_ptr(), self.stream_ptr))
@@ -174,6 +175,80 @@ class ShardedParRecModel:
                 o.apply_sgd(self.unique, self.G, self.gw, lr)
 
 
+class P2PShardedParRecModel:
+    """The same step with the exchange over NVLink peer memory (csrc/p2p.cu) instead of NCCL
+    all-to-alls: kernels store ids / rows / gradients straight into the peers' symmetric buffers and
+    order them with release/acquire flags; only the dense allreduce is still an NCCL call.  Buffers
+    come from torch symmetric memory (plumbing: it maps every rank's allocation into this process)."""
+
+    def __init__(self, ops, dist, spec, batch, n_fields, dim, cap=None, group=None):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        self.ops, self.dist, self.spec, self.group = ops, dist, spec, group
+        self.B, self.F, self.K = batch, n_fields, dim
+        N, G = batch * n_fields, spec.world
+        assert G <= 8, "peer exchange supports up to 8 GPUs (one NVLink box)"
+        self.cap = cap or int(N / G * 1.25) + 1024
+        ops.cap = self.cap
+        n = G * self.cap
+        dev = ops.device
+        gname = (group or dist.group.WORLD).group_name
+
+        def symm(numel, dtype, fill):
+            t = symm_mem.empty(numel, dtype=dtype, device=dev)
+            t.fill_(fill)
+            h = symm_mem.rendezvous(t, gname)
+            ptrs = (C.c_void_p * G)(*[int(p) for p in h.buffer_ptrs])
+            return t, h, ptrs
+
+        self.ids_in = [symm(n, torch.int32, -1) for _ in range(2)]
+        self.rows_in = symm(n * dim, torch.float32, 0)
+        self.w_in = symm(n, torch.float32, 0)
+        self.grad_in = symm(n * dim, torch.float32, 0)
+        self.gw_in = symm(n, torch.float32, 0)
+        self.flags = symm(3 * G, torch.int32, 0)
+        self.dst = torch.empty(N, dtype=torch.int32, device=dev)
+        self.grad_rows = torch.empty(N * dim, dtype=torch.float32, device=dev)   # per-nnz, local order
+        self.grad_w = torch.empty(N, dtype=torch.float32, device=dev)
+        self.unique = torch.empty(n, dtype=torch.int32, device=dev)
+        self.G = torch.empty(n * dim, dtype=torch.float32, device=dev)
+        self.gw = torch.empty(n, dtype=torch.float32, device=dev)
+        self.step = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def optimize(self, feats, targets, lr=None):
+        o, lib, m = self.ops, self.ops.lib, self.ops.model.handle
+        G, r, cap, st = self.spec.world, self.spec.rank, self.cap, o.stream_ptr
+        self.step += 1
+        t = self.step
+        cur, nxt = self.ids_in[t & 1], self.ids_in[(t + 1) & 1]
+        flags_t, _, flags_p = self.flags
+        with o.stream_ctx():
+            nxt[0].fill_(-1)   # nobody writes this buffer before my next signal (see csrc/p2p.cu)
+            L.check(lib.b200rec_p2p_dispatch_ids_dev(m, feats.numel(), G, r, self.spec.period, cap, t,
+                                                     feats.data_ptr(), cur[2], flags_p, self.dst.data_ptr(),
+                                                     o.overflow.data_ptr(), st))
+            L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 0, G, t, st))
+            o.segsum_sort(cur[0], self.unique)                               # owner-side sort, side stream
+            L.check(lib.b200rec_p2p_gather_dev(m, o.table.handle, G, r, cap, t, cur[0].data_ptr(),
+                                               self.rows_in[2], self.w_in[2], flags_p, st))
+            L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 1, G, t, st))
+            L.check(lib.b200rec_step_rows_dev(m, self.B, self.dst.data_ptr(), self.rows_in[0].data_ptr(),
+                                              self.w_in[0].data_ptr(), self.w_in[0].numel(),
+                                              targets.data_ptr(), self.grad_rows.data_ptr(),
+                                              self.grad_w.data_ptr(), 0, st))
+            work = self.dist.all_reduce(o.dense_grads(), group=self.group, async_op=True)
+            L.check(lib.b200rec_p2p_push_grads_dev(m, feats.numel(), G, r, cap, t, self.dst.data_ptr(),
+                                                   self.grad_rows.data_ptr(), self.grad_w.data_ptr(),
+                                                   self.grad_in[2], self.gw_in[2], flags_p, st))
+            L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 2, G, t, st))
+            o.segsum(cur[0], self.grad_in[0], self.gw_in[0], self.unique, self.G, self.gw)
+            work.wait()
+            if lr is not None:
+                o.apply_sgd(self.unique, self.G, self.gw, lr)
+
+
 # ------------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1, launched by torchrun): weak scaling, per-GPU batch fixed
 # ------------------------------------------------------------------------------------------------------
@@ -207,7 +282,8 @@ def bench(args, pkg):
     ps = pkg.ParRecModel(model, table)
     ps.setParams(np.array([0.1], np.float32), synth.init_mats(B.SEED_PARAMS, model.getMatsSize()))
     ops = GpuOps(pkg, model, table, spec, batch, None, torch, dev)
-    sh = ShardedParRecModel(ops, dist, spec, batch, F, K)
+    use_p2p = getattr(args, "exchange", "p2p") == "p2p" and world <= 8
+    sh = (P2PShardedParRecModel if use_p2p else ShardedParRecModel)(ops, dist, spec, batch, F, K)
     ops.cap = sh.cap
     W, Ksteps = args.warmup, args.steps
     nb = min(W + Ksteps, 32)
@@ -289,8 +365,9 @@ def bench(args, pkg):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.model} k={K} F={F} fc={fc} cin={cin} depth={depth} per-GPU batch={batch} "
                                    f"table_rows={rows} row-sharded over {world} GPUs (BASELINE configs[2]/[4])",
-                       "global_batch": batch * world, "parallelism": f"table row-sharded x{world} (NCCL all-to-all), "
-                       f"dense dp{world} (NCCL allreduce)", "bucket_capacity": sh.cap,
+                       "global_batch": batch * world, "parallelism": f"table row-sharded x{world} "
+                       f"({'NVLink peer-memory stores fused into the gather / gradient kernels' if use_p2p else 'NCCL all-to-all'}), "
+                       f"dense dp{world} (NCCL allreduce)", "exchange": "p2p" if use_p2p else "nccl", "bucket_capacity": sh.cap,
                        "bucket_overflow": int(ovf.item()),
                        "l2": "table shard > L2; new ids every step; no explicit flush", "gemm_mode": args.gemm_mode},
             "clocks": clk,

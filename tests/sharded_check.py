@@ -123,7 +123,7 @@ def run(rank, world, backend, device=None):
     import __graft_entry__ as g
     pkg = g.load_package()
     from oracle import refport
-    from recommendation_models_b200.sharded import GpuOps, ShardedParRecModel, ShardSpec
+    from recommendation_models_b200.sharded import GpuOps, P2PShardedParRecModel, ShardedParRecModel, ShardSpec
     synth = pkg.synth
     spec = ShardSpec(ROWS, world, rank)
     cap = int(B * F / world * 1.5) + 64
@@ -143,8 +143,11 @@ def run(rank, world, backend, device=None):
                                                 synth.init_mats(SEED_PARAMS, model.getMatsSize()))
         ops = GpuOps(pkg, model, table, spec, B, cap, torch, dev)
         tf, tt = torch.from_numpy(feats).to(dev), torch.from_numpy(targets).to(dev)
-    sh = ShardedParRecModel(ops, dist, spec, B, F, K, cap=cap)
+    cls = P2PShardedParRecModel if backend == "p2p" else ShardedParRecModel
+    sh = cls(ops, dist, spec, B, F, K, cap=cap)
     sh.optimize(tf, tt)
+    if backend == "p2p":   # a second step exercises the double-buffered id slots and the step flags
+        sh.optimize(tf, tt)
     if backend != "gloo":
         torch.cuda.synchronize()
         assert int(ops.overflow.item()) == 0
@@ -194,8 +197,9 @@ if __name__ == "__main__":
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    u = run(rank, world, "nccl", device=local)
-    print(f"rank {rank}/{world}: sharded step ok, {u} owned distinct rows", flush=True)
+    for backend in ("nccl", "p2p"):
+        u = run(rank, world, backend, device=local)
+        print(f"rank {rank}/{world}: sharded step ok ({backend}), {u} owned distinct rows", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.stdout.flush()
