@@ -217,12 +217,19 @@ int b200rec_segsum_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, in
 
 /* The two halves of b200rec_segsum_dev, for overlap: the sort needs only the ids and runs on the
  * handle's side stream forked from `stream`; the reduce joins it.  Pass the same arguments to both. */
-int b200rec_segsum_sort_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
+/* `ws` selects one of the handle's three sort workspaces / side streams: 0 and 2 for a batch's own
+ * ids (two, so the NEXT batch's ids can be sorted while the current step runs), 1 for the ids an
+ * owner received.  The sorts overlap the dense math of the step. */
+int b200rec_segsum_sort_dev(b200rec_model_t m, int ws, int dim, int64_t nnz, int key_bits, int drop_pad,
                             const int* feats, int* unique_out, int* n_unique_dev, void* stream);
-int b200rec_segsum_reduce_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
+int b200rec_segsum_reduce_dev(b200rec_model_t m, int ws, int dim, int64_t nnz, int key_bits, int drop_pad,
                               const int* feats, const float* emb_grad, const float* w_grad,
                               int* unique_out, float* emb_out, float* w_out, int* n_unique_dev,
                               void* stream);
+/* make `stream` wait for the sort of workspace ws */
+int b200rec_segsum_join_dev(b200rec_model_t m, int ws, void* stream);
+/* inv_out[i] = position of non-zero i's id in the sorted distinct ids of workspace ws's last sort */
+int b200rec_segsum_inverse_dev(b200rec_model_t m, int ws, int64_t nnz, int* inv_out, void* stream);
 
 /* ---- row-sharded table: the PS pull / push as NCCL all-to-all of fixed-capacity slot buffers -------
  * The Angel PS range-shards the matrices over PS nodes (ColumnRangePartitioner,
@@ -253,17 +260,24 @@ int b200rec_step_rows_dev(b200rec_model_t m, int batch_size, const int* slots, c
  * (the host maps them, e.g. torch symmetric memory or cudaIpc): ids_in[world*cap] int (double-buffered
  * by the caller, reset to -1 one step ahead), rows_in[world*cap*K], w_in[world*cap], grad_in, gw_in
  * (same shapes), flags[3*world] int (zero-initialised).  `step` counts from 1 and must increase. */
-int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, int world, int rank, int64_t period,
-                                 int cap, int step, const int* feats, void* const* peer_ids_in,
-                                 void* const* peer_flags, int* dst, int* overflow, void* stream);
+/* n_dev (may be NULL): device count of valid ids, e.g. the distinct ids of the batch (dedup before the
+ * exchange: every id is requested once, its gradient is pre-reduced locally and pushed once). */
+int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, const int* n_dev, int world, int rank,
+                                 int64_t period, int cap, int step, const int* feats,
+                                 void* const* peer_ids_in, void* const* peer_flags, int* dst,
+                                 int* overflow, void* stream);
+/* dst[i] = dst_unique[inv[i]]: slot of every non-zero from the slot of its distinct id */
+int b200rec_p2p_compose_dst_dev(b200rec_model_t m, int64_t nnz, const int* inv, const int* dst_unique,
+                                int* dst, void* stream);
 /* spin (device side) until every rank's flag of `phase` (0 ids, 1 rows, 2 grads) has reached `step` */
 int b200rec_p2p_wait_dev(b200rec_model_t m, const int* flags_local, int phase, int world, int step,
                          void* stream);
 int b200rec_p2p_gather_dev(b200rec_model_t m, b200rec_table_t t, int world, int rank, int cap, int step,
                            const int* ids_in, void* const* peer_rows_in, void* const* peer_w_in,
                            void* const* peer_flags, void* stream);
-int b200rec_p2p_push_grads_dev(b200rec_model_t m, int64_t nnz, int world, int rank, int cap, int step,
-                               const int* dst, const float* emb_grad, const float* w_grad,
+int b200rec_p2p_push_grads_dev(b200rec_model_t m, int64_t nnz, const int* n_dev, int world, int rank,
+                               int cap, int step, const int* dst, const float* emb_grad,
+                               const float* w_grad,
                                void* const* peer_grad_in, void* const* peer_gw_in,
                                void* const* peer_flags, void* stream);
 /* Plain SGD on the touched rows: E[id] -= lr * G[id], w[id] -= lr * gw[id] (rec/optim/

@@ -66,16 +66,20 @@ SIGNATURES = {
     "b200rec_step_nnz_grad_ptrs": [vp, C.POINTER(vp), C.POINTER(vp)],
     "b200rec_step_gathered_dev": [vp, C.c_int, vp, vp, vp, vp],
     "b200rec_segsum_dev": [vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp],
-    "b200rec_segsum_sort_dev": [vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp],
-    "b200rec_segsum_reduce_dev": [vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp],
+    "b200rec_segsum_sort_dev": [vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp],
+    "b200rec_segsum_reduce_dev": [vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp],
+    "b200rec_segsum_join_dev": [vp, C.c_int, vp],
+    "b200rec_segsum_inverse_dev": [vp, C.c_int, C.c_int64, vp, vp],
+    "b200rec_p2p_compose_dst_dev": [vp, C.c_int64, vp, vp, vp, vp],
     "b200rec_table_init_uniform_sharded": [vp, C.c_uint64, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int64],
     "b200rec_shard_plan_dev": [vp, C.c_int64, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp, vp],
     "b200rec_table_lookup_padded_dev": [vp, C.c_int64, vp, vp, vp, vp],
     "b200rec_step_rows_dev": [vp, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int, vp],
-    "b200rec_p2p_dispatch_ids_dev": [vp, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp],
+    "b200rec_p2p_dispatch_ids_dev": [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp,
+                                     vp],
     "b200rec_p2p_wait_dev": [vp, vp, C.c_int, C.c_int, C.c_int, vp],
     "b200rec_p2p_gather_dev": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp],
-    "b200rec_p2p_push_grads_dev": [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp],
+    "b200rec_p2p_push_grads_dev": [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp],
     "b200rec_table_apply_sgd_dev": [vp, C.c_int64, vp, vp, vp, vp, C.c_float, vp],
     "b200rec_table_apply_optimizer_dev": [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_int64, vp, vp, vp,
                                           vp, vp],

@@ -932,23 +932,38 @@ static int fill_segsum(Model* m, int dim, int64_t nnz, int key_bits, int drop_pa
   return B200REC_OK;
 }
 
-int b200rec_segsum_sort_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
+int b200rec_segsum_sort_dev(b200rec_model_t m, int ws, int dim, int64_t nnz, int key_bits, int drop_pad,
                             const int* feats, int* unique_out, int* n_unique_dev, void* stream) {
   B200_GUARD_BEGIN
   SegSum a;
   B200_TRY(fill_segsum(m, dim, nnz, key_bits, drop_pad, feats, nullptr, nullptr, unique_out, nullptr,
                        nullptr, n_unique_dev, a));
+  B200_REQUIRE(ws >= 0 && ws <= 2, B200REC_ERR_ARG, "workspace must be 0, 1 or 2");
   B200_TRY(use_device(m->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
-  B200_CUDA(cudaEventRecord(m->ev_fork, st));
-  B200_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-  B200_TRY(segsum_sort(m->seg, a, m->side));
-  B200_CUDA(cudaEventRecord(m->ev_join, m->side));
+  cudaStream_t side = m->side_of(ws);
+  B200_CUDA(cudaEventRecord(m->fork_of(ws), st));
+  B200_CUDA(cudaStreamWaitEvent(side, m->fork_of(ws), 0));
+  B200_TRY(segsum_sort(m->ws_of(ws), a, side));
+  B200_CUDA(cudaEventRecord(m->join_of(ws), side));
   return B200REC_OK;
   B200_GUARD_END
 }
 
-int b200rec_segsum_reduce_dev(b200rec_model_t m, int dim, int64_t nnz, int key_bits, int drop_pad,
+int b200rec_segsum_join_dev(b200rec_model_t m, int ws, void* stream) {
+  B200_REQUIRE(m && ws >= 0 && ws <= 2, B200REC_ERR_ARG, "bad argument");
+  B200_TRY(use_device(m->device));
+  B200_CUDA(cudaStreamWaitEvent(stream ? (cudaStream_t)stream : m->stream, m->join_of(ws), 0));
+  return B200REC_OK;
+}
+
+int b200rec_segsum_inverse_dev(b200rec_model_t m, int ws, int64_t nnz, int* inv_out, void* stream) {
+  B200_REQUIRE(m && inv_out && ws >= 0 && ws <= 2, B200REC_ERR_ARG, "bad argument");
+  B200_TRY(use_device(m->device));
+  return segsum_inverse(m->ws_of(ws), nnz, inv_out, stream ? (cudaStream_t)stream : m->stream);
+}
+
+int b200rec_segsum_reduce_dev(b200rec_model_t m, int ws, int dim, int64_t nnz, int key_bits, int drop_pad,
                               const int* feats, const float* emb_grad, const float* w_grad,
                               int* unique_out, float* emb_out, float* w_out, int* n_unique_dev,
                               void* stream) {
@@ -956,10 +971,11 @@ int b200rec_segsum_reduce_dev(b200rec_model_t m, int dim, int64_t nnz, int key_b
   SegSum a;
   B200_TRY(fill_segsum(m, dim, nnz, key_bits, drop_pad, feats, emb_grad, w_grad, unique_out, emb_out,
                        w_out, n_unique_dev, a));
+  B200_REQUIRE(ws >= 0 && ws <= 2, B200REC_ERR_ARG, "workspace must be 0, 1 or 2");
   B200_TRY(use_device(m->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
-  B200_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
-  if (a.dE || a.dw) B200_TRY(segsum_reduce(m->seg, a, st));
+  B200_CUDA(cudaStreamWaitEvent(st, m->join_of(ws), 0));
+  if (a.dE || a.dw) B200_TRY(segsum_reduce(m->ws_of(ws), a, st));
   return B200REC_OK;
   B200_GUARD_END
 }
@@ -1051,9 +1067,10 @@ int b200rec_p2p_wait_dev(b200rec_model_t m, const int* flags_local, int phase, i
   return p2p_wait(flags_local, phase, world, step, stream ? (cudaStream_t)stream : m->stream);
 }
 
-int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, int world, int rank, int64_t period,
-                                 int cap, int step, const int* feats, void* const* peer_ids_in,
-                                 void* const* peer_flags, int* dst, int* overflow, void* stream) {
+int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, const int* n_dev, int world, int rank,
+                                 int64_t period, int cap, int step, const int* feats,
+                                 void* const* peer_ids_in, void* const* peer_flags, int* dst,
+                                 int* overflow, void* stream) {
   B200_GUARD_BEGIN
   P2P c;
   B200_TRY(fill_p2p(m, world, rank, step, peer_flags, c));
@@ -1061,7 +1078,7 @@ int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, int world, int 
   B200_TRY(use_device(m->device));
   PeerI ids;
   for (int p = 0; p < world; ++p) ids.p[p] = (int*)peer_ids_in[p];
-  return p2p_plan(m->plan, nnz, period, cap, feats, dst, overflow, c, ids,
+  return p2p_plan(m->plan, nnz, n_dev, period, cap, feats, dst, overflow, c, ids,
                   stream ? (cudaStream_t)stream : m->stream);
   B200_GUARD_END
 }
@@ -1081,8 +1098,16 @@ int b200rec_p2p_gather_dev(b200rec_model_t m, b200rec_table_t t, int world, int 
   B200_GUARD_END
 }
 
-int b200rec_p2p_push_grads_dev(b200rec_model_t m, int64_t nnz, int world, int rank, int cap, int step,
-                               const int* dst, const float* emb_grad, const float* w_grad,
+int b200rec_p2p_compose_dst_dev(b200rec_model_t m, int64_t nnz, const int* inv, const int* dst_unique,
+                                int* dst, void* stream) {
+  B200_REQUIRE(m && inv && dst_unique && dst, B200REC_ERR_ARG, "NULL argument");
+  B200_TRY(use_device(m->device));
+  return p2p_compose(nnz, inv, dst_unique, dst, stream ? (cudaStream_t)stream : m->stream);
+}
+
+int b200rec_p2p_push_grads_dev(b200rec_model_t m, int64_t nnz, const int* n_dev, int world, int rank,
+                               int cap, int step, const int* dst, const float* emb_grad,
+                               const float* w_grad,
                                void* const* peer_grad_in, void* const* peer_gw_in,
                                void* const* peer_flags, void* stream) {
   B200_GUARD_BEGIN
@@ -1092,7 +1117,7 @@ int b200rec_p2p_push_grads_dev(b200rec_model_t m, int64_t nnz, int world, int ra
   B200_TRY(use_device(m->device));
   PeerF g, gw;
   for (int p = 0; p < world; ++p) { g.p[p] = (float*)peer_grad_in[p]; gw.p[p] = (float*)peer_gw_in[p]; }
-  return p2p_push_grads(nnz, m->kind == B200REC_LR ? 4 : m->K, cap, dst, m->kind == B200REC_LR ? nullptr : emb_grad,
+  return p2p_push_grads(nnz, n_dev, m->kind == B200REC_LR ? 4 : m->K, cap, dst, m->kind == B200REC_LR ? nullptr : emb_grad,
                         w_grad, c, g, gw, stream ? (cudaStream_t)stream : m->stream);
   B200_GUARD_END
 }

@@ -81,6 +81,7 @@ struct SegSum {
 int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st);
 // reduce half (needs dE / dw)
 int segsum_reduce(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st);
+int segsum_inverse(SegSumWorkspace& ws, long long n, int* inv, cudaStream_t st);
 // ---------------------------------------------------------------- shard.cu (row-sharded table) --
 // owner(id) = (id + id / period) % world, local row = id / world (period is a multiple of world, so
 // the `world` consecutive ids of a block rotate over the ranks: a bijection id <-> (owner, row)).
@@ -91,6 +92,8 @@ struct ShardPlanWorkspace {
 };
 // send_ids[world*cap]: local row ids grouped by owner in slot order (-1 = padding);
 // dst[n]: slot (owner*cap + position) of non-zero i; overflow[0] |= 1 when a bucket exceeds cap.
+int shard_sort(ShardPlanWorkspace& ws, long long n, const int* n_dev, int world, long long period,
+               const int* feats, cudaStream_t st);
 int shard_plan(ShardPlanWorkspace& ws, long long n, int world, long long period, int cap,
                const int* feats, int* send_ids, int* dst, int* overflow, cudaStream_t st);
 // ---------------------------------------------------------------- p2p.cu (NVLink peer exchange) --
@@ -103,12 +106,14 @@ struct P2P {
   int* flags[P2P_MAX];       // every rank's flags[3][world]
 };
 int p2p_wait(const int* flags, int phase, int world, int step, cudaStream_t st);
-int p2p_plan(ShardPlanWorkspace& ws, long long n, long long period, int cap, const int* feats, int* dst,
-             int* overflow, const P2P& c, const PeerI& ids_in, cudaStream_t st);
+// n_dev (optional): device count of valid ids (<= n); ids beyond it are ignored
+int p2p_plan(ShardPlanWorkspace& ws, long long n, const int* n_dev, long long period, int cap,
+             const int* feats, int* dst, int* overflow, const P2P& c, const PeerI& ids_in, cudaStream_t st);
+int p2p_compose(long long n, const int* inv, const int* dst_unique, int* dst, cudaStream_t st);
 int p2p_gather(long long rows, int K, int cap, const int* ids_in, const float* table, const float* wtable,
                const P2P& c, const PeerF& rows_in, const PeerF& w_in, int* err, cudaStream_t st);
-int p2p_push_grads(long long n, int K, int cap, const int* dst, const float* dE, const float* dw,
-                   const P2P& c, const PeerF& grad_in, const PeerF& gw_in, cudaStream_t st);
+int p2p_push_grads(long long n, const int* n_dev, int K, int cap, const int* dst, const float* dE,
+                   const float* dw, const P2P& c, const PeerF& grad_in, const PeerF& gw_in, cudaStream_t st);
 int table_init_uniform_sharded(float* table, float* wtable, long long rows, int K, uint64_t seed,
                                float lo, float hi, int rank, int world, long long period,
                                cudaStream_t st);

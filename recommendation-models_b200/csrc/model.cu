@@ -110,6 +110,12 @@ int b200rec_model_s::init(int kind_, int F_, int K_, const int* fc_, int n_fc, c
   B200_CUDA(cudaSetDevice(device));
   B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&side3, cudaStreamNonBlocking));
+  B200_CUDA(cudaEventCreateWithFlags(&ev_fork3, cudaEventDisableTiming));
+  B200_CUDA(cudaEventCreateWithFlags(&ev_join3, cudaEventDisableTiming));
+  B200_CUDA(cudaEventCreateWithFlags(&ev_fork2, cudaEventDisableTiming));
+  B200_CUDA(cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   B200_CUDA(cudaMallocHost(&h_scal, 64));
@@ -125,6 +131,8 @@ void b200rec_model_s::destroy() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
   if (side) cudaStreamSynchronize(side);
+  if (side2) cudaStreamSynchronize(side2);
+  if (side3) cudaStreamSynchronize(side3);
   DevBuf* bufs[] = {&p_bias, &p_mats, &gmats, &scal, &d_feats, &d_targets, &d_index, &X, &wnz, &S,
                     &first, &second, &branch, &preds, &dlogit, &dXd, &dw, &gA, &gB, &scratch,
                     &uniq, &G, &gwU, &wpack, &s1m, &s2m, &p2p_ctr, &x0, &gx0, &gy, &gnA, &gnB, &pooled, &gpooled, &xL, &s_cross,
@@ -133,6 +141,8 @@ void b200rec_model_s::destroy() {
   for (auto& b : acts) b.release();
   for (auto& b : xl) b.release();
   seg.release();
+  seg2.release();
+  seg3.release();
   plan.release();
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   graph_exec = nullptr;
@@ -141,6 +151,12 @@ void b200rec_model_s::destroy() {
   if (ev_join) cudaEventDestroy(ev_join);
   if (stream) cudaStreamDestroy(stream);
   if (side) cudaStreamDestroy(side);
+  if (side2) cudaStreamDestroy(side2);
+  if (side3) cudaStreamDestroy(side3);
+  if (ev_fork3) cudaEventDestroy(ev_fork3);
+  if (ev_join3) cudaEventDestroy(ev_join3);
+  if (ev_fork2) cudaEventDestroy(ev_fork2);
+  if (ev_join2) cudaEventDestroy(ev_join2);
 }
 
 int b200rec_model_s::reserve(int B, long long nnz) {

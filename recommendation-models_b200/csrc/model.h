@@ -59,8 +59,9 @@ struct b200rec_model_s {
   b200rec::MlpPlan mlp;
   std::vector<long long> cin_w, cin_b;
   long long out_off = 0;
-  cudaStream_t stream = nullptr, side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t stream = nullptr, side = nullptr, side2 = nullptr, side3 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+  cudaEvent_t ev_fork3 = nullptr, ev_join3 = nullptr;
   float* h_scal = nullptr;  // pinned 16 words: loss, dbias, n_unique, -, err, sorted
   bool params_set = false;
   // CUDA graph of the resident step (one per (B, table, gemm_mode)); captured after one eager warm-up
@@ -82,7 +83,12 @@ struct b200rec_model_s {
   DevBuf xL, s_cross, g_xL;
   DevBuf ip, gip, pre, hbuf;
   std::vector<DevBuf> acts, xl;
-  b200rec::SegSumWorkspace seg;
+  // sort workspaces: 0 the batch's ids, 1 the ids an owner received, 2 the NEXT batch's ids (prefetch)
+  b200rec::SegSumWorkspace seg, seg2, seg3;
+  b200rec::SegSumWorkspace& ws_of(int i) { return i == 0 ? seg : (i == 1 ? seg2 : seg3); }
+  cudaStream_t side_of(int i) const { return i == 0 ? side : (i == 1 ? side2 : side3); }
+  cudaEvent_t fork_of(int i) const { return i == 0 ? ev_fork : (i == 1 ? ev_fork2 : ev_fork3); }
+  cudaEvent_t join_of(int i) const { return i == 0 ? ev_join : (i == 1 ? ev_join2 : ev_join3); }
   b200rec::ShardPlanWorkspace plan;
 
   int init(int kind, int F, int K, const int* fc, int n_fc, const int* cin, int n_cin, int depth,

@@ -57,9 +57,10 @@ int p2p_wait(const int* flags, int phase, int world, int step, cudaStream_t st) 
 }
 
 // ---- phase 0: ids to their owners ------------------------------------------------------------------
-__global__ void p2p_place_kernel(long long n, int cap, const int* feats, const unsigned* owner_sorted,
-                                 const unsigned* perm, const int* offsets, int* dst, int* overflow,
-                                 P2P c, PeerI ids_in) {
+__global__ void p2p_place_kernel(long long n, const int* n_dev, int cap, const int* feats,
+                                 const unsigned* owner_sorted, const unsigned* perm, const int* offsets,
+                                 int* dst, int* overflow, P2P c, PeerI ids_in) {
+  if (n_dev) n = min(n, (long long)*n_dev);
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (p < n) {
     const int o = (int)owner_sorted[p];
@@ -77,16 +78,26 @@ __global__ void p2p_place_kernel(long long n, int cap, const int* feats, const u
 }
 
 // shard.cu: owner keys -> stable sort -> per-owner offsets
-int shard_sort(ShardPlanWorkspace& ws, long long n, int world, long long period, const int* feats,
-               cudaStream_t st);
-
-int p2p_plan(ShardPlanWorkspace& ws, long long n, long long period, int cap, const int* feats, int* dst,
-             int* overflow, const P2P& c, const PeerI& ids_in, cudaStream_t st) {
+int p2p_plan(ShardPlanWorkspace& ws, long long n, const int* n_dev, long long period, int cap,
+             const int* feats, int* dst, int* overflow, const P2P& c, const PeerI& ids_in, cudaStream_t st) {
   ProfTag tag("p2p_dispatch_ids");
-  B200_TRY(shard_sort(ws, n, c.world, period, feats, st));
+  B200_TRY(shard_sort(ws, n, n_dev, c.world, period, feats, st));
   int grid = cdiv(n > 0 ? n : 1, 256);
-  B200_LAUNCH(p2p_place_kernel, grid, 256, 0, st, n, cap, feats, ws.keys_sorted.as<unsigned>(),
+  B200_LAUNCH(p2p_place_kernel, grid, 256, 0, st, n, n_dev, cap, feats, ws.keys_sorted.as<unsigned>(),
               ws.perm.as<unsigned>(), ws.offsets.as<int>(), dst, overflow, c, ids_in);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+// per-nnz slot = slot of the non-zero's distinct id  (dispatch over distinct ids: dedup before exchange)
+__global__ void p2p_compose_kernel(long long n, const int* inv, const int* dst_unique, int* dst) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = dst_unique[inv[i]];
+}
+int p2p_compose(long long n, const int* inv, const int* dst_unique, int* dst, cudaStream_t st) {
+  if (n <= 0) return B200REC_OK;
+  ProfTag tag("p2p_dispatch_ids");
+  B200_LAUNCH(p2p_compose_kernel, cdiv(n, 256), 256, 0, st, n, inv, dst_unique, dst);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -138,10 +149,12 @@ int p2p_gather(long long rows, int K, int cap, const int* ids_in, const float* t
 
 // ---- phase 2: per-nnz gradients stored into the owners' buffers (after the dense backward) ----------
 template <int LPR>
-__global__ void __launch_bounds__(256) p2p_push_grads_kernel(long long n, int cap, const int* dst,
-                                                             const float* dE, const float* dw, P2P c,
-                                                             PeerF grad_in, PeerF gw_in) {
+__global__ void __launch_bounds__(256) p2p_push_grads_kernel(long long n, const int* n_dev, int cap,
+                                                             const int* dst, const float* dE,
+                                                             const float* dw, P2P c, PeerF grad_in,
+                                                             PeerF gw_in) {
   constexpr int K = 4 * LPR;
+  if (n_dev) n = min(n, (long long)*n_dev);
   const long long n_vec = n * LPR;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_vec;
        t += (long long)gridDim.x * blockDim.x) {
@@ -156,18 +169,18 @@ __global__ void __launch_bounds__(256) p2p_push_grads_kernel(long long n, int ca
   p2p_signal(c, 2);
 }
 
-int p2p_push_grads(long long n, int K, int cap, const int* dst, const float* dE, const float* dw,
-                   const P2P& c, const PeerF& grad_in, const PeerF& gw_in, cudaStream_t st) {
+int p2p_push_grads(long long n, const int* n_dev, int K, int cap, const int* dst, const float* dE,
+                   const float* dw, const P2P& c, const PeerF& grad_in, const PeerF& gw_in, cudaStream_t st) {
   ProfTag tag("p2p_push_grads");
   int grid = cdiv(n * (K / 4 > 0 ? K / 4 : 1), 256);
   if (grid > 148 * 16) grid = 148 * 16;
   if (grid < 1) grid = 1;
   switch (K) {
-    case 4: B200_LAUNCH(p2p_push_grads_kernel<1>, grid, 256, 0, st, n, cap, dst, dE, dw, c, grad_in, gw_in); break;
-    case 8: B200_LAUNCH(p2p_push_grads_kernel<2>, grid, 256, 0, st, n, cap, dst, dE, dw, c, grad_in, gw_in); break;
-    case 16: B200_LAUNCH(p2p_push_grads_kernel<4>, grid, 256, 0, st, n, cap, dst, dE, dw, c, grad_in, gw_in); break;
-    case 32: B200_LAUNCH(p2p_push_grads_kernel<8>, grid, 256, 0, st, n, cap, dst, dE, dw, c, grad_in, gw_in); break;
-    case 64: B200_LAUNCH(p2p_push_grads_kernel<16>, grid, 256, 0, st, n, cap, dst, dE, dw, c, grad_in, gw_in); break;
+    case 4: B200_LAUNCH(p2p_push_grads_kernel<1>, grid, 256, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
+    case 8: B200_LAUNCH(p2p_push_grads_kernel<2>, grid, 256, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
+    case 16: B200_LAUNCH(p2p_push_grads_kernel<4>, grid, 256, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
+    case 32: B200_LAUNCH(p2p_push_grads_kernel<8>, grid, 256, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
+    case 64: B200_LAUNCH(p2p_push_grads_kernel<16>, grid, 256, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
     default: set_error("p2p exchange supports embeddingDim in {4,8,16,32,64}, got %d", K); return B200REC_ERR_ARG;
   }
   B200_CHECK_LAUNCH();

@@ -109,6 +109,18 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
   return B200REC_OK;
 }
 
+// inv[i] = index of the distinct id of non-zero i (valid after segsum_sort on the same workspace)
+__global__ void seg_inverse_kernel(long long n, const unsigned* perm, const int* seg_idx, int* inv) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p < n) inv[perm[p]] = seg_idx[p] - 1;
+}
+int segsum_inverse(SegSumWorkspace& ws, long long n, int* inv, cudaStream_t st) {
+  if (n <= 0) return B200REC_OK;
+  B200_LAUNCH(seg_inverse_kernel, cdiv(n, 256), 256, 0, st, n, ws.vals_b.as<unsigned>(), ws.vals_a.as<int>(), inv);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
 // ---- in-order segment sums --------------------------------------------------------------------
 template <int LPR>
 __global__ void __launch_bounds__(256) segsum_short_kernel(const int* n_unique,

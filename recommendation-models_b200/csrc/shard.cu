@@ -41,10 +41,12 @@ __device__ __forceinline__ int owner_of(long long id, int world, long long perio
   return (int)((id + id / period) % world);
 }
 
-__global__ void __launch_bounds__(256) shard_hist_kernel(long long n, int world, long long period,
-                                                         const int* feats, int* block_counts,
-                                                         int* send_ids, long long n_send) {
+__global__ void __launch_bounds__(256) shard_hist_kernel(long long n, const int* n_dev, int world,
+                                                         long long period, const int* feats,
+                                                         int* block_counts, int* send_ids,
+                                                         long long n_send) {
   __shared__ int cnt[CS_MAXW];
+  if (n_dev) n = min(n, (long long)*n_dev);
   if (threadIdx.x < CS_MAXW) cnt[threadIdx.x] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * CS_ITEMS;
@@ -96,10 +98,11 @@ __global__ void __launch_bounds__(256) shard_scan_kernel(int n_blocks, int world
   }
 }
 
-__global__ void __launch_bounds__(256) shard_rank_kernel(long long n, int world, long long period,
-                                                         const int* feats, const int* block_offsets,
-                                                         const int* offsets, unsigned* owner_sorted,
-                                                         unsigned* perm) {
+__global__ void __launch_bounds__(256) shard_rank_kernel(long long n, const int* n_dev, int world,
+                                                         long long period, const int* feats,
+                                                         const int* block_offsets, const int* offsets,
+                                                         unsigned* owner_sorted, unsigned* perm) {
+  if (n_dev) n = min(n, (long long)*n_dev);
   __shared__ int run[CS_MAXW];            // items of each owner already ranked in this block
   __shared__ int wcnt[8][CS_MAXW];        // per-warp counts of the current pass
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -152,8 +155,9 @@ __global__ void shard_place_kernel(long long n, int world, int cap, const int* f
 
 // owner keys -> stable sort -> per-owner offsets (ws.keys_sorted / ws.perm / ws.offsets).  When
 // send_ids is given it is reset to all padding on the way.
-static int shard_sort_impl(ShardPlanWorkspace& ws, long long n, int world, long long period,
-                           const int* feats, int* send_ids, long long n_send, cudaStream_t st) {
+static int shard_sort_impl(ShardPlanWorkspace& ws, long long n, const int* n_dev, int world,
+                           long long period, const int* feats, int* send_ids, long long n_send,
+                           cudaStream_t st) {
   B200_REQUIRE(world >= 1 && world <= CS_MAXW, B200REC_ERR_ARG, "world size %d out of range", world);
   B200_REQUIRE(period >= world && period % world == 0, B200REC_ERR_ARG,
                "shard period %lld must be a positive multiple of the world size %d", period, world);
@@ -161,23 +165,23 @@ static int shard_sort_impl(ShardPlanWorkspace& ws, long long n, int world, long 
   const int n_blocks = cdiv(n > 0 ? n : 1, CS_ITEMS);
   B200_TRY(ws.keys.reserve((size_t)n_blocks * world * sizeof(int) + 64));   // block counts / offsets
   int* block_counts = ws.keys.as<int>();
-  B200_LAUNCH(shard_hist_kernel, n_blocks, 256, 0, st, n, world, period, feats, block_counts, send_ids, n_send);
+  B200_LAUNCH(shard_hist_kernel, n_blocks, 256, 0, st, n, n_dev, world, period, feats, block_counts, send_ids, n_send);
   B200_LAUNCH(shard_scan_kernel, 1, 256, 0, st, n_blocks, world, block_counts, ws.offsets.as<int>());
-  B200_LAUNCH(shard_rank_kernel, n_blocks, 256, 0, st, n, world, period, feats, block_counts,
+  B200_LAUNCH(shard_rank_kernel, n_blocks, 256, 0, st, n, n_dev, world, period, feats, block_counts,
               ws.offsets.as<int>(), ws.keys_sorted.as<unsigned>(), ws.perm.as<unsigned>());
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }
 
-int shard_sort(ShardPlanWorkspace& ws, long long n, int world, long long period, const int* feats,
-               cudaStream_t st) {
-  return shard_sort_impl(ws, n, world, period, feats, nullptr, 0, st);
+int shard_sort(ShardPlanWorkspace& ws, long long n, const int* n_dev, int world, long long period,
+               const int* feats, cudaStream_t st) {
+  return shard_sort_impl(ws, n, n_dev, world, period, feats, nullptr, 0, st);
 }
 
 int shard_plan(ShardPlanWorkspace& ws, long long n, int world, long long period, int cap,
                const int* feats, int* send_ids, int* dst, int* overflow, cudaStream_t st) {
   ProfTag tag("shard_plan");
-  B200_TRY(shard_sort_impl(ws, n, world, period, feats, send_ids, (long long)world * cap, st));
+  B200_TRY(shard_sort_impl(ws, n, nullptr, world, period, feats, send_ids, (long long)world * cap, st));
   if (n > 0)
     B200_LAUNCH(shard_place_kernel, cdiv(n, 256), 256, 0, st, n, world, cap, feats,
                 ws.keys_sorted.as<unsigned>(), ws.perm.as<unsigned>(), ws.offsets.as<int>(), send_ids,

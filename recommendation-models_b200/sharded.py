@@ -110,14 +110,14 @@ class GpuOps:
                                                grad_rows.data_ptr(), grad_w.data_ptr(), 1, self.stream_ptr))
 
     def segsum_sort(self, recv_ids, unique):
-        """Owner-side sort of the received ids on the side stream (overlaps the dense math)."""
-        L.check(self.lib.b200rec_segsum_sort_dev(self.model.handle, self.K, recv_ids.numel(), self.key_bits, 1,
-                                                 recv_ids.data_ptr(), unique.data_ptr(),
+        """Owner-side sort of the received ids on a side stream (overlaps the dense math)."""
+        L.check(self.lib.b200rec_segsum_sort_dev(self.model.handle, 1, self.K, recv_ids.numel(), self.key_bits,
+                                                 1, recv_ids.data_ptr(), unique.data_ptr(),
                                                  self.n_unique.data_ptr(), self.stream_ptr))
 
     def segsum(self, recv_ids, grad_rows, grad_w, unique, G, gw):
-        L.check(self.lib.b200rec_segsum_reduce_dev(self.model.handle, self.K, recv_ids.numel(), self.key_bits, 1,
-                                                   recv_ids.data_ptr(), grad_rows.data_ptr(),
+        L.check(self.lib.b200rec_segsum_reduce_dev(self.model.handle, 1, self.K, recv_ids.numel(),
+                                                   self.key_bits, 1, recv_ids.data_ptr(), grad_rows.data_ptr(),
                                                    grad_w.data_ptr(), unique.data_ptr(), G.data_ptr(),
                                                    gw.data_ptr(), self.n_unique.data_ptr(), self.stream_ptr))
 
@@ -210,27 +210,58 @@ class P2PShardedParRecModel:
         self.dst = torch.empty(N, dtype=torch.int32, device=dev)
         self.grad_rows = torch.empty(N * dim, dtype=torch.float32, device=dev)   # per-nnz, local order
         self.grad_w = torch.empty(N, dtype=torch.float32, device=dev)
+        # local dedup (one set per workspace 0 / 2: the next batch's ids are sorted ahead of time)
+        self.loc = {ws: dict(uniq=torch.empty(N, dtype=torch.int32, device=dev),
+                             n=torch.zeros(1, dtype=torch.int32, device=dev), feats=None) for ws in (0, 2)}
+        self.inv = torch.empty(N, dtype=torch.int32, device=dev)
+        self.dst_u = torch.empty(N, dtype=torch.int32, device=dev)
+        self.G_loc = torch.empty(N * dim, dtype=torch.float32, device=dev)
+        self.gw_loc = torch.empty(N, dtype=torch.float32, device=dev)
         self.unique = torch.empty(n, dtype=torch.int32, device=dev)
         self.G = torch.empty(n * dim, dtype=torch.float32, device=dev)
         self.gw = torch.empty(n, dtype=torch.float32, device=dev)
+        self.gbits = max(1, int(spec.rows_global - 1).bit_length())
         self.step = 0
         torch.cuda.synchronize()
         dist.barrier(group=group)
 
-    def optimize(self, feats, targets, lr=None):
+    def _sort_local(self, ws, feats):
+        o = self.ops
+        d = self.loc[ws]
+        L.check(o.lib.b200rec_segsum_sort_dev(o.model.handle, ws, self.K, feats.numel(), self.gbits, 0,
+                                              feats.data_ptr(), d["uniq"].data_ptr(), d["n"].data_ptr(),
+                                              o.stream_ptr))
+        d["feats"] = feats
+
+    def optimize(self, feats, targets, lr=None, next_feats=None):
+        """One step.  Every distinct id of the batch is requested once and its gradient, pre-reduced
+        locally in non-zero order, is pushed once (the owner then sums at most `world` rows per id, in
+        rank order).  `next_feats`: the ids of the following batch; their sort is started now on a
+        side stream so it is off the next step's critical path (input prefetch)."""
         o, lib, m = self.ops, self.ops.lib, self.ops.model.handle
         G, r, cap, st = self.spec.world, self.spec.rank, self.cap, o.stream_ptr
+        N = feats.numel()
         self.step += 1
         t = self.step
+        ws = 0 if t & 1 else 2
         cur, nxt = self.ids_in[t & 1], self.ids_in[(t + 1) & 1]
         flags_t, _, flags_p = self.flags
         with o.stream_ctx():
             nxt[0].fill_(-1)   # nobody writes this buffer before my next signal (see csrc/p2p.cu)
-            L.check(lib.b200rec_p2p_dispatch_ids_dev(m, feats.numel(), G, r, self.spec.period, cap, t,
-                                                     feats.data_ptr(), cur[2], flags_p, self.dst.data_ptr(),
-                                                     o.overflow.data_ptr(), st))
+            loc = self.loc[ws]
+            if loc["feats"] is not feats:
+                self._sort_local(ws, feats)
+            L.check(lib.b200rec_segsum_join_dev(m, ws, st))
+            L.check(lib.b200rec_segsum_inverse_dev(m, ws, N, self.inv.data_ptr(), st))
+            L.check(lib.b200rec_p2p_dispatch_ids_dev(m, N, loc["n"].data_ptr(), G, r, self.spec.period, cap, t,
+                                                     loc["uniq"].data_ptr(), cur[2], flags_p,
+                                                     self.dst_u.data_ptr(), o.overflow.data_ptr(), st))
+            L.check(lib.b200rec_p2p_compose_dst_dev(m, N, self.inv.data_ptr(), self.dst_u.data_ptr(),
+                                                    self.dst.data_ptr(), st))
             L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 0, G, t, st))
             o.segsum_sort(cur[0], self.unique)                               # owner-side sort, side stream
+            if next_feats is not None:
+                self._sort_local(2 - ws, next_feats)                         # next batch's ids, side stream
             L.check(lib.b200rec_p2p_gather_dev(m, o.table.handle, G, r, cap, t, cur[0].data_ptr(),
                                                self.rows_in[2], self.w_in[2], flags_p, st))
             L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 1, G, t, st))
@@ -239,14 +270,21 @@ class P2PShardedParRecModel:
                                               targets.data_ptr(), self.grad_rows.data_ptr(),
                                               self.grad_w.data_ptr(), 0, st))
             work = self.dist.all_reduce(o.dense_grads(), group=self.group, async_op=True)
-            L.check(lib.b200rec_p2p_push_grads_dev(m, feats.numel(), G, r, cap, t, self.dst.data_ptr(),
-                                                   self.grad_rows.data_ptr(), self.grad_w.data_ptr(),
-                                                   self.grad_in[2], self.gw_in[2], flags_p, st))
+            # local pre-reduce per distinct id (in non-zero order), then one push per distinct id
+            L.check(lib.b200rec_segsum_reduce_dev(m, ws, self.K, N, self.gbits, 0, feats.data_ptr(),
+                                                  self.grad_rows.data_ptr(), self.grad_w.data_ptr(),
+                                                  loc["uniq"].data_ptr(), self.G_loc.data_ptr(),
+                                                  self.gw_loc.data_ptr(), loc["n"].data_ptr(), st))
+            L.check(lib.b200rec_p2p_push_grads_dev(m, N, loc["n"].data_ptr(), G, r, cap, t,
+                                                   self.dst_u.data_ptr(), self.G_loc.data_ptr(),
+                                                   self.gw_loc.data_ptr(), self.grad_in[2], self.gw_in[2],
+                                                   flags_p, st))
             L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 2, G, t, st))
             o.segsum(cur[0], self.grad_in[0], self.gw_in[0], self.unique, self.G, self.gw)
             work.wait()
             if lr is not None:
                 o.apply_sgd(self.unique, self.G, self.gw, lr)
+            loc["feats"] = None
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -291,8 +329,15 @@ def bench(args, pkg):
     batches = [synth.make_feats(B.SEED_DATA, s * world + rank, batch, F, rows)[1] for s in range(nb)]
     dev_b = [(torch.from_numpy(f).to(dev), torch.from_numpy(synth.make_targets(B.SEED_DATA, f, batch, F)).to(dev))
              for f in batches]
+    def run_step(i):
+        f, t = dev_b[i % nb]
+        if use_p2p:
+            sh.optimize(f, t, next_feats=dev_b[(i + 1) % nb][0])   # the next batch's ids are known: prefetch
+        else:
+            sh.optimize(f, t)
+
     for i in range(W):
-        sh.optimize(*dev_b[i % nb])
+        run_step(i)
     torch.cuda.synchronize()
     dist.barrier()
     clocks = B.ClockSampler(local)
@@ -304,7 +349,7 @@ def bench(args, pkg):
     torch.cuda.synchronize()
     e0.record(ops.stream)
     for i in range(Ksteps):
-        sh.optimize(*dev_b[(W + i) % nb])
+        run_step(W + i)
     e1.record(ops.stream)
     torch.cuda.synchronize()
     dist.barrier()
@@ -349,7 +394,7 @@ def bench(args, pkg):
     # per-kernel pass on rank 0 (own kernels only; NCCL kernels are not in this list)
     L.profile_begin()
     for i in range(min(Ksteps, 10)):
-        sh.optimize(*dev_b[(W + i) % nb])
+        run_step(W + i)
     prof = L.profile_end()
     dist.barrier()
     if rank == 0:
