@@ -321,7 +321,20 @@ def bench(args, pkg):
     ps.setParams(np.array([0.1], np.float32), synth.init_mats(B.SEED_PARAMS, model.getMatsSize()))
     ops = GpuOps(pkg, model, table, spec, batch, None, torch, dev)
     use_p2p = getattr(args, "exchange", "p2p") == "p2p" and world <= 8
-    sh = (P2PShardedParRecModel if use_p2p else ShardedParRecModel)(ops, dist, spec, batch, F, K)
+    sh = None
+    if use_p2p:
+        # every rank must take the same path: agree on whether symmetric memory came up everywhere
+        try:
+            sh = P2PShardedParRecModel(ops, dist, spec, batch, F, K)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:  # noqa: BLE001  (no peer mapping on this box -> NCCL exchange)
+            sys.stderr.write(f"rank {rank}: peer-memory exchange unavailable ({e!r}); using NCCL all-to-all\n")
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1:
+            use_p2p, sh = False, None
+    if sh is None:
+        sh = ShardedParRecModel(ops, dist, spec, batch, F, K)
     ops.cap = sh.cap
     W, Ksteps = args.warmup, args.steps
     nb = min(W + Ksteps, 32)
