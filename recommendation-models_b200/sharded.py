@@ -303,8 +303,11 @@ def bench(args, pkg):
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
-    # NCCL prints its version banner on stdout when NCCL_DEBUG is set; keep stdout to the one JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is set; stdout must carry the one JSON
+    # line only: point fd 1 at stderr until the communicators exist (end of the warm-up)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=dev)
     synth = pkg.synth
     kind, fc, cin, depth = B.MODELS[args.model]
@@ -353,6 +356,9 @@ def bench(args, pkg):
         run_step(i)
     torch.cuda.synchronize()
     dist.barrier()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     clocks = B.ClockSampler(local)
     clocks.start()
     time.sleep(0.25)
