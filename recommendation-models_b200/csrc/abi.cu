@@ -31,6 +31,7 @@ int g_default_gemm_mode = 1;  // 3xTF32 tcgen05 wherever a tensor-core kernel ex
 thread_local Prof* tl_prof = nullptr;
 thread_local const char* tl_tag = nullptr;
 thread_local DevBuf* tl_pack = nullptr;
+thread_local PrePack* tl_prepack = nullptr;
 
 void Prof::begin(const char* name, cudaStream_t st) {
   if (n >= kMax) return;

@@ -54,6 +54,15 @@ extern thread_local const char* tl_tag;
 struct DevBuf;
 // weight-pack scratch of the handle / call that is currently running on this thread (tc_gemm.cu)
 extern thread_local DevBuf* tl_pack;
+// weights of the MLP tower packed ahead of time in two launches (tc_gemm.cu: tc_prepack_linear);
+// the GEMM launchers look their operand up here before packing it themselves
+struct PrePack {
+  struct Entry { const float* w; int fmt, N, K; size_t off; };   // fmt 0: forward, 1: gradInput
+  Entry e[16];
+  int n = 0;
+  DevBuf* blob = nullptr;
+};
+extern thread_local PrePack* tl_prepack;
 struct PackScope {
   DevBuf* prev;
   explicit PackScope(DevBuf* b) : prev(tl_pack) { tl_pack = b; }

@@ -187,6 +187,51 @@ int wcolsum(int M, int K, const float* d, const float* x, int ldx, float* gw, De
   return B200REC_OK;
 }
 
+// Linear(K -> 1) backward in ONE pass over its input a[M,K] (HigherOrderEncoder.scala:46-58, the
+// "-> 1" layer): g[m,k] = d[m] w[k] (a[m,k] > 0 if masked) for the layer below, and the chunk partials
+// of gw[k] = sum_m d[m] a[m,k] and gb = sum_m d[m]; colsum_stage2 finishes [gw | gb] (adjacent in mats).
+__global__ void __launch_bounds__(128) head_bwd_kernel(int M, int K, const float* d, const float* a,
+                                                       const float* w, bool mask, float* g,
+                                                       int rows_per_chunk, float* part) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  const int r0 = c * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+  if (k < K) {
+    const float wk = __ldg(w + k);
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float dm = __ldg(d + r);
+      const float av = a[(long long)r * K + k];
+      if (g) g[(long long)r * K + k] = (mask && !(av > 0.f)) ? 0.f : dm * wk;
+      s = fmaf(dm, av, s);
+    }
+    part[(long long)c * (K + 1) + k] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float sd = 0.f;
+    for (int r = r0; r < r1; ++r) sd += __ldg(d + r);
+    part[(long long)c * (K + 1) + K] = sd;
+  }
+}
+
+int head_layer_bwd(int M, int K, const float* d, const float* a, const float* w, bool mask, float* g,
+                   float* gw_gb, DevBuf& scratch, cudaStream_t st) {
+  if (M <= 0) return B200REC_OK;
+  int chunks = M / 32;
+  if (chunks > COLSUM_CHUNKS) chunks = COLSUM_CHUNKS;
+  if (chunks < 1) chunks = 1;
+  const int rows_per_chunk = cdiv(M, chunks);
+  chunks = cdiv(M, rows_per_chunk);
+  B200_TRY(scratch.reserve((size_t)chunks * (K + 1) * sizeof(float)));
+  float* part = scratch.as<float>();
+  dim3 g1(cdiv(K, 128), chunks);
+  B200_LAUNCH(head_bwd_kernel, g1, 128, 0, st, M, K, d, a, w, mask, g, rows_per_chunk, part);
+  B200_LAUNCH(colsum_stage2, cdiv((long long)(K + 1) * 32, 256), 256, 0, st, K + 1, chunks, part, 1.0f, false,
+              gw_gb);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
 // deterministic sum of n floats
 __global__ void reduce_stage1(long long n, const float* x, float* part) {
   __shared__ float sh[8];

@@ -148,6 +148,9 @@ int outer_rows(int M, int K, const float* d, const float* w, const float* mask, 
 // gw[K] = sum_m d[m] * x[m,k] ;  deterministic two-stage
 int wcolsum(int M, int K, const float* d, const float* x, int ldx, float* gw, DevBuf& scratch,
             cudaStream_t st);
+// Linear(K -> 1) backward fused: g (optional) = d (x) w (* (a > 0) if mask); gw_gb[K+1] = [sum d a | sum d]
+int head_layer_bwd(int M, int K, const float* d, const float* a, const float* w, bool mask, float* g,
+                   float* gw_gb, DevBuf& scratch, cudaStream_t st);
 // sum of n floats into out[0] (deterministic two-stage); scale applied
 int reduce_sum(long long n, const float* x, float scale, float* out, DevBuf& scratch,
                cudaStream_t st);
@@ -227,6 +230,8 @@ int tc_linear_bwd_input(int M, int N, int K, const float* gy, const float* w, co
 int tc_linear_bwd_params(int M, int N, int K, const float* x, const float* gy, float scale,
                          bool accumulate, float* gw, float* gb, DevBuf& scratch, int passes,
                          cudaStream_t st);
+int tc_prepack_linear(PrePack& pp, const float* mats, int in_dim, const int* dims, int n_layers,
+                      const long long* w_off, bool with_dx, cudaStream_t st);
 bool tc_cin_supported(int F, int H, int C);
 int tc_cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
                      const float* b, float* x_out, int passes, cudaStream_t st);

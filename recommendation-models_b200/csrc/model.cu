@@ -135,7 +135,7 @@ void b200rec_model_s::destroy() {
   if (side3) cudaStreamSynchronize(side3);
   DevBuf* bufs[] = {&p_bias, &p_mats, &gmats, &scal, &d_feats, &d_targets, &d_index, &X, &wnz, &S,
                     &first, &second, &branch, &preds, &dlogit, &dXd, &dw, &gA, &gB, &scratch,
-                    &uniq, &G, &gwU, &wpack, &s1m, &s2m, &p2p_ctr, &x0, &gx0, &gy, &gnA, &gnB, &pooled, &gpooled, &xL, &s_cross,
+                    &uniq, &G, &gwU, &wpack, &wpack_mlp, &s1m, &s2m, &p2p_ctr, &x0, &gx0, &gy, &gnA, &gnB, &pooled, &gpooled, &xL, &s_cross,
                     &g_xL, &ip, &gip, &pre, &hbuf, &stage_a, &stage_b};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : acts) b.release();
@@ -244,19 +244,20 @@ int b200rec_model_s::mlp_head_backward(int B, const float* x_in, const float* ma
   const size_t hl = mlp.dims.size();
   const int last = hl ? mlp.dims[hl - 1] : mlp.in_dim;
   const float* a = hl ? acts[hl - 1].as<float>() : x_in;
-  B200_TRY(wcolsum(B, last, dlg, a, last, gm + mlp.w_off[hl], scratch, st));
-  B200_TRY(reduce_sum(B, dlg, 1.0f, gm + mlp.b_off[hl], scratch, st));
-  if (hl) {
-    B200_TRY(outer_rows(B, last, dlg, mats + mlp.w_off[hl], a, last, gA.as<float>(), last, st));
-  } else if (dx_if_no_hidden) {
-    B200_TRY(outer_rows(B, last, dlg, mats + mlp.w_off[hl], nullptr, 0, dx_if_no_hidden, last, st));
-  }
+  // W_o (1 x last) and b_o are adjacent in mats (LayerUtil.scala:12-24): one fused pass fills both
+  // gradients and the (ReLU-masked) gradient for the layer below
+  float* gbelow = hl ? gA.as<float>() : dx_if_no_hidden;
+  B200_TRY(head_layer_bwd(B, last, dlg, a, mats + mlp.w_off[hl], hl > 0, gbelow, gm + mlp.w_off[hl], scratch, st));
   return B200REC_OK;
 }
 
 // ---- the whole forward (+ backward) on device buffers -------------------------------------------
 int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   PackScope pack_scope(&wpack);
+  struct PrePackScope { PrePack* prev = tl_prepack; ~PrePackScope() { tl_prepack = prev; } } prepack_scope;
+  prepack.n = 0;
+  prepack.blob = &wpack_mlp;
+  tl_prepack = nullptr;
   const int B = a.B;
   const long long nnz = a.nnz;
   const bool train = a.targets != nullptr;
@@ -314,6 +315,13 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
 
   // ---- dense branch forward ---------------------------------------------------------------------
   phase("dense_fwd");
+  if (gemm_mode && !mlp.dims.empty()) {
+    // every Linear weight of the tower, in the forward and (training) the gradInput stage layout, in
+    // two launches instead of one per GEMM
+    B200_TRY(tc_prepack_linear(prepack, mats, mlp.in_dim, mlp.dims.data(), (int)mlp.dims.size(),
+                               mlp.w_off.data(), train, st));
+    tl_prepack = &prepack;
+  }
   Head h;
   h.B = B;
   h.br[h.n_br++] = first.as<float>();

@@ -76,7 +76,8 @@ struct b200rec_model_s {
   DevBuf p_bias, p_mats, gmats, scal;
   DevBuf d_feats, d_targets, d_index, stage_a, stage_b;
   DevBuf X, wnz, S, first, second, branch, preds, dlogit, dXd, dw, gA, gB, scratch;
-  DevBuf uniq, G, gwU, wpack;
+  DevBuf uniq, G, gwU, wpack, wpack_mlp;
+  b200rec::PrePack prepack;
   DevBuf s1m, s2m;  // optimizer slots of [mats | bias]
   DevBuf p2p_ctr;   // block-completion counter of the peer-exchange kernels
   DevBuf x0, gx0, gy, gnA, gnB, pooled, gpooled;

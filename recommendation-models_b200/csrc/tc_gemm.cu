@@ -21,7 +21,8 @@ static int pick_bn(int N) {
 
 template <class AP, class BP, class Sched, class Ep, bool PACKED>
 static int launch_ws(const char* name, dim3 grid, int smem, int M, int N, int bn, int n_stride, int n_valid,
-                     Sched sched, AP ap, BP bp, const char* blob, Ep ep, int passes, cudaStream_t st) {
+                     Sched sched, AP ap, BP bp, const char* blob, int blob_nkb, int blob_kb_per_split, Ep ep,
+                     int passes, cudaStream_t st) {
   const int kc = passes == 3 ? KC_PRECISE : 0;
   const int smem_max = ws_smem_bytes(PACKED, PACKED ? 208 : 256);
   if (passes == 3) {
@@ -31,7 +32,8 @@ static int launch_ws(const char* name, dim3 grid, int smem, int M, int N, int bn
       B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       attr_done = true;
     }
-    B200_LAUNCH_NAMED(name, k, grid, WS_THREADS, smem, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, blob, ep);
+    B200_LAUNCH_NAMED(name, k, grid, WS_THREADS, smem, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, blob, blob_nkb,
+                      blob_kb_per_split, ep);
   } else {
     auto k = gemm_ws_kernel<AP, BP, Sched, Ep, 1, PACKED>;
     static bool attr_done = false;
@@ -39,7 +41,8 @@ static int launch_ws(const char* name, dim3 grid, int smem, int M, int N, int bn
       B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       attr_done = true;
     }
-    B200_LAUNCH_NAMED(name, k, grid, WS_THREADS, smem, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, blob, ep);
+    B200_LAUNCH_NAMED(name, k, grid, WS_THREADS, smem, st, M, N, bn, n_stride, n_valid, kc, sched, ap, bp, blob, blob_nkb,
+                      blob_kb_per_split, ep);
   }
   B200_CHECK_LAUNCH();
   return B200REC_OK;
@@ -52,7 +55,7 @@ static int launch(const char* name, int M, int N, int bn, int n_stride, int n_va
   if (M <= 0 || N <= 0) return B200REC_OK;
   dim3 grid(n_tiles, cdiv(M, BM), splits);
   return launch_ws<AP, BP, Sched, Ep, false>(name, grid, ws_smem_bytes(false, bn), M, N, bn, n_stride, n_valid,
-                                             sched, ap, bp, nullptr, ep, passes, st);
+                                             sched, ap, bp, nullptr, 0, 0, ep, passes, st);
 }
 
 static KCin make_kcin(int F, int H, int Hp, long long KS) {
@@ -64,6 +67,19 @@ static bool colvec(const float* p, long long ld, int rows_total) {
   return ld % 4 == 0 && rows_total % 4 == 0 && aligned16(p);
 }
 
+// split-K factor from a wave model: CTAs run in waves of 148 (one per SM); a CTA costs its stages plus
+// a fixed prologue / epilogue (~6 stages).  Minimise waves x per-CTA cost.
+static int pick_splits_waves(int tiles, int nkb, int max_s) {
+  int best = 1;
+  long long best_t = -1;
+  for (int sp = 1; sp <= max_s && sp <= nkb; ++sp) {
+    const long long waves = ((long long)tiles * sp + 147) / 148;
+    const long long t = waves * ((nkb + sp - 1) / sp + 6);
+    if (best_t < 0 || t < best_t) { best_t = t; best = sp; }
+  }
+  return best;
+}
+
 // widest tile <= 208 (3-deep B ring fits) that splits N evenly
 static int pick_bn_packed(int N) {
   const int tiles = (N + 207) / 208;
@@ -72,26 +88,89 @@ static int pick_bn_packed(int N) {
 }
 
 // pack the weight operand into stage images, then run the bulk-copy GEMM on it
+// `sched` is the schedule of the WHOLE contraction (what gets packed); with splits > 1 (KPlain only)
+// split z covers k_chunk of it and reads its stages from the same blob.
 template <class AP, class BP, class Sched, class Ep>
 static int launch_packed(const char* name, int M, int N, int bn, int n_stride, int n_valid, int n_tiles,
-                         int nkb, Sched sched, AP ap, BP bp, Ep ep, int passes, cudaStream_t st) {
+                         int nkb, Sched sched, AP ap, BP bp, Ep ep, int passes, cudaStream_t st,
+                         const char* prepacked = nullptr, int splits = 1, int k_chunk = 0) {
   if (M <= 0 || N <= 0) return B200REC_OK;
-  B200_REQUIRE(tl_pack, B200REC_ERR_STATE, "no weight-pack buffer bound to this thread");
-  const size_t blob_bytes = (size_t)n_tiles * nkb * 2 * bn * 128;
-  B200_TRY(tl_pack->reserve(blob_bytes));
-  char* blob = tl_pack->as<char>();
-  {
-    dim3 pg(n_tiles, nkb < 64 ? nkb : 64);
+  char* blob = const_cast<char*>(prepacked);
+  if (!blob) {
+    B200_REQUIRE(tl_pack, B200REC_ERR_STATE, "no weight-pack buffer bound to this thread");
+    const size_t blob_bytes = (size_t)n_tiles * nkb * 2 * bn * 128;
+    B200_TRY(tl_pack->reserve(blob_bytes));
+    blob = tl_pack->as<char>();
+    int py = 148 * 8 / (n_tiles > 0 ? n_tiles : 1);   // enough CTAs to pull HBM bandwidth on big operands
+    if (py < 1) py = 1;
+    dim3 pg(n_tiles, nkb < py ? nkb : py);
     B200_LAUNCH_NAMED("tc_pack_weights", (pack_b_kernel<BP, Sched>), pg, THREADS, 0, st, bn, n_stride, sched, bp, blob);
   }
-  dim3 grid(n_tiles, cdiv(M, BM), 1);
+  dim3 grid(n_tiles, cdiv(M, BM), splits);
   return launch_ws<AP, BP, Sched, Ep, true>(name, grid, ws_smem_bytes(true, bn), M, N, bn, n_stride, n_valid,
-                                            sched, ap, bp, (const char*)blob, ep, passes, st);
+                                            sched, ap, bp, (const char*)blob, nkb, splits > 1 ? k_chunk / BK : 0,
+                                            ep, passes, st);
 }
 
 }  // namespace tc
 
 using namespace tc;
+
+// the stage images of a Linear weight packed ahead by tc_prepack_linear, or nullptr
+static const char* find_prepacked(const float* w, int fmt, int N, int K) {
+  const PrePack* pp = tl_prepack;
+  if (!pp || !pp->blob) return nullptr;
+  for (int i = 0; i < pp->n; ++i)
+    if (pp->e[i].w == w && pp->e[i].fmt == fmt && pp->e[i].N == N && pp->e[i].K == K)
+      return pp->blob->as<char>() + pp->e[i].off;
+  return nullptr;
+}
+
+int tc_prepack_linear(PrePack& pp, const float* mats, int in_dim, const int* dims, int n_layers,
+                      const long long* w_off, bool with_dx, cudaStream_t st) {
+  pp.n = 0;
+  if (n_layers <= 0 || n_layers > 8 || !pp.blob) return B200REC_OK;
+  PackJobs fwd{}, dx{};
+  size_t off = 0;
+  int max_tiles_f = 0, max_nkb_f = 0, max_tiles_d = 0, max_nkb_d = 0, nf = 0, nd = 0;
+  int K = in_dim;
+  for (int l = 0; l < n_layers; ++l) {
+    const int N = dims[l];
+    const float* w = mats + w_off[l];
+    if (N > 1) {   // Linear(K -> 1) runs as a row dot product, not a GEMM
+      {
+        const int bn = pick_bn_packed(N), nt = cdiv(N, bn), nkb = cdiv(K, BK);
+        fwd.j[nf++] = PackJob{w, N, K, bn, nkb, nt, (long long)off};
+        pp.e[pp.n++] = PrePack::Entry{w, 0, N, K, off};
+        off += (size_t)nt * nkb * 2 * bn * 128;
+        max_tiles_f = nt > max_tiles_f ? nt : max_tiles_f;
+        max_nkb_f = nkb > max_nkb_f ? nkb : max_nkb_f;
+      }
+      if (with_dx) {
+        const int bn = pick_bn_packed(K), nt = cdiv(K, bn), nkb = cdiv(N, BK);
+        dx.j[nd++] = PackJob{w, N, K, bn, nkb, nt, (long long)off};
+        pp.e[pp.n++] = PrePack::Entry{w, 1, N, K, off};
+        off += (size_t)nt * nkb * 2 * bn * 128;
+        max_tiles_d = nt > max_tiles_d ? nt : max_tiles_d;
+        max_nkb_d = nkb > max_nkb_d ? nkb : max_nkb_d;
+      }
+    }
+    K = N;
+  }
+  if (!pp.n) return B200REC_OK;
+  B200_TRY(pp.blob->reserve(off));
+  char* blob = pp.blob->as<char>();
+  if (nf) {
+    dim3 g(max_tiles_f, max_nkb_f < 32 ? max_nkb_f : 32, nf);
+    B200_LAUNCH_NAMED("tc_pack_weights", pack_linear_multi_kernel<false>, g, THREADS, 0, st, fwd, blob);
+  }
+  if (nd) {
+    dim3 g(max_tiles_d, max_nkb_d < 32 ? max_nkb_d : 32, nd);
+    B200_LAUNCH_NAMED("tc_pack_weights", pack_linear_multi_kernel<true>, g, THREADS, 0, st, dx, blob);
+  }
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
 
 // y[M,N] = act(x[M,K] W[N,K]^T + b)
 int tc_linear_fwd(int M, int N, int K, const float* x, const float* w, const float* b, bool relu,
@@ -101,7 +180,7 @@ int tc_linear_fwd(int M, int N, int K, const float* x, const float* w, const flo
   RowProd<4, KPlain> ap{x, K, M, BM, (K % 4 == 0) && aligned16(x)};
   RowProd<8, KPlain> bp{w, K, N, bn, (K % 4 == 0) && aligned16(w)};
   return launch_packed("tc_linear_fwd", M, N, bn, bn, bn, cdiv(N, bn), cdiv(K, BK), s, ap, bp,
-                       tc::EpBiasAct{y, N, b, relu}, passes, st);
+                       tc::EpBiasAct{y, N, b, relu}, passes, st, find_prepacked(w, 0, N, K));
 }
 
 // PNN product layer: h = relu(prev + ip Wp^T + c0)
@@ -123,7 +202,7 @@ int tc_linear_bwd_input(int M, int N, int K, const float* gy, const float* w, co
   RowProd<4, KPlain> ap{gy, N, M, BM, (N % 4 == 0) && aligned16(gy)};
   ColProd<256, KPlain> bp{w, K, K, bn, colvec(w, K, K)};   // B(k_out, n) = W[n*K + k_out]
   return launch_packed("tc_linear_dx", M, K, bn, bn, bn, cdiv(K, bn), cdiv(N, BK), s, ap, bp,
-                       tc::EpMaskAcc{gx, K, mask, K, accumulate}, passes, st);
+                       tc::EpMaskAcc{gx, K, mask, K, accumulate}, passes, st, find_prepacked(w, 1, N, K));
 }
 
 // gw[N,K] (+)= scale * gy[M,N]^T x[M,K]  (split-K over the batch, fixed-order reduce) ; gb likewise
@@ -132,10 +211,7 @@ int tc_linear_bwd_params(int M, int N, int K, const float* x, const float* gy, f
                          cudaStream_t st) {
   const int bn = pick_bn(K);
   const int tiles = cdiv(N, BM) * cdiv(K, bn);
-  int splits = (148 + tiles - 1) / tiles;
-  const int max_s = M / 256 > 0 ? M / 256 : 1;
-  if (splits > max_s) splits = max_s;
-  if (splits < 1) splits = 1;
+  int splits = pick_splits_waves(tiles, cdiv(M, BK), M / 256 > 0 ? M / 256 : 1);
   int k_chunk = ((cdiv(M, splits) + BK - 1) / BK) * BK;
   splits = cdiv(M, k_chunk);
   const long long MN = (long long)N * K;
@@ -143,8 +219,9 @@ int tc_linear_bwd_params(int M, int N, int K, const float* x, const float* gy, f
   float* ws = scratch.as<float>();
   KPlain s{0, M, k_chunk};
   ColProd<128, KPlain> ap{gy, N, N, BM, colvec(gy, N, N)};  // A(n, m) = gy[m*N + n]
-  ColProd<256, KPlain> bp{x, K, K, bn, colvec(x, K, K)};   // B(k, m) = x[m*K + k]
-  B200_TRY(launch("tc_linear_dW", N, K, bn, bn, bn, cdiv(K, bn), splits, s, ap, bp, tc::EpPartial{ws, MN, K}, passes, st));
+  ColProd<256, KPlain> bp{x, K, K, bn, colvec(x, K, K)};   // B(k, m) = x[m*K + k]: packed once (all splits)
+  B200_TRY(launch_packed("tc_linear_dW", N, K, bn, bn, bn, cdiv(K, bn), cdiv(M, BK), s, ap, bp,
+                         tc::EpPartial{ws, MN, K}, passes, st, nullptr, splits, k_chunk));
   B200_TRY(splitk_reduce(ws, splits, MN, scale, accumulate, gw, st));
   if (gb) B200_TRY(colsum(M, N, gy, scale, accumulate, gb, ws + (size_t)splits * MN, st));
   return B200REC_OK;
@@ -177,10 +254,7 @@ int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x
   {  // ---- gW^T tile: out(m = (i,j), n = c), contraction over r
     const int bn = pick_bn(C);
     const int tiles = cdiv(FH, BM) * cdiv(C, bn);
-    int splits = (2 * 148 + tiles - 1) / tiles;
-    const int max_s = R / 512 > 0 ? R / 512 : 1;
-    if (splits > max_s) splits = max_s;
-    if (splits < 1) splits = 1;
+    int splits = pick_splits_waves(tiles, cdiv(R, BK), R / 512 > 0 ? (R / 512 < 32 ? R / 512 : 32) : 1);
     int k_chunk = ((cdiv(R, splits) + BK - 1) / BK) * BK;
     splits = cdiv(R, k_chunk);
     const long long MN = (long long)C * FH;
@@ -188,8 +262,9 @@ int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x
     float* ws = scratch.as<float>();
     KPlain s{0, R, k_chunk};
     CinZtProd ap{x0, x_in, F, H, (H % 4 == 0) && aligned16(x_in)};
-    ColProd<256, KPlain> bp{gy, C, C, bn, colvec(gy, C, C)};   // B(c, r) = gy[r*C + c]
-    B200_TRY(launch("tc_cin_dW", FH, C, bn, bn, bn, cdiv(C, bn), splits, s, ap, bp, tc::EpPartialT{ws, MN, FH}, passes, st));
+    ColProd<256, KPlain> bp{gy, C, C, bn, colvec(gy, C, C)};   // B(c, r) = gy[r*C + c]: packed once (all splits)
+    B200_TRY(launch_packed("tc_cin_dW", FH, C, bn, bn, bn, cdiv(C, bn), cdiv(R, BK), s, ap, bp,
+                           tc::EpPartialT{ws, MN, FH}, passes, st, nullptr, splits, k_chunk));
     B200_TRY(splitk_reduce(ws, splits, MN, 1.0f, false, gW, st));
     B200_TRY(colsum(R, C, gy, 1.0f, false, gb, ws + (size_t)splits * MN, st));
   }

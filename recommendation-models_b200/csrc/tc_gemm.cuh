@@ -590,10 +590,29 @@ struct EpRowDot {
   const float* x; long long ldx; float* out; long long ldo;
   static constexpr bool kRowReduce = true;
   __device__ __forceinline__ void load_tile(float* xs, int m0, int M, int ncols, int tid) const {
+    // one warp per row pair, lanes over the columns: coalesced, no per-element division, and all
+    // (up to 14) loads of an iteration in flight before the first store (latency, not bandwidth, rules)
     const int stride = ncols + 1;
-    for (int idx = tid; idx < BM * ncols; idx += THREADS) {
-      const int r = idx / ncols, j = idx - r * ncols;
-      xs[r * stride + j] = (m0 + r < M) ? __ldg(x + (long long)(m0 + r) * ldx + j) : 0.f;
+    const int lane = tid & 31;
+    for (int r = 2 * (tid >> 5); r < BM; r += 2 * (THREADS / 32)) {
+      float v[2][7];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const bool ok = m0 + r + rr < M;
+        const float* src = x + (long long)(m0 + r + rr) * ldx;
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+          const int j = lane + 32 * u;
+          v[rr][u] = (ok && j < ncols) ? __ldg(src + j) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+          const int j = lane + 32 * u;
+          if (j < ncols) xs[(r + rr) * stride + j] = v[rr][u];
+        }
     }
   }
   __device__ __forceinline__ float dot(const float* xs, int ncols, int rl, int nl0, const float* v, int nv) const {
@@ -636,6 +655,35 @@ __global__ void __launch_bounds__(THREADS) pack_b_kernel(int bn, int n_stride, S
   }
 }
 
+// several Linear weights in one launch (blockIdx.z = job): W[N,K] row-major ->
+//   TRANSPOSED = false: B(n, k) = W[n*K + k]          (forward:   y = x W^T)
+//   TRANSPOSED = true : B(k_out, n) = W[n*K + k_out]  (gradInput: gx = gy W, contraction over N)
+struct PackJob { const float* w; int N, K, bn, nkb, n_tiles; long long off; };
+struct PackJobs { PackJob j[8]; };
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(THREADS) pack_linear_multi_kernel(PackJobs jobs, char* blob) {
+  const PackJob jb = jobs.j[blockIdx.z];
+  const int tile = blockIdx.x;
+  if (tile >= jb.n_tiles) return;
+  const bool al = (reinterpret_cast<uintptr_t>(jb.w) & 15) == 0;
+  for (int kb = blockIdx.y; kb < jb.nkb; kb += gridDim.y) {
+    char* hi = blob + jb.off + ((size_t)tile * jb.nkb + kb) * (size_t)(2 * jb.bn * 128);
+    if (!TRANSPOSED) {
+      RowProd<8, KPlain> bp{jb.w, jb.K, jb.N, jb.bn, (jb.K % 4 == 0) && al};
+      bp.s = KPlain{0, jb.K, jb.K};
+      bp.init(nullptr, tile * jb.bn, threadIdx.x);
+      bp.prefetch(kb);
+      bp.store(kb, hi, hi + jb.bn * 128);
+    } else {
+      ColProd<256, KPlain> bp{jb.w, jb.K, jb.K, jb.bn, (jb.K % 4 == 0) && al};
+      bp.s = KPlain{0, jb.N, jb.N};
+      bp.init(nullptr, tile * jb.bn, threadIdx.x);
+      bp.prefetch(kb);
+      bp.store(kb, hi, hi + jb.bn * 128);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // Warp-specialised kernel (the one the launchers use).  9 warps:
 //   warp 0      : one thread issues tcgen05.mma (<= 4 K-steps x 3 passes per stage) and commits the
@@ -671,7 +719,9 @@ __host__ __device__ inline int ws_smem_bytes(bool packed, int bn) {
 template <class AP, class BP, class Sched, class Ep, int PASSES, bool PACKED>
 __global__ void __launch_bounds__(WS_THREADS, 1)   // registers are granted per 4 warps: 9 warps -> cap 168
 gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sched, AP ap, BP bp,
-               const char* __restrict__ bblob, Ep ep) {
+               const char* __restrict__ bblob, int blob_nkb, int blob_kb_per_split, Ep ep) {
+  // packed B with split-K: the blob holds the stages of the WHOLE contraction ([n_tile][blob_nkb]);
+  // split z starts at stage z * blob_kb_per_split
   extern __shared__ char smem_raw[];
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int NB = ws_nb(PACKED, bn);
@@ -750,7 +800,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
       bp.s = s;
       bp.init(nullptr, n0, tid);
     }
-    const char* myblob = bblob + (size_t)blockIdx.x * nkb * b_stage;
+    const char* myblob = bblob + ((size_t)blockIdx.x * blob_nkb + (size_t)blockIdx.z * blob_kb_per_split) * b_stage;
     auto issue_b = [&](int kb) {
       const int sb = kb % NB;
       mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)b_stage);
