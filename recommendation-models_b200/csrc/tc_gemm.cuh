@@ -516,12 +516,20 @@ struct EpBiasAct {  // y = act(acc + bias[n])
   static constexpr bool kRowReduce = false;
   __device__ __forceinline__ void operator()(int m, int n0, float* v, int nv, int) const {
     float* dst = y + (long long)m * ld + n0;
+    if (bias && nv == 16 && ((reinterpret_cast<uintptr_t>(bias + n0) & 15) == 0)) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if (i < nv) {
-        float t = v[i] + (bias ? __ldg(bias + n0 + i) : 0.f);
-        v[i] = relu ? fmaxf(t, 0.f) : t;
+      for (int q = 0; q < 4; ++q) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 4 * q));
+        v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
       }
+    } else if (bias) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nv) v[i] += __ldg(bias + n0 + i);
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
     }
     if (nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -539,11 +547,33 @@ struct EpMaskAcc {  // g = acc * (mask > 0) (+ g)
   static constexpr bool kRowReduce = false;
   __device__ __forceinline__ void operator()(int m, int n0, float* v, int nv, int) const {
     float* dst = g + (long long)m * ld + n0;
+    const float* mk = mask ? mask + (long long)m * ldm + n0 : nullptr;
+    const bool vec = nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                     (!mk || (reinterpret_cast<uintptr_t>(mk) & 15) == 0);
+    if (vec) {  // a thread owns 64 contiguous bytes of its row: 128-bit accesses
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        if (mk) {
+          const float4 k = __ldg(reinterpret_cast<const float4*>(mk + 4 * q));
+          if (!(k.x > 0.f)) o.x = 0.f;
+          if (!(k.y > 0.f)) o.y = 0.f;
+          if (!(k.z > 0.f)) o.z = 0.f;
+          if (!(k.w > 0.f)) o.w = 0.f;
+        }
+        if (accumulate) {
+          const float4 p = *reinterpret_cast<const float4*>(dst + 4 * q);
+          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        *reinterpret_cast<float4*>(dst + 4 * q) = o;
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       if (i < nv) {
         float t = v[i];
-        if (mask && !(__ldg(mask + (long long)m * ldm + n0 + i) > 0.f)) t = 0.f;
+        if (mk && !(__ldg(mk + i) > 0.f)) t = 0.f;
         if (accumulate) t += dst[i];
         dst[i] = t;
       }
@@ -555,6 +585,12 @@ struct EpPartial {  // split-K partial: ws[z][m][n]
   static constexpr bool kRowReduce = false;
   __device__ __forceinline__ void operator()(int m, int n0, float* v, int nv, int z) const {
     float* dst = ws + (long long)z * MN + (long long)m * ld + n0;
+    if (nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i)
       if (i < nv) dst[i] = v[i];
@@ -889,7 +925,9 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
 
     // ---- epilogue: thread = accumulator row (TMEM lane), 16 columns per tcgen05.ld ----------------
     if (nkb > 0) {
+      if (tid == 0) TC_TRACE(2, 511, 0);
       mbar_wait(bar_empty + 8 * ((nkb - 1) & 1), ((nkb - 1) >> 1) & 1);
+      if (tid == 0) TC_TRACE(2, 511, 1);
       tc_fence_after();
       const bool add_s = kc > 0 && nkb > kc;   // result = S + P (the last chunk is still in P)
       const int row = m0 + (warp & 3) * 32 + lane;
@@ -919,21 +957,28 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         if (pw < 4 && row < M) ep.finish(row, blockIdx.x, acc + red[(warp & 3) * 32 + lane]);
       } else {
         for (int ch = pw >> 2; ch * 16 < ncols; ch += 2) {
-          tmem_ld16(tmem + lane_addr + ch * 16, v);
+          uint32_t pr[16], sr[16];
+          tmem_ld16_nowait(tmem + lane_addr + ch * 16, pr);          // P and S in one TMEM round trip
           if (add_s) {
-            float sv[16];
-            tmem_ld16(tmem + lane_addr + TMEM_S + ch * 16, sv);
+            tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, sr);
+            tmem_wait_ld2(pr, sr);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += sv[i];
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(pr[i]) + __uint_as_float(sr[i]);
+          } else {
+            tmem_wait_ld1(pr);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(pr[i]);
           }
           if (row < M) ep(row, n0 + ch * 16, v, min(16, ncols - ch * 16), blockIdx.z);
         }
       }
     }
   }
+  if (threadIdx.x == 32) TC_TRACE(2, 511, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+  if (threadIdx.x == 0) TC_TRACE(2, 511, 3);
 }
 
 }  // namespace tc

@@ -18,10 +18,12 @@ def dump(title, nkb):
         m, p = a[0, kb] - t0, a[1, kb] - t0
         d = a[2, kb, 0] - t0 if a[2, kb, 0] else 0
         print(f"{kb:3d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d} | {p[0]:7d} {p[1]:7d} {p[2]:7d} {p[3]:7d} | {d:7d}")
+    e = a[2, 511] - t0
+    print(f" epilogue: producers done {e[0]}, last MMA drained {e[1]}, epilogue stored {e[2]}, CTA end {e[3]}")
     m = a[0, :nkb] - t0
     print(" mean stage period (MMA issued->issued):", float(np.diff(m[:, 3]).mean()) if nkb > 1 else 0)
 
-B, I, O = 1024, 624, 400
+B, I, O = 8192, 624, 400
 x = rng.standard_normal((B, I)).astype(np.float32)
 w = (rng.standard_normal((O, I)) / np.sqrt(I)).astype(np.float32)
 lin = pkg.Linear(I, O, False, w)
