@@ -257,19 +257,49 @@ int b200rec_step_rows_dev(b200rec_model_t m, int batch_size, const int* slots, c
  * The id dispatch, the row return and the gradient push are stores into the PEERS' buffers issued by
  * the producing kernels (fused gather + dispatch); release/acquire flags in peer memory order them
  * (csrc/p2p.cu).  peer_* are arrays of `world` device pointers, one per rank, to symmetric buffers
- * (the host maps them, e.g. torch symmetric memory or cudaIpc): ids_in[world*cap] int (double-buffered
- * by the caller, reset to -1 one step ahead), rows_in[world*cap*K], w_in[world*cap], grad_in, gw_in
- * (same shapes), flags[3*world] int (zero-initialised).  `step` counts from 1 and must increase. */
+ * (the host maps them, e.g. torch symmetric memory or cudaIpc): ids_in[world*cap] int (a ring kept
+ * by the caller, reset to -1 ahead of use: 2 deep, or 4 deep when ids are dispatched one step ahead), rows_in[world*cap*K], w_in[world*cap], grad_in, gw_in
+ * (same shapes), flags[4*world] int (zero-initialised).  `step` counts from 1 and must increase; pass
+ * step <= 0 for (the model's device step counter - step), see b200rec_p2p_begin_step_dev: 0 = the
+ * current step, -1 = the next one (an id dispatch issued one step ahead). */
 /* n_dev (may be NULL): device count of valid ids, e.g. the distinct ids of the batch (dedup before the
  * exchange: every id is requested once, its gradient is pre-reduced locally and pushed once). */
 int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, const int* n_dev, int world, int rank,
                                  int64_t period, int cap, int step, const int* feats,
                                  void* const* peer_ids_in, void* const* peer_flags, int* dst,
                                  int* overflow, void* stream);
-/* dst[i] = dst_unique[inv[i]]: slot of every non-zero from the slot of its distinct id */
-int b200rec_p2p_compose_dst_dev(b200rec_model_t m, int64_t nnz, const int* inv, const int* dst_unique,
-                                int* dst, void* stream);
-/* spin (device side) until every rank's flag of `phase` (0 ids, 1 rows, 2 grads) has reached `step` */
+/* Start of a sharded step: advances the model's DEVICE step counter (the p2p calls use it whenever
+ * their `step` argument is <= 0, which is what a replayed CUDA graph needs) and fills ids_next[0..n)
+ * with the -1 padding. */
+int b200rec_p2p_begin_step_dev(b200rec_model_t m, int* ids_next, int64_t n, void* stream);
+
+/* One-shot allreduce (sum, rank order) of the dense gradients over NVLink peer loads: inout is copied
+ * to this rank's symmetric buffer peer_bufs[rank], flagged (phase 3), and the sum of all ranks'
+ * buffers is written back to inout.  Replaces the worker -> PS push of the dense gradients
+ * (rec/model/ParRecModel.scala:247-264) for data-parallel replicas. */
+int b200rec_p2p_allreduce_dev(b200rec_model_t m, int64_t n, int world, int rank, int step, float* inout,
+                              void* const* peer_bufs, void* const* peer_flags, const int* flags_local,
+                              void* stream);
+
+/* Side streams: the sorts of workspace `ws` (0, 1, 2) run on a side stream of the model
+ * (b200rec_segsum_sort_dev forks it from `stream`; b200rec_segsum_join_dev / _reduce_dev join it).
+ * A caller may put more work there: _side_stream returns it, _side_fork_dev makes it wait for what
+ * `stream` holds so far, _side_rejoin_dev moves the join point behind what the side stream holds now. */
+int b200rec_model_side_stream(b200rec_model_t m, int ws, void** stream_out);
+int b200rec_side_fork_dev(b200rec_model_t m, int ws, void* stream);
+int b200rec_side_rejoin_dev(b200rec_model_t m, int ws);
+
+/* Capture the device calls issued on the model's stream (and its side streams) between _begin and
+ * _end into a CUDA graph; b200rec_graph_launch replays it.  Calls made while capturing are recorded,
+ * not executed; every buffer must already have its final size (run the step eagerly once before). */
+int b200rec_capture_begin(b200rec_model_t m, void* stream);
+int b200rec_capture_end(b200rec_model_t m, int* graph_id, void* stream);
+int b200rec_graph_launch(b200rec_model_t m, int graph_id, void* stream);
+
+/* slot of every non-zero from the slot of its distinct id (the ids' sort of workspace `ws` links them) */
+int b200rec_p2p_compose_dst_dev(b200rec_model_t m, int ws, int64_t nnz, const int* dst_unique, int* dst,
+                                void* stream);
+/* spin (device side) until every rank's flag of `phase` (0 ids, 1 rows, 2 grads, 3 dense) has reached `step` */
 int b200rec_p2p_wait_dev(b200rec_model_t m, const int* flags_local, int phase, int world, int step,
                          void* stream);
 int b200rec_p2p_gather_dev(b200rec_model_t m, b200rec_table_t t, int world, int rank, int cap, int step,

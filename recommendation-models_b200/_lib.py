@@ -70,7 +70,15 @@ SIGNATURES = {
     "b200rec_segsum_reduce_dev": [vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp],
     "b200rec_segsum_join_dev": [vp, C.c_int, vp],
     "b200rec_segsum_inverse_dev": [vp, C.c_int, C.c_int64, vp, vp],
-    "b200rec_p2p_compose_dst_dev": [vp, C.c_int64, vp, vp, vp, vp],
+    "b200rec_p2p_begin_step_dev": [vp, vp, C.c_int64, vp],
+    "b200rec_p2p_allreduce_dev": [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp],
+    "b200rec_model_side_stream": [vp, C.c_int, C.POINTER(vp)],
+    "b200rec_side_fork_dev": [vp, C.c_int, vp],
+    "b200rec_side_rejoin_dev": [vp, C.c_int],
+    "b200rec_capture_begin": [vp, vp],
+    "b200rec_capture_end": [vp, C.POINTER(C.c_int), vp],
+    "b200rec_graph_launch": [vp, C.c_int, vp],
+    "b200rec_p2p_compose_dst_dev": [vp, C.c_int, C.c_int64, vp, vp, vp],
     "b200rec_table_init_uniform_sharded": [vp, C.c_uint64, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int64],
     "b200rec_shard_plan_dev": [vp, C.c_int64, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp, vp],
     "b200rec_table_lookup_padded_dev": [vp, C.c_int64, vp, vp, vp, vp],

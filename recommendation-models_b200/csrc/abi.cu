@@ -947,6 +947,7 @@ int b200rec_segsum_sort_dev(b200rec_model_t m, int ws, int dim, int64_t nnz, int
   B200_CUDA(cudaStreamWaitEvent(side, m->fork_of(ws), 0));
   B200_TRY(segsum_sort(m->ws_of(ws), a, side));
   B200_CUDA(cudaEventRecord(m->join_of(ws), side));
+  m->join_pending[ws] = true;
   return B200REC_OK;
   B200_GUARD_END
 }
@@ -954,7 +955,9 @@ int b200rec_segsum_sort_dev(b200rec_model_t m, int ws, int dim, int64_t nnz, int
 int b200rec_segsum_join_dev(b200rec_model_t m, int ws, void* stream) {
   B200_REQUIRE(m && ws >= 0 && ws <= 2, B200REC_ERR_ARG, "bad argument");
   B200_TRY(use_device(m->device));
-  B200_CUDA(cudaStreamWaitEvent(stream ? (cudaStream_t)stream : m->stream, m->join_of(ws), 0));
+  // joined once: a later capture must not wait on an event recorded by an earlier capture
+  if (m->join_pending[ws]) B200_CUDA(cudaStreamWaitEvent(stream ? (cudaStream_t)stream : m->stream, m->join_of(ws), 0));
+  m->join_pending[ws] = false;
   return B200REC_OK;
 }
 
@@ -975,7 +978,8 @@ int b200rec_segsum_reduce_dev(b200rec_model_t m, int ws, int dim, int64_t nnz, i
   B200_REQUIRE(ws >= 0 && ws <= 2, B200REC_ERR_ARG, "workspace must be 0, 1 or 2");
   B200_TRY(use_device(m->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
-  B200_CUDA(cudaStreamWaitEvent(st, m->join_of(ws), 0));
+  if (m->join_pending[ws]) B200_CUDA(cudaStreamWaitEvent(st, m->join_of(ws), 0));
+  m->join_pending[ws] = false;
   if (a.dE || a.dw) B200_TRY(segsum_reduce(m->ws_of(ws), a, st));
   return B200REC_OK;
   B200_GUARD_END
@@ -1047,25 +1051,122 @@ int b200rec_step_rows_dev(b200rec_model_t m, int batch_size, const int* slots, c
 }
 
 // ---- NVLink peer-memory exchange (csrc/p2p.cu) -------------------------------------------------------
-static int fill_p2p(Model* m, int world, int rank, int step, void* const* peer_flags, P2P& c) {
+// ctr: which block-completion counter (kernels that may run concurrently need their own: 0 gather /
+// push on the main stream, 2 id dispatch (prefetched on a side stream), 3 dense allreduce)
+static int fill_p2p(Model* m, int world, int rank, int step, void* const* peer_flags, P2P& c, int ctr = 0) {
   B200_REQUIRE(m && peer_flags, B200REC_ERR_ARG, "NULL argument");
   B200_REQUIRE(world >= 1 && world <= P2P_MAX && rank >= 0 && rank < world, B200REC_ERR_ARG,
                "bad rank %d / world %d (peer exchange supports up to %d GPUs)", rank, world, P2P_MAX);
   if (!m->p2p_ctr.p) {
     B200_TRY(m->p2p_ctr.reserve(16));
     B200_CUDA(cudaMemset(m->p2p_ctr.p, 0, 16));
+    B200_CUDA(cudaDeviceSynchronize());
   }
   c.world = world; c.rank = rank; c.step = step;
-  c.block_counter = m->p2p_ctr.as<unsigned>();
+  c.block_counter = m->p2p_ctr.as<unsigned>() + ctr;
+  c.step_ptr = m->p2p_ctr.as<int>() + 1;
   for (int p = 0; p < world; ++p) c.flags[p] = (int*)peer_flags[p];
   return B200REC_OK;
 }
 
 int b200rec_p2p_wait_dev(b200rec_model_t m, const int* flags_local, int phase, int world, int step,
                          void* stream) {
-  B200_REQUIRE(m && flags_local && phase >= 0 && phase < 3, B200REC_ERR_ARG, "bad argument");
+  B200_GUARD_BEGIN
+  B200_REQUIRE(flags_local && phase >= 0 && phase < 4, B200REC_ERR_ARG, "bad argument");
+  P2P c;
+  void* none[P2P_MAX] = {};
+  B200_TRY(fill_p2p(m, world, 0, step, none, c));
   B200_TRY(use_device(m->device));
-  return p2p_wait(flags_local, phase, world, step, stream ? (cudaStream_t)stream : m->stream);
+  return p2p_wait(flags_local, phase, world, step, c.step_ptr, stream ? (cudaStream_t)stream : m->stream);
+  B200_GUARD_END
+}
+
+int b200rec_p2p_begin_step_dev(b200rec_model_t m, int* ids_next, int64_t n, void* stream) {
+  B200_GUARD_BEGIN
+  P2P c;
+  void* none[P2P_MAX] = {};
+  B200_TRY(fill_p2p(m, 1, 0, 0, none, c));
+  B200_REQUIRE(ids_next || n == 0, B200REC_ERR_ARG, "NULL argument");
+  B200_TRY(use_device(m->device));
+  return p2p_begin_step(m->p2p_ctr.as<int>() + 1, ids_next, n, stream ? (cudaStream_t)stream : m->stream);
+  B200_GUARD_END
+}
+
+int b200rec_p2p_allreduce_dev(b200rec_model_t m, int64_t n, int world, int rank, int step, float* inout,
+                              void* const* peer_bufs, void* const* peer_flags, const int* flags_local,
+                              void* stream) {
+  B200_GUARD_BEGIN
+  P2P c;
+  B200_TRY(fill_p2p(m, world, rank, step, peer_flags, c, 3));
+  B200_REQUIRE(inout && peer_bufs && flags_local && n >= 0, B200REC_ERR_ARG, "bad argument");
+  B200_TRY(use_device(m->device));
+  PeerF bufs;
+  for (int p = 0; p < world; ++p) bufs.p[p] = (float*)peer_bufs[p];
+  return p2p_allreduce(n, inout, flags_local, c, bufs, stream ? (cudaStream_t)stream : m->stream);
+  B200_GUARD_END
+}
+
+// ---- side streams of the sort workspaces, for work the caller wants off the main stream ----------------
+int b200rec_model_side_stream(b200rec_model_t m, int ws, void** stream_out) {
+  B200_REQUIRE(m && stream_out && ws >= 0 && ws <= 2, B200REC_ERR_ARG, "bad argument");
+  *stream_out = (void*)m->side_of(ws);
+  return B200REC_OK;
+}
+
+int b200rec_side_fork_dev(b200rec_model_t m, int ws, void* stream) {
+  B200_REQUIRE(m && ws >= 0 && ws <= 2, B200REC_ERR_ARG, "bad argument");
+  B200_TRY(use_device(m->device));
+  B200_CUDA(cudaEventRecord(m->fork_of(ws), stream ? (cudaStream_t)stream : m->stream));
+  B200_CUDA(cudaStreamWaitEvent(m->side_of(ws), m->fork_of(ws), 0));
+  return B200REC_OK;
+}
+
+int b200rec_side_rejoin_dev(b200rec_model_t m, int ws) {
+  B200_REQUIRE(m && ws >= 0 && ws <= 2, B200REC_ERR_ARG, "bad argument");
+  B200_TRY(use_device(m->device));
+  B200_CUDA(cudaEventRecord(m->join_of(ws), m->side_of(ws)));
+  m->join_pending[ws] = true;
+  return B200REC_OK;
+}
+
+// ---- user-driven CUDA graph capture of a multi-call step (the sharded step is a sequence of ABI calls) --
+int b200rec_capture_begin(b200rec_model_t m, void* stream) {
+  B200_REQUIRE(m, B200REC_ERR_ARG, "NULL model");
+  B200_REQUIRE(!m->capturing, B200REC_ERR_STATE, "a capture is already open on this model");
+  B200_TRY(use_device(m->device));
+  m->capture_l0 = g_launches.load();
+  B200_CUDA(cudaStreamBeginCapture(stream ? (cudaStream_t)stream : m->stream, cudaStreamCaptureModeThreadLocal));
+  m->capturing = true;
+  return B200REC_OK;
+}
+
+int b200rec_capture_end(b200rec_model_t m, int* graph_id, void* stream) {
+  B200_REQUIRE(m && graph_id, B200REC_ERR_ARG, "NULL argument");
+  B200_REQUIRE(m->capturing, B200REC_ERR_STATE, "no capture is open on this model");
+  m->capturing = false;
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(stream ? (cudaStream_t)stream : m->stream, &graph);
+  const int nodes = (int)(g_launches.load() - m->capture_l0);   // recorded, not executed
+  g_launches.fetch_sub(nodes);
+  cudaGraphExec_t exec = nullptr;
+  if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (e != cudaSuccess || !exec) {
+    cudaGetLastError();
+    set_error("graph capture failed: %s", cudaGetErrorString(e));
+    return B200REC_ERR_CUDA;
+  }
+  m->user_graphs.push_back({exec, nodes});
+  *graph_id = (int)m->user_graphs.size() - 1;
+  return B200REC_OK;
+}
+
+int b200rec_graph_launch(b200rec_model_t m, int graph_id, void* stream) {
+  B200_REQUIRE(m && graph_id >= 0 && graph_id < (int)m->user_graphs.size(), B200REC_ERR_ARG, "bad graph id");
+  B200_TRY(use_device(m->device));
+  B200_CUDA(cudaGraphLaunch(m->user_graphs[graph_id].first, stream ? (cudaStream_t)stream : m->stream));
+  g_launches.fetch_add(m->user_graphs[graph_id].second, std::memory_order_relaxed);
+  return B200REC_OK;
 }
 
 int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, const int* n_dev, int world, int rank,
@@ -1074,7 +1175,7 @@ int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, const int* n_de
                                  int* overflow, void* stream) {
   B200_GUARD_BEGIN
   P2P c;
-  B200_TRY(fill_p2p(m, world, rank, step, peer_flags, c));
+  B200_TRY(fill_p2p(m, world, rank, step, peer_flags, c, 2));
   B200_REQUIRE(peer_ids_in && dst && overflow && (feats || nnz == 0), B200REC_ERR_ARG, "NULL argument");
   B200_TRY(use_device(m->device));
   PeerI ids;
@@ -1099,11 +1200,11 @@ int b200rec_p2p_gather_dev(b200rec_model_t m, b200rec_table_t t, int world, int 
   B200_GUARD_END
 }
 
-int b200rec_p2p_compose_dst_dev(b200rec_model_t m, int64_t nnz, const int* inv, const int* dst_unique,
-                                int* dst, void* stream) {
-  B200_REQUIRE(m && inv && dst_unique && dst, B200REC_ERR_ARG, "NULL argument");
+int b200rec_p2p_compose_dst_dev(b200rec_model_t m, int ws, int64_t nnz, const int* dst_unique, int* dst,
+                                void* stream) {
+  B200_REQUIRE(m && dst_unique && dst && ws >= 0 && ws <= 2, B200REC_ERR_ARG, "bad argument");
   B200_TRY(use_device(m->device));
-  return p2p_compose(nnz, inv, dst_unique, dst, stream ? (cudaStream_t)stream : m->stream);
+  return p2p_compose(m->ws_of(ws), nnz, dst_unique, dst, stream ? (cudaStream_t)stream : m->stream);
 }
 
 int b200rec_p2p_push_grads_dev(b200rec_model_t m, int64_t nnz, const int* n_dev, int world, int rank,

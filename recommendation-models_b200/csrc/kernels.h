@@ -102,14 +102,20 @@ struct PeerI { int* p[P2P_MAX]; };
 struct PeerF { float* p[P2P_MAX]; };
 struct P2P {
   int world, rank, step;
+  const int* step_ptr;       // device step counter: step <= 0 means "*step_ptr - step" (CUDA-graph replays
+                             // carry no host step; -1 = the step after the current one, for prefetches)
   unsigned* block_counter;   // local, zero-initialised; wraps back to 0 through atomicInc
   int* flags[P2P_MAX];       // every rank's flags[3][world]
 };
-int p2p_wait(const int* flags, int phase, int world, int step, cudaStream_t st);
+int p2p_wait(const int* flags, int phase, int world, int step, const int* step_ptr, cudaStream_t st);
+int p2p_begin_step(int* step_ctr, int* ids_next, long long n, cudaStream_t st);
+// dense gradients: inout -> my symmetric buffer, then the sum over all ranks (rank order) back into inout
+int p2p_allreduce(long long n, float* inout, const int* flags_local, const P2P& c, const PeerF& bufs,
+                  cudaStream_t st);
 // n_dev (optional): device count of valid ids (<= n); ids beyond it are ignored
 int p2p_plan(ShardPlanWorkspace& ws, long long n, const int* n_dev, long long period, int cap,
              const int* feats, int* dst, int* overflow, const P2P& c, const PeerI& ids_in, cudaStream_t st);
-int p2p_compose(long long n, const int* inv, const int* dst_unique, int* dst, cudaStream_t st);
+int p2p_compose(SegSumWorkspace& ws, long long n, const int* dst_unique, int* dst, cudaStream_t st);
 int p2p_gather(long long rows, int K, int cap, const int* ids_in, const float* table, const float* wtable,
                const P2P& c, const PeerF& rows_in, const PeerF& w_in, int* err, cudaStream_t st);
 int p2p_push_grads(long long n, const int* n_dev, int K, int cap, const int* dst, const float* dE,

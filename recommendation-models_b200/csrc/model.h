@@ -79,7 +79,11 @@ struct b200rec_model_s {
   DevBuf uniq, G, gwU, wpack, wpack_mlp;
   b200rec::PrePack prepack;
   DevBuf s1m, s2m;  // optimizer slots of [mats | bias]
-  DevBuf p2p_ctr;   // block-completion counter of the peer-exchange kernels
+  DevBuf p2p_ctr;   // [0] block-completion counter of the peer-exchange kernels, [1] device step counter
+  bool join_pending[3] = {false, false, false};   // a side-stream sort was forked and not joined yet
+  bool capturing = false;                        // b200rec_capture_begin .. _end
+  long long capture_l0 = 0;
+  std::vector<std::pair<cudaGraphExec_t, int>> user_graphs;   // (executable, kernel nodes)
   DevBuf x0, gx0, gy, gnA, gnB, pooled, gpooled;
   DevBuf xL, s_cross, g_xL;
   DevBuf ip, gip, pre, hbuf;

@@ -9,7 +9,10 @@
 //                       double-buffered by step parity so the owner can reset the next one)
 //   rows_in[G*cap*K], w_in[G*cap]        rows returned by each owner (block o written by owner o)
 //   grad_in[G*cap*K], gw_in[G*cap]       per-nnz gradients from each source (block s)
-//   flags  [3][G]       flags[phase][src] = step number, written by src after its data (release.sys)
+//   dense_in[mats]      this rank's dense gradients, read by every peer (one-shot allreduce, phase 3)
+//   flags  [4][G]       flags[phase][src] = step number, written by src after its data (release.sys)
+// The step number lives in a device counter (advanced by p2p_begin_step) so that a captured CUDA
+// graph of the whole step can be replayed.
 // A writer kernel ends with: __threadfence_system() by every thread, __syncthreads(), one atomicInc
 // per block, and the LAST block stores the step number into every peer's flag.  A one-warp wait kernel
 // spins (acquire.sys) until all G flags of a phase reach the step, trapping after ~2 s.
@@ -26,6 +29,8 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   return v;
 }
 
+__device__ __forceinline__ int p2p_step(const P2P& c) { return c.step > 0 ? c.step : *c.step_ptr - c.step; }
+
 // end-of-kernel signal: every thread of every block must call this (convergently)
 __device__ __forceinline__ void p2p_signal(const P2P& c, int phase) {
   __threadfence_system();
@@ -34,12 +39,14 @@ __device__ __forceinline__ void p2p_signal(const P2P& c, int phase) {
     const unsigned last = gridDim.x * gridDim.y - 1;
     if (atomicInc(c.block_counter, last) == last) {
       __threadfence_system();
-      for (int p = 0; p < c.world; ++p) st_release_sys(c.flags[p] + phase * c.world + c.rank, c.step);
+      const int step = p2p_step(c);
+      for (int p = 0; p < c.world; ++p) st_release_sys(c.flags[p] + phase * c.world + c.rank, step);
     }
   }
 }
 
-__global__ void p2p_wait_kernel(const int* flags, int phase, int world, int step) {
+// threads 0..world-1 spin until every source's flag of `phase` reaches the step; then the block syncs
+__device__ __forceinline__ void p2p_wait_block(const int* flags, int phase, int world, int step) {
   const int s = threadIdx.x;
   if (s < world) {
     const long long t0 = clock64();
@@ -49,55 +56,170 @@ __global__ void p2p_wait_kernel(const int* flags, int phase, int world, int step
   __syncthreads();
 }
 
-int p2p_wait(const int* flags, int phase, int world, int step, cudaStream_t st) {
+__global__ void p2p_wait_kernel(const int* flags, int phase, int world, int step, const int* step_ptr) {
+  p2p_wait_block(flags, phase, world, step > 0 ? step : *step_ptr - step);
+}
+
+int p2p_wait(const int* flags, int phase, int world, int step, const int* step_ptr, cudaStream_t st) {
   ProfTag tag("p2p_wait");
-  B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags, phase, world, step);
+  B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags, phase, world, step, step_ptr);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+// start of a step: advance the device step counter and reset the ids buffer of the NEXT step to the
+// -1 padding (nobody writes that buffer before this rank's next phase-0 signal)
+__global__ void p2p_begin_step_kernel(int* step_ctr, int* ids_next, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    ids_next[i] = -1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *step_ctr += 1;
+}
+int p2p_begin_step(int* step_ctr, int* ids_next, long long n, cudaStream_t st) {
+  ProfTag tag("p2p_dispatch_ids");
+  int grid = cdiv(n > 0 ? n : 1, 1024);
+  if (grid > 148 * 4) grid = 148 * 4;
+  B200_LAUNCH(p2p_begin_step_kernel, grid, 256, 0, st, step_ctr, ids_next, n);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+// ---- phase 3: dense gradients, one-shot allreduce over peer loads -----------------------------------
+// Reference: the dense gradients go to the PS like the embedding ones (ParRecModel.scala:247-264);
+// data-parallel replicas need their SUM.  Every rank publishes its vector in symmetric memory and
+// then reads all G vectors, adding them in rank order: all replicas get bit-identical sums.
+__global__ void __launch_bounds__(256) p2p_publish_kernel(long long n, const float* src, float* mine, P2P c) {
+  const long long n4 = n >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(mine);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x)
+    d4[i] = s4[i];
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) mine[n4 * 4 + threadIdx.x] = src[n4 * 4 + threadIdx.x];
+  p2p_signal(c, 3);
+}
+
+__global__ void __launch_bounds__(256) p2p_reduce_kernel(long long n, float* dst, P2P c, PeerF bufs) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v[P2P_MAX];
+#pragma unroll
+    for (int p = 0; p < P2P_MAX; ++p)
+      if (p < c.world) v[p] = __ldcg(reinterpret_cast<const float4*>(bufs.p[p]) + i);
+    float4 a = v[0];
+#pragma unroll
+    for (int p = 1; p < P2P_MAX; ++p)
+      if (p < c.world) {
+        a.x = __fadd_rn(a.x, v[p].x); a.y = __fadd_rn(a.y, v[p].y);
+        a.z = __fadd_rn(a.z, v[p].z); a.w = __fadd_rn(a.w, v[p].w);
+      }
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    float a = __ldcg(bufs.p[0] + i);
+    for (int p = 1; p < c.world; ++p) a = __fadd_rn(a, __ldcg(bufs.p[p] + i));
+    dst[i] = a;
+  }
+}
+
+int p2p_allreduce(long long n, float* inout, const int* flags_local, const P2P& c, const PeerF& bufs,
+                  cudaStream_t st) {
+  if (n <= 0) return B200REC_OK;
+  ProfTag tag("p2p_allreduce");
+  int grid = cdiv(n / 4 > 0 ? n / 4 : 1, 256);
+  if (grid > 148 * 4) grid = 148 * 4;
+  B200_LAUNCH(p2p_publish_kernel, grid, 256, 0, st, n, (const float*)inout, bufs.p[c.rank], c);
+  // a one-warp kernel does the spinning: the reduce blocks must not hold SMs while a peer is late
+  B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags_local, 3, c.world, c.step, c.step_ptr);
+  B200_LAUNCH(p2p_reduce_kernel, grid, 256, 0, st, n, inout, c, bufs);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }
 
 // ---- phase 0: ids to their owners ------------------------------------------------------------------
-__global__ void p2p_place_kernel(long long n, const int* n_dev, int cap, const int* feats,
-                                 const unsigned* owner_sorted, const unsigned* perm, const int* offsets,
-                                 int* dst, int* overflow, P2P c, PeerI ids_in) {
+// Ranking (stable counting sort by owner, csrc/shard.cu) and placement in ONE kernel: an item's sorted
+// position gives its slot; its local row is stored straight into the owner's ids_in.
+constexpr int PCS_ITEMS = 2048;   // must equal CS_ITEMS of shard.cu
+constexpr int PCS_MAXW = 32;
+
+__global__ void __launch_bounds__(256) p2p_rank_place_kernel(long long n, const int* n_dev, long long period,
+                                                             int cap, const int* feats,
+                                                             const int* block_offsets, int* dst,
+                                                             int* overflow, P2P c, PeerI ids_in) {
+  __shared__ int run[PCS_MAXW];
+  __shared__ int wcnt[8][PCS_MAXW];
   if (n_dev) n = min(n, (long long)*n_dev);
-  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (p < n) {
-    const int o = (int)owner_sorted[p];
-    const int slot = (int)p - offsets[o];
-    const long long i = perm[p];
-    if (slot >= cap) {
-      atomicOr(overflow, 1);
-      dst[i] = o * cap;
-    } else {
-      ids_in.p[o][(long long)c.rank * cap + slot] = feats[i] / c.world;   // store into the owner's memory
-      dst[i] = o * cap + slot;
+  const int world = c.world;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < PCS_MAXW) run[threadIdx.x] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * PCS_ITEMS;
+  for (int k0 = 0; k0 < PCS_ITEMS; k0 += 256) {
+    const long long i = base + k0 + threadIdx.x;
+    long long id = 0;
+    int o = -1;
+    if (i < n) {
+      id = feats[i];
+      o = (int)((id + id / period) % world);
     }
+    int my_rank = 0;
+    for (int q = 0; q < world; ++q) {
+      const unsigned m = __ballot_sync(0xffffffffu, o == q);
+      if (o == q) my_rank = __popc(m & ((1u << lane) - 1));
+      if (lane == 0) wcnt[warp][q] = __popc(m);
+    }
+    __syncthreads();
+    if (o >= 0) {
+      int before = run[o];
+      for (int w = 0; w < warp; ++w) before += wcnt[w][o];
+      const int slot = block_offsets[blockIdx.x * world + o] + before + my_rank;   // position within owner o
+      if (slot >= cap) {
+        atomicOr(overflow, 1);
+        dst[i] = o * cap;
+      } else {
+        ids_in.p[o][(long long)c.rank * cap + slot] = (int)(id / world);   // store into the owner's memory
+        dst[i] = o * cap + slot;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < world) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += wcnt[w][threadIdx.x];
+      run[threadIdx.x] += t;
+    }
+    __syncthreads();
   }
   p2p_signal(c, 0);
 }
 
-// shard.cu: owner keys -> stable sort -> per-owner offsets
+int shard_hist_scan(ShardPlanWorkspace& ws, long long n, const int* n_dev, int world, long long period,
+                    const int* feats, cudaStream_t st);
+
 int p2p_plan(ShardPlanWorkspace& ws, long long n, const int* n_dev, long long period, int cap,
              const int* feats, int* dst, int* overflow, const P2P& c, const PeerI& ids_in, cudaStream_t st) {
   ProfTag tag("p2p_dispatch_ids");
-  B200_TRY(shard_sort(ws, n, n_dev, c.world, period, feats, st));
-  int grid = cdiv(n > 0 ? n : 1, 256);
-  B200_LAUNCH(p2p_place_kernel, grid, 256, 0, st, n, n_dev, cap, feats, ws.keys_sorted.as<unsigned>(),
-              ws.perm.as<unsigned>(), ws.offsets.as<int>(), dst, overflow, c, ids_in);
+  B200_TRY(shard_hist_scan(ws, n, n_dev, c.world, period, feats, st));
+  const int n_blocks = cdiv(n > 0 ? n : 1, PCS_ITEMS);
+  B200_LAUNCH(p2p_rank_place_kernel, n_blocks, 256, 0, st, n, n_dev, period, cap, feats, ws.keys.as<int>(),
+              dst, overflow, c, ids_in);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }
 
 // per-nnz slot = slot of the non-zero's distinct id  (dispatch over distinct ids: dedup before exchange)
-__global__ void p2p_compose_kernel(long long n, const int* inv, const int* dst_unique, int* dst) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = dst_unique[inv[i]];
+__global__ void p2p_compose_kernel(long long n, const unsigned* perm, const int* seg_idx,
+                                   const int* dst_unique, int* dst) {
+  // sorted position p of the batch's ids: non-zero perm[p] belongs to distinct id seg_idx[p] - 1
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p < n) dst[perm[p]] = dst_unique[seg_idx[p] - 1];
 }
-int p2p_compose(long long n, const int* inv, const int* dst_unique, int* dst, cudaStream_t st) {
+int p2p_compose(SegSumWorkspace& ws, long long n, const int* dst_unique, int* dst, cudaStream_t st) {
   if (n <= 0) return B200REC_OK;
   ProfTag tag("p2p_dispatch_ids");
-  B200_LAUNCH(p2p_compose_kernel, cdiv(n, 256), 256, 0, st, n, inv, dst_unique, dst);
+  B200_LAUNCH(p2p_compose_kernel, cdiv(n, 256), 256, 0, st, n, ws.vals_b.as<unsigned>(), ws.vals_a.as<int>(),
+              dst_unique, dst);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }

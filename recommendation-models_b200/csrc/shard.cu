@@ -173,6 +173,24 @@ static int shard_sort_impl(ShardPlanWorkspace& ws, long long n, const int* n_dev
   return B200REC_OK;
 }
 
+// histogram + scan only (the caller ranks and places in one kernel): block offsets in ws.keys,
+// owner offsets in ws.offsets
+int shard_hist_scan(ShardPlanWorkspace& ws, long long n, const int* n_dev, int world, long long period,
+                    const int* feats, cudaStream_t st) {
+  B200_REQUIRE(world >= 1 && world <= CS_MAXW, B200REC_ERR_ARG, "world size %d out of range", world);
+  B200_REQUIRE(period >= world && period % world == 0, B200REC_ERR_ARG,
+               "shard period %lld must be a positive multiple of the world size %d", period, world);
+  B200_TRY(ws.reserve(n));
+  const int n_blocks = cdiv(n > 0 ? n : 1, CS_ITEMS);
+  B200_TRY(ws.keys.reserve((size_t)n_blocks * world * sizeof(int) + 64));
+  int* block_counts = ws.keys.as<int>();
+  B200_LAUNCH(shard_hist_kernel, n_blocks, 256, 0, st, n, n_dev, world, period, feats, block_counts,
+              (int*)nullptr, 0LL);
+  B200_LAUNCH(shard_scan_kernel, 1, 256, 0, st, n_blocks, world, block_counts, ws.offsets.as<int>());
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
 int shard_sort(ShardPlanWorkspace& ws, long long n, const int* n_dev, int world, long long period,
                const int* feats, cudaStream_t st) {
   return shard_sort_impl(ws, n, n_dev, world, period, feats, nullptr, 0, st);

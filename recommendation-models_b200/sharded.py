@@ -176,10 +176,12 @@ class ShardedParRecModel:
 
 
 class P2PShardedParRecModel:
-    """The same step with the exchange over NVLink peer memory (csrc/p2p.cu) instead of NCCL
-    all-to-alls: kernels store ids / rows / gradients straight into the peers' symmetric buffers and
-    order them with release/acquire flags; only the dense allreduce is still an NCCL call.  Buffers
-    come from torch symmetric memory (plumbing: it maps every rank's allocation into this process)."""
+    """The same step with the exchange over NVLink peer memory (csrc/p2p.cu) instead of NCCL: kernels
+    store ids / rows / gradients straight into the peers' symmetric buffers and order them with
+    release/acquire flags; the dense gradients are summed by a one-shot allreduce over peer loads.
+    No NCCL call is left in the step, so the whole step (side-stream sorts included) is captured in
+    a CUDA graph per step parity and replayed (`load` + `step`).  Buffers come from torch symmetric
+    memory (plumbing: it maps every rank's allocation into this process)."""
 
     def __init__(self, ops, dist, spec, batch, n_fields, dim, cap=None, group=None):
         import torch
@@ -201,29 +203,49 @@ class P2PShardedParRecModel:
             ptrs = (C.c_void_p * G)(*[int(p) for p in h.buffer_ptrs])
             return t, h, ptrs
 
-        self.ids_in = [symm(n, torch.int32, -1) for _ in range(2)]
+        # ids ring, 4 deep: while step t runs, peers may already store the ids of step t + 1 (dispatched
+        # one step ahead), buffer t - 1 may still be read by a slower owner, and buffer t + 3 is reset
+        self.ids_in = [symm(n, torch.int32, -1) for _ in range(4)]
         self.rows_in = symm(n * dim, torch.float32, 0)
         self.w_in = symm(n, torch.float32, 0)
         self.grad_in = symm(n * dim, torch.float32, 0)
         self.gw_in = symm(n, torch.float32, 0)
-        self.flags = symm(3 * G, torch.int32, 0)
-        self.dst = torch.empty(N, dtype=torch.int32, device=dev)
+        self.n_dense = ops.dense_grads().numel()
+        self.dense_in = symm((self.n_dense + 3) // 4 * 4, torch.float32, 0)
+        self.flags = symm(4 * G, torch.int32, 0)
+        self.dst = [torch.empty(N, dtype=torch.int32, device=dev) for _ in range(2)]       # by step parity
+        self.dst_u = [torch.empty(N, dtype=torch.int32, device=dev) for _ in range(2)]
         self.grad_rows = torch.empty(N * dim, dtype=torch.float32, device=dev)   # per-nnz, local order
         self.grad_w = torch.empty(N, dtype=torch.float32, device=dev)
         # local dedup (one set per workspace 0 / 2: the next batch's ids are sorted ahead of time)
         self.loc = {ws: dict(uniq=torch.empty(N, dtype=torch.int32, device=dev),
-                             n=torch.zeros(1, dtype=torch.int32, device=dev), feats=None) for ws in (0, 2)}
-        self.inv = torch.empty(N, dtype=torch.int32, device=dev)
-        self.dst_u = torch.empty(N, dtype=torch.int32, device=dev)
+                             n=torch.zeros(1, dtype=torch.int32, device=dev), feats=None, dispatched=None)
+                    for ws in (0, 2)}
+        self.side = {}
+        for ws in (0, 1, 2):
+            sp = C.c_void_p()
+            L.check(ops.lib.b200rec_model_side_stream(ops.model.handle, ws, C.byref(sp)))
+            self.side[ws] = sp.value
         self.G_loc = torch.empty(N * dim, dtype=torch.float32, device=dev)
         self.gw_loc = torch.empty(N, dtype=torch.float32, device=dev)
         self.unique = torch.empty(n, dtype=torch.int32, device=dev)
         self.G = torch.empty(n * dim, dtype=torch.float32, device=dev)
         self.gw = torch.empty(n, dtype=torch.float32, device=dev)
         self.gbits = max(1, int(spec.rows_global - 1).bit_length())
-        self.step = 0
+        self.step_no = 0
+        # replay mode: static input buffers per step parity, one captured graph per (parity, lr)
+        self.s_feats = [torch.zeros(N, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.s_targets = [torch.zeros(batch, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.loaded = [False, False]
+        self.graphs = {}
+        self.use_graph = True      # False: step() launches call by call (per-kernel profiling)
+        self.warm = False
         torch.cuda.synchronize()
         dist.barrier(group=group)
+
+    @staticmethod
+    def _ws(t):
+        return 0 if t & 1 else 2
 
     def _sort_local(self, ws, feats):
         o = self.ops
@@ -231,60 +253,139 @@ class P2PShardedParRecModel:
         L.check(o.lib.b200rec_segsum_sort_dev(o.model.handle, ws, self.K, feats.numel(), self.gbits, 0,
                                               feats.data_ptr(), d["uniq"].data_ptr(), d["n"].data_ptr(),
                                               o.stream_ptr))
-        d["feats"] = feats
+        d["feats"], d["dispatched"] = feats, None
 
-    def optimize(self, feats, targets, lr=None, next_feats=None):
-        """One step.  Every distinct id of the batch is requested once and its gradient, pre-reduced
-        locally in non-zero order, is pushed once (the owner then sums at most `world` rows per id, in
-        rank order).  `next_feats`: the ids of the following batch; their sort is started now on a
-        side stream so it is off the next step's critical path (input prefetch)."""
+    def _dispatch(self, t, ws, N, stream, step_arg):
+        """Distinct ids of step t's batch to their owners (+ the slot of every non-zero)."""
+        o, lib, m = self.ops, self.ops.lib, self.ops.model.handle
+        loc, p = self.loc[ws], t & 1
+        L.check(lib.b200rec_p2p_dispatch_ids_dev(m, N, loc["n"].data_ptr(), self.spec.world, self.spec.rank,
+                                                 self.spec.period, self.cap, step_arg, loc["uniq"].data_ptr(),
+                                                 self.ids_in[t % 4][2], self.flags[2], self.dst_u[p].data_ptr(),
+                                                 o.overflow.data_ptr(), stream))
+        L.check(lib.b200rec_p2p_compose_dst_dev(m, ws, N, self.dst_u[p].data_ptr(), self.dst[p].data_ptr(), stream))
+        loc["dispatched"] = t
+
+    def _body(self, t, feats, targets, lr, next_feats, join_next):
+        """Device calls of step `t` (t picks the ids buffer, the slot arrays and the sort workspace);
+        the step number the flags carry is the model's device counter, so the calls can be replayed."""
         o, lib, m = self.ops, self.ops.lib, self.ops.model.handle
         G, r, cap, st = self.spec.world, self.spec.rank, self.cap, o.stream_ptr
         N = feats.numel()
-        self.step += 1
-        t = self.step
-        ws = 0 if t & 1 else 2
-        cur, nxt = self.ids_in[t & 1], self.ids_in[(t + 1) & 1]
+        ws, p = self._ws(t), t & 1
+        cur, rst = self.ids_in[t % 4], self.ids_in[(t + 3) % 4]
         flags_t, _, flags_p = self.flags
+        loc = self.loc[ws]
+        L.check(lib.b200rec_p2p_begin_step_dev(m, rst[0].data_ptr(), rst[0].numel(), st))
+        if loc["feats"] is not feats:
+            if loc["dispatched"] == t:
+                # its ids are in the owners' buffers and flagged: another batch cannot take the step
+                raise RuntimeError("the batch passed as next_feats / staged by load() must be the next step's")
+            self._sort_local(ws, feats)
+        L.check(lib.b200rec_segsum_join_dev(m, ws, st))
+        if loc["dispatched"] != t:                                       # not sent one step ahead
+            self._dispatch(t, ws, N, st, 0)
+        L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 0, G, 0, st))
+        o.segsum_sort(cur[0], self.unique)                               # owner-side sort, side stream
+        if next_feats is not None:
+            # next batch, on a side stream: sort its ids and send them to their owners already
+            self._sort_local(2 - ws, next_feats)
+            self._dispatch(t + 1, 2 - ws, next_feats.numel(), self.side[2 - ws], -1)
+            L.check(lib.b200rec_side_rejoin_dev(m, 2 - ws))
+        L.check(lib.b200rec_p2p_gather_dev(m, o.table.handle, G, r, cap, 0, cur[0].data_ptr(),
+                                           self.rows_in[2], self.w_in[2], flags_p, st))
+        L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 1, G, 0, st))
+        L.check(lib.b200rec_step_rows_dev(m, self.B, self.dst[p].data_ptr(), self.rows_in[0].data_ptr(),
+                                          self.w_in[0].data_ptr(), self.w_in[0].numel(),
+                                          targets.data_ptr(), self.grad_rows.data_ptr(),
+                                          self.grad_w.data_ptr(), 0, st))
+        # dense gradients: summed over the replicas on the owner-sort side stream, under the embedding
+        # gradient exchange
+        L.check(lib.b200rec_side_fork_dev(m, 1, st))
+        L.check(lib.b200rec_p2p_allreduce_dev(m, self.n_dense, G, r, 0, o._mats_grad_ptr,
+                                              self.dense_in[2], flags_p, flags_t.data_ptr(), self.side[1]))
+        L.check(lib.b200rec_side_rejoin_dev(m, 1))
+        # local pre-reduce per distinct id (in non-zero order), then one push per distinct id
+        L.check(lib.b200rec_segsum_reduce_dev(m, ws, self.K, N, self.gbits, 0, feats.data_ptr(),
+                                              self.grad_rows.data_ptr(), self.grad_w.data_ptr(),
+                                              loc["uniq"].data_ptr(), self.G_loc.data_ptr(),
+                                              self.gw_loc.data_ptr(), loc["n"].data_ptr(), st))
+        L.check(lib.b200rec_p2p_push_grads_dev(m, N, loc["n"].data_ptr(), G, r, cap, 0,
+                                               self.dst_u[p].data_ptr(), self.G_loc.data_ptr(),
+                                               self.gw_loc.data_ptr(), self.grad_in[2], self.gw_in[2],
+                                               flags_p, st))
+        L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 2, G, 0, st))
+        o.segsum(cur[0], self.grad_in[0], self.gw_in[0], self.unique, self.G, self.gw)   # joins side stream 1
+        if lr is not None:
+            o.apply_sgd(self.unique, self.G, self.gw, lr)
+        if join_next and next_feats is not None:
+            L.check(lib.b200rec_segsum_join_dev(m, 2 - ws, st))   # a graph must end with every fork joined
+        loc["feats"] = None
+
+    def optimize(self, feats, targets, lr=None, next_feats=None):
+        """One step, launched call by call.  Every distinct id of the batch is requested once and its
+        gradient, pre-reduced locally in non-zero order, is pushed once (the owner then sums at most
+        `world` rows per id, in rank order).  `next_feats`: the ids of the following batch; their sort
+        is started now on a side stream so it is off the next step's critical path (input prefetch)."""
+        self.step_no += 1
+        with self.ops.stream_ctx():
+            self._body(self.step_no, feats, targets, lr, next_feats, False)
+        self.loaded = [False, False]
+        self.warm = True
+
+    # ---- replay mode -------------------------------------------------------------------------------
+    def load(self, feats, targets):
+        """Stage the batch of the step AFTER the next `step()` call (or of the first one) into the
+        static buffers; feats / targets: device or pinned host tensors.  Stream-ordered."""
+        p = (self.step_no + 1) & 1
+        if self.loaded[p]:
+            p ^= 1
+            if self.loaded[p]:
+                raise RuntimeError("two batches are staged already: call step()")
+        with self.ops.stream_ctx():
+            self.s_feats[p].copy_(feats, non_blocking=True)
+            self.s_targets[p].copy_(targets, non_blocking=True)
+        self.loaded[p] = True
+
+    def step(self, lr=None):
+        """Run the step on the batch staged first; the batch staged second (if any) has its ids sorted
+        on a side stream meanwhile.  The device calls are captured once per (parity, lr, prefetch) and
+        replayed as one CUDA graph afterwards (4 graphs in steady state: the ids ring is 4 deep)."""
+        o, lib, m = self.ops, self.ops.lib, self.ops.model.handle
+        t = self.step_no + 1
+        p, ws = t & 1, self._ws(t)
+        if not self.loaded[p]:
+            raise RuntimeError("step() without a staged batch: call load(feats, targets) first")
+        have_next = self.loaded[p ^ 1]
+        feats, targets = self.s_feats[p], self.s_targets[p]
+        nxt = self.s_feats[p ^ 1] if have_next else None
         with o.stream_ctx():
-            nxt[0].fill_(-1)   # nobody writes this buffer before my next signal (see csrc/p2p.cu)
-            loc = self.loc[ws]
-            if loc["feats"] is not feats:
+            if self.loc[ws]["feats"] is not feats:        # first step after load(): nothing prefetched
                 self._sort_local(ws, feats)
-            L.check(lib.b200rec_segsum_join_dev(m, ws, st))
-            L.check(lib.b200rec_segsum_inverse_dev(m, ws, N, self.inv.data_ptr(), st))
-            L.check(lib.b200rec_p2p_dispatch_ids_dev(m, N, loc["n"].data_ptr(), G, r, self.spec.period, cap, t,
-                                                     loc["uniq"].data_ptr(), cur[2], flags_p,
-                                                     self.dst_u.data_ptr(), o.overflow.data_ptr(), st))
-            L.check(lib.b200rec_p2p_compose_dst_dev(m, N, self.inv.data_ptr(), self.dst_u.data_ptr(),
-                                                    self.dst.data_ptr(), st))
-            L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 0, G, t, st))
-            o.segsum_sort(cur[0], self.unique)                               # owner-side sort, side stream
-            if next_feats is not None:
-                self._sort_local(2 - ws, next_feats)                         # next batch's ids, side stream
-            L.check(lib.b200rec_p2p_gather_dev(m, o.table.handle, G, r, cap, t, cur[0].data_ptr(),
-                                               self.rows_in[2], self.w_in[2], flags_p, st))
-            L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 1, G, t, st))
-            L.check(lib.b200rec_step_rows_dev(m, self.B, self.dst.data_ptr(), self.rows_in[0].data_ptr(),
-                                              self.w_in[0].data_ptr(), self.w_in[0].numel(),
-                                              targets.data_ptr(), self.grad_rows.data_ptr(),
-                                              self.grad_w.data_ptr(), 0, st))
-            work = self.dist.all_reduce(o.dense_grads(), group=self.group, async_op=True)
-            # local pre-reduce per distinct id (in non-zero order), then one push per distinct id
-            L.check(lib.b200rec_segsum_reduce_dev(m, ws, self.K, N, self.gbits, 0, feats.data_ptr(),
-                                                  self.grad_rows.data_ptr(), self.grad_w.data_ptr(),
-                                                  loc["uniq"].data_ptr(), self.G_loc.data_ptr(),
-                                                  self.gw_loc.data_ptr(), loc["n"].data_ptr(), st))
-            L.check(lib.b200rec_p2p_push_grads_dev(m, N, loc["n"].data_ptr(), G, r, cap, t,
-                                                   self.dst_u.data_ptr(), self.G_loc.data_ptr(),
-                                                   self.gw_loc.data_ptr(), self.grad_in[2], self.gw_in[2],
-                                                   flags_p, st))
-            L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 2, G, t, st))
-            o.segsum(cur[0], self.grad_in[0], self.gw_in[0], self.unique, self.G, self.gw)
-            work.wait()
-            if lr is not None:
-                o.apply_sgd(self.unique, self.G, self.gw, lr)
-            loc["feats"] = None
+                L.check(lib.b200rec_segsum_join_dev(m, ws, o.stream_ptr))
+            if not self.warm or not self.use_graph:       # buffers take their final size in an eager step
+                self.step_no = t
+                self._body(t, feats, targets, lr, nxt, True)
+                self.warm = True
+            else:
+                pre = self.loc[ws]["dispatched"] == t
+                key = (t % 4, lr, have_next, pre)
+                if key not in self.graphs:
+                    gid = C.c_int(-1)
+                    L.check(lib.b200rec_capture_begin(m, o.stream_ptr))
+                    try:
+                        self._body(t, feats, targets, lr, nxt, True)
+                    finally:
+                        rc = lib.b200rec_capture_end(m, C.byref(gid), o.stream_ptr)
+                    L.check(rc)
+                    self.graphs[key] = gid.value
+                    self.loc[ws]["feats"] = feats         # the capture recorded, it did not run
+                self.step_no = t
+                L.check(lib.b200rec_graph_launch(m, self.graphs[key], o.stream_ptr))
+                self.loc[ws]["feats"] = None
+        self.loaded[p] = False
+        if have_next:
+            self.loc[2 - ws]["feats"], self.loc[2 - ws]["dispatched"] = nxt, t + 1
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -324,11 +425,27 @@ def bench(args, pkg):
     ps.setParams(np.array([0.1], np.float32), synth.init_mats(B.SEED_PARAMS, model.getMatsSize()))
     ops = GpuOps(pkg, model, table, spec, batch, None, torch, dev)
     use_p2p = getattr(args, "exchange", "p2p") == "p2p" and world <= 8
+    W, Ksteps = args.warmup, args.steps
+    nb = min(W + Ksteps, 32)
+    # every rank draws its own batches: global step index = s * world + rank
+    batches = [synth.make_feats(B.SEED_DATA, s * world + rank, batch, F, rows)[1] for s in range(nb)]
+    cap = None
+    if use_p2p:
+        # bucket capacity of the dedup'd exchange from the data: largest per-owner count of distinct ids
+        # over the first batches, +30 % (the NCCL path exchanges every non-zero and keeps N/G * 1.25);
+        # overflow is still flagged on the device and reported in the result line
+        need = 0
+        for f in batches[:8]:
+            u = np.unique(f)
+            need = max(need, int(np.bincount(spec.owner(u), minlength=world).max()))
+        t = torch.tensor([need], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cap = (int(t.item() * 1.3) + 1024 + 15) // 16 * 16
     sh = None
     if use_p2p:
         # every rank must take the same path: agree on whether symmetric memory came up everywhere
         try:
-            sh = P2PShardedParRecModel(ops, dist, spec, batch, F, K)
+            sh = P2PShardedParRecModel(ops, dist, spec, batch, F, K, cap=cap)
             ok = torch.ones(1, device=dev)
         except Exception as e:  # noqa: BLE001  (no peer mapping on this box -> NCCL exchange)
             sys.stderr.write(f"rank {rank}: peer-memory exchange unavailable ({e!r}); using NCCL all-to-all\n")
@@ -339,19 +456,24 @@ def bench(args, pkg):
     if sh is None:
         sh = ShardedParRecModel(ops, dist, spec, batch, F, K)
     ops.cap = sh.cap
-    W, Ksteps = args.warmup, args.steps
-    nb = min(W + Ksteps, 32)
-    # every rank draws its own batches: global step index = s * world + rank
-    batches = [synth.make_feats(B.SEED_DATA, s * world + rank, batch, F, rows)[1] for s in range(nb)]
     dev_b = [(torch.from_numpy(f).to(dev), torch.from_numpy(synth.make_targets(B.SEED_DATA, f, batch, F)).to(dev))
              for f in batches]
+    graphed = use_p2p and not getattr(args, "no_graph", False)
+    if use_p2p:
+        sh.use_graph = graphed
+
     def run_step(i):
         f, t = dev_b[i % nb]
         if use_p2p:
-            sh.optimize(f, t, next_feats=dev_b[(i + 1) % nb][0])   # the next batch's ids are known: prefetch
+            # batch i was staged (its ids sorted and sent to their owners) during the previous step;
+            # stage batch i + 1 and run (replay) the step
+            sh.load(*dev_b[(i + 1) % nb])
+            sh.step()
         else:
             sh.optimize(f, t)
 
+    if use_p2p:
+        sh.load(*dev_b[0])
     for i in range(W):
         run_step(i)
     torch.cuda.synchronize()
@@ -386,11 +508,15 @@ def bench(args, pkg):
     h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
 
     def host_step(i):
-        f, t = pin[i % nb]
-        with ops.stream_ctx():
-            d_f.copy_(f, non_blocking=True)
-            d_t.copy_(t, non_blocking=True)
-        sh.optimize(d_f, d_t)
+        if use_p2p:
+            sh.load(*pin[(i + 1) % nb])     # H2D of the next batch, then the replayed step on the staged one
+            sh.step()
+        else:
+            f, t = pin[i % nb]
+            with ops.stream_ctx():
+                d_f.copy_(f, non_blocking=True)
+                d_t.copy_(t, non_blocking=True)
+            sh.optimize(d_f, d_t)
         with ops.stream_ctx():
             h_loss.copy_(ops.loss(), non_blocking=True)
         ops.stream.synchronize()
@@ -411,6 +537,8 @@ def bench(args, pkg):
     clk = clocks.stop()
 
     # per-kernel pass on rank 0 (own kernels only; NCCL kernels are not in this list)
+    if use_p2p:
+        sh.use_graph = False                    # call by call: the per-kernel events need eager launches
     L.profile_begin()
     for i in range(min(Ksteps, 10)):
         run_step(W + i)
@@ -431,13 +559,15 @@ def bench(args, pkg):
                                    f"table_rows={rows} row-sharded over {world} GPUs (BASELINE configs[2]/[4])",
                        "global_batch": batch * world, "parallelism": f"table row-sharded x{world} "
                        f"({'NVLink peer-memory stores fused into the gather / gradient kernels' if use_p2p else 'NCCL all-to-all'}), "
-                       f"dense dp{world} (NCCL allreduce)", "exchange": "p2p" if use_p2p else "nccl", "bucket_capacity": sh.cap,
+                       f"dense dp{world} ({'one-shot allreduce over NVLink peer loads' if use_p2p else 'NCCL allreduce'})",
+                       "exchange": "p2p" if use_p2p else "nccl", "cuda_graph": bool(graphed), "bucket_capacity": sh.cap,
                        "bucket_overflow": int(ovf.item()),
                        "l2": "table shard > L2; new ids every step; no explicit flush", "gemm_mode": args.gemm_mode},
             "clocks": clk,
             "e2e": {"value": round(batch * world * Ksteps / float(e2e.item()), 1), "unit": "samples/s",
                     "h2d_bytes_per_step": batch * F * 4 + batch * 4, "d2h_bytes_per_step": 4,
-                    "call": "ShardedParRecModel.optimize (pinned host ids + labels in, loss out), per rank",
+                    "call": ("P2PShardedParRecModel.load + step" if use_p2p else "ShardedParRecModel.optimize") +
+                            " (pinned host ids + labels in, loss out), per rank",
                     "last_loss": round(last, 6)},
             "gpu_launches": int(launches),
             "exchange_bytes_per_gpu_per_step": {"ids": n_slots * 4, "rows_back": n_slots * (K + 1) * 4,

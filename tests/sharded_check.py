@@ -143,9 +143,18 @@ def run(rank, world, backend, device=None):
                                                 synth.init_mats(SEED_PARAMS, model.getMatsSize()))
         ops = GpuOps(pkg, model, table, spec, B, cap, torch, dev)
         tf, tt = torch.from_numpy(feats).to(dev), torch.from_numpy(targets).to(dev)
-    cls = P2PShardedParRecModel if backend == "p2p" else ShardedParRecModel
+    cls = P2PShardedParRecModel if backend.startswith("p2p") else ShardedParRecModel
     sh = cls(ops, dist, spec, B, F, K, cap=cap)
-    sh.optimize(tf, tt)
+    if backend == "p2p_graph":
+        # replay mode: step 1 runs call by call (buffers take their size), steps 2 and 3 capture the
+        # two parities, steps 4 and 5 replay them; the next batch is staged and sorted one step ahead
+        sh.load(tf, tt)
+        for _ in range(5):
+            sh.load(tf, tt)
+            sh.step()
+        assert len(sh.graphs) >= 2
+    else:
+        sh.optimize(tf, tt)
     if backend == "p2p":   # a second step exercises the double-buffered id slots and the step flags
         sh.optimize(tf, tt)
     if backend != "gloo":
@@ -197,7 +206,7 @@ if __name__ == "__main__":
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    for backend in ("nccl", "p2p"):
+    for backend in ("nccl", "p2p", "p2p_graph"):
         u = run(rank, world, backend, device=local)
         print(f"rank {rank}/{world}: sharded step ok ({backend}), {u} owned distinct rows", flush=True)
     dist.barrier()
