@@ -10,6 +10,7 @@
 // second pass (no float atomics).
 #pragma once
 #include "common.cuh"
+#include "kernels.h"
 
 namespace b200rec {
 
@@ -164,10 +165,7 @@ gemm_simt_kernel(int M, int N, int K, int k_chunk, AOp aop, BOp bop, Ep ep) {
 // out (+)= scale * sum_z ws[z]   (z ascending: fixed order)            -- dense.cu
 int splitk_reduce(const float* ws, int splits, long long MN, float scale, bool accumulate,
                   float* out, cudaStream_t st);
-// out[n] (+)= scale * sum_m g[m,n]; part = COLSUM_CHUNKS*N floats of scratch (fixed-order two stage) -- dense.cu
-constexpr int COLSUM_CHUNKS = 512;
-int colsum(int M, int N, const float* g, float scale, bool accumulate, float* out, float* part,
-           cudaStream_t st);
+// colsum / COLSUM_CHUNKS: kernels.h
 // the split count gemm_simt really uses for (K, splits)
 static inline int real_splits(int K, int splits) {
   if (splits < 1) splits = 1;

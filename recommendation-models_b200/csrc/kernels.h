@@ -237,7 +237,11 @@ int tc_linear_bwd_params(int M, int N, int K, const float* x, const float* gy, f
                          bool accumulate, float* gw, float* gb, DevBuf& scratch, int passes,
                          cudaStream_t st);
 int tc_prepack_linear(PrePack& pp, const float* mats, int in_dim, const int* dims, int n_layers,
-                      const long long* w_off, bool with_dx, cudaStream_t st);
+                      const long long* w_off, bool with_dx, cudaStream_t st, cudaStream_t st_dx);
+// out[n] (+)= scale * sum_m g[m,n]; part = COLSUM_CHUNKS*N floats of scratch (fixed-order two stage) -- dense.cu
+constexpr int COLSUM_CHUNKS = 512;
+int colsum(int M, int N, const float* g, float scale, bool accumulate, float* out, float* part,
+           cudaStream_t st);
 bool tc_cin_supported(int F, int H, int C);
 int tc_cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x_in, const float* W,
                      const float* b, float* x_out, int passes, cudaStream_t st);

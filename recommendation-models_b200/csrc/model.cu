@@ -112,6 +112,9 @@ int b200rec_model_s::init(int kind_, int F_, int K_, const int* fc_, int n_fc, c
   B200_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&side3, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&ev_aux_fork, &ev_aux_pack, &ev_aux_join, &ev_aux_cs[0], &ev_aux_cs[1]})
+    B200_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&ev_fork3, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&ev_join3, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&ev_fork2, cudaEventDisableTiming));
@@ -133,6 +136,7 @@ void b200rec_model_s::destroy() {
   if (side) cudaStreamSynchronize(side);
   if (side2) cudaStreamSynchronize(side2);
   if (side3) cudaStreamSynchronize(side3);
+  if (aux) cudaStreamSynchronize(aux);
   DevBuf* bufs[] = {&p_bias, &p_mats, &gmats, &scal, &d_feats, &d_targets, &d_index, &X, &wnz, &S,
                     &first, &second, &branch, &preds, &dlogit, &dXd, &dw, &gA, &gB, &scratch,
                     &uniq, &G, &gwU, &wpack, &wpack_mlp, &s1m, &s2m, &p2p_ctr, &x0, &gx0, &gy, &gnA, &gnB, &pooled, &gpooled, &xL, &s_cross,
@@ -154,6 +158,10 @@ void b200rec_model_s::destroy() {
   if (side) cudaStreamDestroy(side);
   if (side2) cudaStreamDestroy(side2);
   if (side3) cudaStreamDestroy(side3);
+  if (aux) cudaStreamDestroy(aux);
+  for (cudaEvent_t e : {ev_aux_fork, ev_aux_pack, ev_aux_join, ev_aux_cs[0], ev_aux_cs[1]})
+    if (e) cudaEventDestroy(e);
+  scratch_aux.release();
   if (ev_fork3) cudaEventDestroy(ev_fork3);
   if (ev_join3) cudaEventDestroy(ev_join3);
   if (ev_fork2) cudaEventDestroy(ev_fork2);
@@ -224,18 +232,40 @@ int b200rec_model_s::mlp_backward(int B, const float* x_in, const float* mats, f
                         const float* in_mask, cudaStream_t st) {
   float* g = gA.as<float>();
   float* g2 = gB.as<float>();
-  for (int l = (int)mlp.dims.size() - 1; l >= 0; --l) {
+  const int L = (int)mlp.dims.size();
+  int max_out = 1;
+  for (int d : mlp.dims) max_out = d > max_out ? d : max_out;
+  B200_TRY(scratch_aux.reserve((size_t)COLSUM_CHUNKS * max_out * sizeof(float)));
+  for (int l = L - 1; l >= 0; --l) {
     const int out = mlp.dims[l];
     const int in = l == 0 ? mlp.in_dim : mlp.dims[l - 1];
     const float* xp = l == 0 ? x_in : acts[l - 1].as<float>();
-    B200_TRY(linear_bwd_params(B, out, in, xp, g, 1.0f, false, gm + mlp.w_off[l], gm + mlp.b_off[l], scratch, st, gemm_mode));
+    // bias gradient (column sums of g) on the auxiliary stream, beside the two GEMMs of the layer
+    B200_CUDA(cudaEventRecord(ev_aux_fork, st));
+    B200_CUDA(cudaStreamWaitEvent(aux, ev_aux_fork, 0));
+    aux_open = true;
+    B200_TRY(colsum(B, out, g, 1.0f, false, gm + mlp.b_off[l], scratch_aux.as<float>(), aux));
+    B200_CUDA(cudaEventRecord(ev_aux_cs[l & 1], aux));
+    B200_TRY(linear_bwd_params(B, out, in, xp, g, 1.0f, false, gm + mlp.w_off[l], nullptr, scratch, st, gemm_mode));
     if (l > 0) {
+      // g2 held the gradient of layer l + 1: its column sums must have been read
+      if (l + 1 < L) B200_CUDA(cudaStreamWaitEvent(st, ev_aux_cs[(l + 1) & 1], 0));
       B200_TRY(linear_bwd_input(B, out, in, g, mats + mlp.w_off[l], acts[l - 1].as<float>(), g2, false, st, gemm_mode));
       float* t = g; g = g2; g2 = t;
     } else if (dx) {
       B200_TRY(linear_bwd_input(B, out, in, g, mats + mlp.w_off[l], in_mask, dx, false, st, gemm_mode));
     }
   }
+  return B200REC_OK;
+}
+
+// everything forked to the auxiliary stream is joined into st (a captured graph must end joined)
+int b200rec_model_s::aux_join(cudaStream_t st) {
+  if (!aux_open) return B200REC_OK;
+  B200_CUDA(cudaEventRecord(ev_aux_join, aux));
+  B200_CUDA(cudaStreamWaitEvent(st, ev_aux_join, 0));
+  aux_open = false;
+  aux_pack_pending = false;
   return B200REC_OK;
 }
 
@@ -319,8 +349,19 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   if (gemm_mode && !mlp.dims.empty()) {
     // every Linear weight of the tower, in the forward and (training) the gradInput stage layout, in
     // two launches instead of one per GEMM
+    cudaStream_t st_dx = st;
+    if (train) {   // the gradInput images are first needed in the backward: pack them beside the forward
+      B200_CUDA(cudaEventRecord(ev_aux_fork, st));
+      B200_CUDA(cudaStreamWaitEvent(aux, ev_aux_fork, 0));
+      st_dx = aux;
+      aux_open = true;
+    }
     B200_TRY(tc_prepack_linear(prepack, mats, mlp.in_dim, mlp.dims.data(), (int)mlp.dims.size(),
-                               mlp.w_off.data(), train, st));
+                               mlp.w_off.data(), train, st, st_dx));
+    if (train) {
+      B200_CUDA(cudaEventRecord(ev_aux_pack, aux));
+      aux_pack_pending = true;
+    }
     tl_prepack = &prepack;
   }
   Head h;
@@ -381,10 +422,14 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   h.dbias = a.dbias_out;
   if (a.gmats_out == gmats.as<float>()) h.dbias2 = gmats.as<float>() + mats_len;  // [mats grad | bias grad]
   B200_TRY(head_run(h, scratch, st));
-  if (!train) return B200REC_OK;
+  if (!train) return aux_join(st);
 
   // ---- dense branch backward ----------------------------------------------------------------------
   phase("dense_bwd");
+  if (aux_pack_pending) {
+    B200_CUDA(cudaStreamWaitEvent(st, ev_aux_pack, 0));
+    aux_pack_pending = false;
+  }
   const float* dlg = dlogit.as<float>();
   float* gm = a.gmats_out;
   float* dxd = nullptr;  // dense-branch gradient w.r.t. the embedding input
@@ -452,6 +497,8 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
     B200_TRY(linear_bwd_input(B, O, P, gh, wp, nullptr, gip.as<float>(), false, st, gemm_mode));
     B200_TRY(pnn_ip_bwd(B, F, K, Xp, gip.as<float>(), dxd, true, st));
   }
+
+  B200_TRY(aux_join(st));
 
   // ---- per-nnz gradients (GradUtil.scala:7-42) ------------------------------------------------------
   phase("emb_grad");

@@ -62,6 +62,12 @@ struct b200rec_model_s {
   cudaStream_t stream = nullptr, side = nullptr, side2 = nullptr, side3 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev_fork3 = nullptr, ev_join3 = nullptr;
+  // auxiliary stream of the dense branch: work that is off the dx chain (the gradInput weight images,
+  // the bias-gradient column sums) runs beside the GEMMs; always joined before run() returns
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_aux_fork = nullptr, ev_aux_pack = nullptr, ev_aux_join = nullptr, ev_aux_cs[2] = {nullptr, nullptr};
+  bool aux_pack_pending = false, aux_open = false;
+  b200rec::DevBuf scratch_aux;
   float* h_scal = nullptr;  // pinned 16 words: loss, dbias, n_unique, -, err, sorted
   bool params_set = false;
   // CUDA graph of the resident step (one per (B, table, gemm_mode)); captured after one eager warm-up
@@ -104,6 +110,7 @@ struct b200rec_model_s {
                   float* head_out, cudaStream_t st);
   int mlp_backward(int B, const float* x_in, const float* mats, float* gm, float* dx,
                    const float* in_mask, cudaStream_t st);
+  int aux_join(cudaStream_t st);
   int mlp_head_backward(int B, const float* x_in, const float* mats, float* gm, const float* dlg,
                         float* dx_if_no_hidden, cudaStream_t st);
   int run(const b200rec::RunArgs& a, cudaStream_t st);

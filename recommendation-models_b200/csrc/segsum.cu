@@ -75,6 +75,14 @@ __global__ void seg_heads_kernel(long long n, const unsigned* keys, const int* s
   }
 }
 
+// hot ids (segments longer than LONG_T) -> long_list, still in the sort half (off the critical path)
+__global__ void seg_long_kernel(const int* n_unique, const int* seg_start, int* long_list, int* long_count) {
+  const int U = *n_unique;
+  for (long long seg = blockIdx.x * (long long)blockDim.x + threadIdx.x; seg < U;
+       seg += (long long)gridDim.x * blockDim.x)
+    if (seg_start[seg + 1] - seg_start[seg] > LONG_T) long_list[atomicAdd(long_count, 1)] = (int)seg;
+}
+
 int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
   ProfTag tag("scatter_sort");
   B200_TRY(ws.reserve(a.n));
@@ -105,6 +113,12 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
   g_launches.fetch_add(2, std::memory_order_relaxed);
   B200_LAUNCH(seg_heads_kernel, cdiv(n, 256), 256, 0, st, (long long)n, keys_sorted, seg_idx,
               ws.seg_start.as<int>(), a.unique, a.n_unique, a.drop_pad);
+  {
+    int grid = cdiv(n, 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    B200_LAUNCH(seg_long_kernel, grid, 256, 0, st, a.n_unique, ws.seg_start.as<int>(), ws.long_list.as<int>(),
+                counters);
+  }
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -123,58 +137,83 @@ int segsum_inverse(SegSumWorkspace& ws, long long n, int* inv, cudaStream_t st) 
 
 // ---- in-order segment sums --------------------------------------------------------------------
 template <int LPR>
-__global__ void __launch_bounds__(256) segsum_short_kernel(const int* n_unique,
-                                                           const int* seg_start,
-                                                           const unsigned* perm, const float* dE,
-                                                           const float* dw, float* G, float* gw,
-                                                           int* long_list, int* long_count) {
+__device__ __forceinline__ void segsum_short_role(int block, int n_blocks, const int* n_unique,
+                                                  const int* seg_start, const unsigned* perm,
+                                                  const float* dE, const float* dw, float* G, float* gw) {
   constexpr int K = 4 * LPR;
   constexpr int UNR = 4;
   const int U = *n_unique;
-  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long tid = block * (long long)blockDim.x + threadIdx.x;
   const int sub = (int)(tid % LPR);
-  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
-  for (long long seg = tid / LPR; seg < U; seg += n_groups) {
-    const int start = seg_start[seg];
-    const int len = seg_start[seg + 1] - start;
-    if (len > LONG_T) {
-      if (sub == 0) long_list[atomicAdd(long_count, 1)] = (int)seg;
-      continue;
-    }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float aw = 0.f;
-    for (int j0 = 0; j0 < len; j0 += UNR) {
-      float4 v[UNR];
-      float w[UNR];
+  const long long n_groups = ((long long)n_blocks * blockDim.x) / LPR;
+  // SB segments per iteration: their (start, length), first position and first row are loaded as
+  // three batches of independent loads (the chain start -> perm -> row is paid once per batch, and
+  // most segments have one row); the remaining rows of a segment follow in order.
+  constexpr int SB = 4;
+  for (long long seg0 = tid / LPR; seg0 < U; seg0 += n_groups * SB) {
+    int start[SB], len[SB];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        w[u] = 0.f;
-        if (j0 + u < len) {
-          const long long p = perm[start + j0 + u];
-          if (dE) v[u] = ldg_f4(dE + p * K + sub * 4);
-          if (dw && sub == 0) w[u] = __ldg(dw + p);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        if (j0 + u < len) {
-          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
-          aw += w[u];
-        }
+    for (int i = 0; i < SB; ++i) {
+      const long long seg = seg0 + i * n_groups;
+      start[i] = 0; len[i] = 0;
+      if (seg < U) {
+        start[i] = seg_start[seg];
+        len[i] = seg_start[seg + 1] - start[i];
+        if (len[i] > LONG_T) len[i] = 0;   // a hot id: the long role sums it
       }
     }
-    if (G) st_f4(G + seg * K + sub * 4, acc);
-    if (gw && sub == 0) gw[seg] = aw;
+    unsigned p0[SB];
+#pragma unroll
+    for (int i = 0; i < SB; ++i) p0[i] = len[i] > 0 ? perm[start[i]] : 0u;
+    float4 v0[SB];
+    float w0[SB];
+#pragma unroll
+    for (int i = 0; i < SB; ++i) {
+      v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w0[i] = 0.f;
+      if (len[i] > 0) {
+        if (dE) v0[i] = ldg_f4(dE + (long long)p0[i] * K + sub * 4);
+        if (dw && sub == 0) w0[i] = __ldg(dw + p0[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < SB; ++i) {
+      if (len[i] <= 0) continue;
+      const long long seg = seg0 + i * n_groups;
+      float4 acc = make_float4(0.f + v0[i].x, 0.f + v0[i].y, 0.f + v0[i].z, 0.f + v0[i].w);
+      float aw = 0.f + w0[i];
+      for (int j0 = 1; j0 < len[i]; j0 += UNR) {
+        float4 v[UNR];
+        float w[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          w[u] = 0.f;
+          if (j0 + u < len[i]) {
+            const long long p = perm[start[i] + j0 + u];
+            if (dE) v[u] = ldg_f4(dE + p * K + sub * 4);
+            if (dw && sub == 0) w[u] = __ldg(dw + p);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          if (j0 + u < len[i]) {
+            acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+            aw += w[u];
+          }
+        }
+      }
+      if (G) st_f4(G + seg * K + sub * 4, acc);
+      if (gw && sub == 0) gw[seg] = aw;
+    }
   }
 }
 
 template <int LPR>
-__global__ void __launch_bounds__(256) segsum_long_kernel(const int* seg_start,
-                                                          const unsigned* perm, const float* dE,
-                                                          const float* dw, float* G, float* gw,
-                                                          const int* long_list,
-                                                          const int* long_count) {
+__device__ __forceinline__ void segsum_long_role(int block, int n_blocks, const int* seg_start,
+                                                 const unsigned* perm, const float* dE,
+                                                 const float* dw, float* G, float* gw,
+                                                 const int* long_list, const int* long_count) {
   // One warp per hot id.  Rows are LOADED 32/LPR x UNR at a time (all loads of a batch in flight,
   // the positions of the next batch prefetched meanwhile) and ADDED strictly in non-zero order
   // through shuffles, so the result equals the reference's sequential hash-map accumulation.
@@ -184,8 +223,8 @@ __global__ void __launch_bounds__(256) segsum_long_kernel(const int* seg_start,
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR, slot = lane / LPR;
   const int n_long = *long_count;
-  const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-  const int n_warps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  const int warp = (int)((block * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int n_warps = (int)(((long long)n_blocks * blockDim.x) >> 5);
   for (int wi = warp; wi < n_long; wi += n_warps) {
     const int seg = long_list[wi];
     const int start = seg_start[seg];
@@ -240,6 +279,19 @@ __global__ void __launch_bounds__(256) segsum_long_kernel(const int* seg_start,
   }
 }
 
+// ONE launch: the first l_blocks blocks take the hot ids (one warp each: they run longest, so they
+// start first), the others the short segments.  The hot-id list comes from the sort half.
+template <int LPR>
+__global__ void __launch_bounds__(256) segsum_kernel(int l_blocks, const int* n_unique, const int* seg_start,
+                                                     const unsigned* perm, const float* dE, const float* dw,
+                                                     float* G, float* gw, const int* long_list,
+                                                     const int* long_count) {
+  if ((int)blockIdx.x < l_blocks)
+    segsum_long_role<LPR>(blockIdx.x, l_blocks, seg_start, perm, dE, dw, G, gw, long_list, long_count);
+  else
+    segsum_short_role<LPR>(blockIdx.x - l_blocks, gridDim.x - l_blocks, n_unique, seg_start, perm, dE, dw, G, gw);
+}
+
 // any K: one thread per (segment, k), strictly sequential
 __global__ void segsum_generic_kernel(const int* n_unique, const int* seg_start,
                                       const unsigned* perm, int K, const float* dE,
@@ -273,13 +325,11 @@ static int launch_segsum(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) 
   long long groups = a.n;  // upper bound on the number of segments
   int grid = cdiv(groups * LPR, 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  B200_LAUNCH((segsum_short_kernel<LPR>), grid, 256, 0, st, a.n_unique, seg_start, perm, a.dE, a.dw,
-              a.G, a.gw, long_list, counters);
   long long max_long = a.n / LONG_T + 1;
   int lgrid = cdiv(max_long * 32, 256);
-  if (lgrid > 148 * 4) lgrid = 148 * 4;
-  B200_LAUNCH((segsum_long_kernel<LPR>), lgrid, 256, 0, st, seg_start, perm, a.dE, a.dw, a.G, a.gw,
-              long_list, counters);
+  if (lgrid > 148) lgrid = 148;
+  B200_LAUNCH((segsum_kernel<LPR>), lgrid + grid, 256, 0, st, lgrid, a.n_unique, seg_start, perm, a.dE, a.dw,
+              a.G, a.gw, long_list, counters);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }

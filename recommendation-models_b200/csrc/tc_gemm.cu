@@ -127,7 +127,7 @@ static const char* find_prepacked(const float* w, int fmt, int N, int K) {
 }
 
 int tc_prepack_linear(PrePack& pp, const float* mats, int in_dim, const int* dims, int n_layers,
-                      const long long* w_off, bool with_dx, cudaStream_t st) {
+                      const long long* w_off, bool with_dx, cudaStream_t st, cudaStream_t st_dx) {
   pp.n = 0;
   if (n_layers <= 0 || n_layers > 8 || !pp.blob) return B200REC_OK;
   PackJobs fwd{}, dx{};
@@ -166,7 +166,7 @@ int tc_prepack_linear(PrePack& pp, const float* mats, int in_dim, const int* dim
   }
   if (nd) {
     dim3 g(max_tiles_d, max_nkb_d < 32 ? max_nkb_d : 32, nd);
-    B200_LAUNCH_NAMED("tc_pack_weights", pack_linear_multi_kernel<true>, g, THREADS, 0, st, dx, blob);
+    B200_LAUNCH_NAMED("tc_pack_weights", pack_linear_multi_kernel<true>, g, THREADS, 0, st_dx, dx, blob);
   }
   B200_CHECK_LAUNCH();
   return B200REC_OK;
