@@ -162,6 +162,7 @@ void b200rec_model_s::destroy() {
   for (cudaEvent_t e : {ev_aux_fork, ev_aux_pack, ev_aux_join, ev_aux_cs[0], ev_aux_cs[1]})
     if (e) cudaEventDestroy(e);
   scratch_aux.release();
+  wpack_aux.release();
   if (ev_fork3) cudaEventDestroy(ev_fork3);
   if (ev_join3) cudaEventDestroy(ev_join3);
   if (ev_fork2) cudaEventDestroy(ev_fork2);
@@ -233,22 +234,23 @@ int b200rec_model_s::mlp_backward(int B, const float* x_in, const float* mats, f
   float* g = gA.as<float>();
   float* g2 = gB.as<float>();
   const int L = (int)mlp.dims.size();
-  int max_out = 1;
-  for (int d : mlp.dims) max_out = d > max_out ? d : max_out;
-  B200_TRY(scratch_aux.reserve((size_t)COLSUM_CHUNKS * max_out * sizeof(float)));
   for (int l = L - 1; l >= 0; --l) {
     const int out = mlp.dims[l];
     const int in = l == 0 ? mlp.in_dim : mlp.dims[l - 1];
     const float* xp = l == 0 ? x_in : acts[l - 1].as<float>();
-    // bias gradient (column sums of g) on the auxiliary stream, beside the two GEMMs of the layer
+    // parameter gradients (weight GEMM + split-K reduce + bias column sums) on the auxiliary stream:
+    // only the gradInput GEMMs are on the chain to the embedding gradients
     B200_CUDA(cudaEventRecord(ev_aux_fork, st));
     B200_CUDA(cudaStreamWaitEvent(aux, ev_aux_fork, 0));
     aux_open = true;
-    B200_TRY(colsum(B, out, g, 1.0f, false, gm + mlp.b_off[l], scratch_aux.as<float>(), aux));
+    {
+      PackScope aux_pack(&wpack_aux);   // the main stream's GEMMs pack into wpack meanwhile
+      B200_TRY(linear_bwd_params(B, out, in, xp, g, 1.0f, false, gm + mlp.w_off[l], gm + mlp.b_off[l],
+                                 scratch_aux, aux, gemm_mode));
+    }
     B200_CUDA(cudaEventRecord(ev_aux_cs[l & 1], aux));
-    B200_TRY(linear_bwd_params(B, out, in, xp, g, 1.0f, false, gm + mlp.w_off[l], nullptr, scratch, st, gemm_mode));
     if (l > 0) {
-      // g2 held the gradient of layer l + 1: its column sums must have been read
+      // g2 held the gradient of layer l + 1: its parameter gradients must have been computed
       if (l + 1 < L) B200_CUDA(cudaStreamWaitEvent(st, ev_aux_cs[(l + 1) & 1], 0));
       B200_TRY(linear_bwd_input(B, out, in, g, mats + mlp.w_off[l], acts[l - 1].as<float>(), g2, false, st, gemm_mode));
       float* t = g; g = g2; g2 = t;

@@ -67,7 +67,7 @@ struct b200rec_model_s {
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_aux_fork = nullptr, ev_aux_pack = nullptr, ev_aux_join = nullptr, ev_aux_cs[2] = {nullptr, nullptr};
   bool aux_pack_pending = false, aux_open = false;
-  b200rec::DevBuf scratch_aux;
+  b200rec::DevBuf scratch_aux, wpack_aux;
   float* h_scal = nullptr;  // pinned 16 words: loss, dbias, n_unique, -, err, sorted
   bool params_set = false;
   // CUDA graph of the resident step (one per (B, table, gemm_mode)); captured after one eager warm-up
