@@ -125,6 +125,34 @@ class ParRecModel:
                                         L.ptr(preds)))
         return preds
 
+    # ---- checkpoint (the reference has no format of its own: ParRecModel.scala:66-123
+    # only initialises) ------------------------------------------------------------------------------
+    def save(self, path, chunk_rows=1 << 20):
+        """bias, mats and the table (embedding + first-order weights) to one .npz, read from the GPU in
+        row chunks.  Optimizer slots are not saved."""
+        bias, mats = self.getParams()
+        t = self.table
+        emb = np.empty((t.rows, t.dim), np.float32)
+        w = np.empty(t.rows, np.float32)
+        for r0 in range(0, t.rows, chunk_rows):
+            n = min(chunk_rows, t.rows - r0)
+            emb[r0:r0 + n], w[r0:r0 + n] = t.read(r0, n)
+        np.savez(path, bias=bias, mats=mats, embedding=emb, weights=w,
+                 meta=np.array([t.rows, t.dim, self.model.matsLen()], np.int64))
+
+    def load(self, path, chunk_rows=1 << 20):
+        z = np.load(path)
+        rows, dim, mats_len = (int(v) for v in z["meta"])
+        t = self.table
+        if (rows, dim, mats_len) != (t.rows, t.dim, self.model.matsLen()):
+            raise ValueError(f"checkpoint is for rows={rows} dim={dim} mats={mats_len}, "
+                             f"this model has rows={t.rows} dim={t.dim} mats={self.model.matsLen()}")
+        self.setParams(z["bias"], z["mats"] if mats_len else None)
+        emb, w = z["embedding"], z["weights"]
+        for r0 in range(0, rows, chunk_rows):
+            n = min(chunk_rows, rows - r0)
+            t.write(r0, emb[r0:r0 + n] if dim else None, w[r0:r0 + n])
+
     # ---- optimizer step: rec/optim/OptimUtils.scala:5-12 + Async*.scala defaults -------------------
     _DEFAULTS = {"sgd": (0.0, 0.0), "momentum": (0.9, 0.0), "adagrad": (0.9, 0.0), "adam": (0.99, 0.9)}
 

@@ -90,3 +90,31 @@ def test_training_reduces_loss_and_auc_matches_oracle(gpu_pkg):
     assert abs(a - refport.auc(targets, preds)) < 1e-12
     assert a > 0.6, a
     model.close(); table.close()
+
+
+def test_checkpoint_round_trip(gpu_pkg, tmp_path):
+    """save -> fresh model + table -> load gives bit-identical predictions."""
+    synth = gpu_pkg.synth
+    F, K, rows, B = 39, 16, 39 * 64, 64
+    fc = [32, 16]
+    def fresh():
+        m = gpu_pkg.make_model("deepfm", F, K, fc)
+        t = gpu_pkg.EmbeddingTable(rows, K)
+        return gpu_pkg.ParRecModel(m, t)
+    ps = fresh()
+    ps.table.init_uniform(42, -0.3, 0.3)
+    ps.setParams(np.array([0.1], np.float32), synth.init_mats(7, ps.model.getMatsSize()))
+    _, feats = synth.make_feats(5, 1, B, F, rows)
+    targets = synth.make_targets(5, feats, B, F)
+    ps.optimize(feats, targets)
+    ps.applyOptimizer("adam", 0.01)          # move every kind of parameter off its initial value
+    want = ps.predict(feats, B)
+    path = str(tmp_path / "ckpt.npz")
+    ps.save(path, chunk_rows=1000)           # several chunks
+    ps2 = fresh()
+    ps2.load(path, chunk_rows=700)
+    got = ps2.predict(feats, B)
+    assert np.array_equal(got, want)
+    bad = gpu_pkg.ParRecModel(gpu_pkg.make_model("deepfm", F, K, [8]), gpu_pkg.EmbeddingTable(rows, K))
+    with pytest.raises(ValueError):
+        bad.load(path)
