@@ -81,6 +81,9 @@ int b200rec_launch_count(int64_t* count);
  * "phase|kernel|launches|total_ms\n" into buf (truncated to cap; *needed = full size). */
 int b200rec_profile_begin(void);
 int b200rec_profile_end(char* buf, int64_t cap, int64_t* needed);
+/* Median elapsed time (microseconds) of an event pair around an EMPTY kernel on `device`: what the
+ * per-launch event bracketing of a profile pass adds to each kernel's time. */
+int b200rec_profile_overhead_us(int device, float* us);
 
 /* ---- model: Internal<M>Model (constructor args are the reference's) -------------------- */
 /* DeepFM.scala:51-53, XDeepFM.scala:58-61, DCN.scala:62-65, PNN.scala:56-58.
@@ -184,6 +187,14 @@ int b200rec_step_dev(b200rec_model_t m, b200rec_table_t t, int batch_size,
 /* The training step replays as a CUDA graph after one eager warm-up per (batch size, table); 0 turns
  * that off (plain stream launches). */
 int b200rec_model_set_graph(b200rec_model_t m, int enabled);
+/* b200rec_step with input prefetch: _stage_batch copies a batch's ids and labels (pinned host memory,
+ * or the copy does not overlap; the arrays must stay valid until the matching _step_staged returns)
+ * to the device on a copy stream and returns at once; _step_staged runs the step on the batch staged
+ * first and returns its loss.  Staging batch i+1 before stepping batch i hides the host->device copy
+ * under the step.  At most two batches are staged (B200REC_ERR_STATE otherwise, or when none is). */
+int b200rec_stage_batch(b200rec_model_t m, int batch_size, const int* feats, const float* targets);
+int b200rec_step_staged(b200rec_model_t m, b200rec_table_t t, float* loss);
+
 /* Predict: preds[B] = sigmoid(logit) (ParRecModel.predict :519-533). */
 int b200rec_predict(b200rec_model_t m, b200rec_table_t t, int batch_size,
                     const int* feats, float* preds);

@@ -30,6 +30,7 @@ SIGNATURES = {
     "b200rec_launch_count": [c_i64_p],
     "b200rec_profile_begin": [],
     "b200rec_profile_end": [C.c_char_p, C.c_int64, c_i64_p],
+    "b200rec_profile_overhead_us": [C.c_int, c_float_p],
     "b200rec_model_create": [C.c_int, C.c_int, C.c_int, c_int_p, C.c_int, c_int_p, C.c_int, C.c_int,
                              C.c_int, C.POINTER(vp)],
     "b200rec_model_destroy": [vp],
@@ -75,6 +76,8 @@ SIGNATURES = {
     "b200rec_model_side_stream": [vp, C.c_int, C.POINTER(vp)],
     "b200rec_side_fork_dev": [vp, C.c_int, vp],
     "b200rec_side_rejoin_dev": [vp, C.c_int],
+    "b200rec_stage_batch": [vp, C.c_int, vp, vp],
+    "b200rec_step_staged": [vp, vp, C.POINTER(C.c_float)],
     "b200rec_capture_begin": [vp, vp],
     "b200rec_capture_end": [vp, C.POINTER(C.c_int), vp],
     "b200rec_graph_launch": [vp, C.c_int, vp],
@@ -190,6 +193,13 @@ def profile_end():
         tag, name, cnt, ms = line.split("|")
         rows.append((tag, name, int(cnt), float(ms)))
     return rows
+
+
+def profile_overhead_us(device=0) -> float:
+    """What the event pair of a profile pass adds to each bracketed kernel (microseconds)."""
+    us = C.c_float(0)
+    check(lib().b200rec_profile_overhead_us(device, C.byref(us)))
+    return float(us.value)
 
 
 def set_default_gemm_mode(mode: int):

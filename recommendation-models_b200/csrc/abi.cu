@@ -5,6 +5,7 @@
 // Error convention: the reference raises IllegalArgumentException from Scala
 // `require`s (nn/Scatter.scala:29-30,52-53; nn/DuplicateTable.scala:61-62); here every entry point
 // returns a negative status and b200rec_last_error() carries the message.  Nothing throws.
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -32,6 +33,18 @@ thread_local Prof* tl_prof = nullptr;
 thread_local const char* tl_tag = nullptr;
 thread_local DevBuf* tl_pack = nullptr;
 thread_local PrePack* tl_prepack = nullptr;
+
+// Under the per-kernel profiler a step starts with this spin: the host gets ~0.5 ms ahead, the step's
+// launches queue up behind it, and the event pairs then time kernels that run back to back instead
+// of host launch gaps.
+__global__ void prof_delay_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(1000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
 
 void Prof::begin(const char* name, cudaStream_t st) {
   if (n >= kMax) return;
@@ -165,6 +178,41 @@ int b200rec_profile_begin(void) {
   prof.n = 0;
   tl_prof = &prof;
   return B200REC_OK;
+}
+
+__global__ void prof_empty_kernel() {}
+
+// What an event pair adds to the kernel it brackets: the median elapsed time of 64 bracketed empty
+// kernels queued behind a spin (so that no host launch gap is in it).  A profile_begin/_end pass
+// reports raw event times; a caller comparing them with durations (ncu gpu__time_duration, or a
+// graph replay) subtracts this per launch.
+int b200rec_profile_overhead_us(int device, float* us) {
+  B200_GUARD_BEGIN
+  B200_REQUIRE(us, B200REC_ERR_ARG, "NULL argument");
+  B200_TRY(use_device(device));
+  constexpr int N = 64;
+  cudaStream_t st;
+  B200_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaEvent_t a[N], b[N];
+  for (int i = 0; i < N; ++i) { cudaEventCreate(&a[i]); cudaEventCreate(&b[i]); }
+  prof_delay_kernel<<<1, 1, 0, st>>>(500000ull);
+  for (int i = 0; i < N; ++i) {
+    cudaEventRecord(a[i], st);
+    prof_empty_kernel<<<1, 32, 0, st>>>();
+    cudaEventRecord(b[i], st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  std::vector<float> ms(N, 0.f);
+  for (int i = 0; i < N; ++i) {
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms[i], a[i], b[i]);
+    cudaEventDestroy(a[i]); cudaEventDestroy(b[i]);
+  }
+  cudaStreamDestroy(st);
+  B200_CUDA(e);
+  std::sort(ms.begin(), ms.end());
+  *us = ms[N / 2] * 1000.f;
+  return B200REC_OK;
+  B200_GUARD_END
 }
 
 int b200rec_profile_end(char* buf, int64_t cap, int64_t* needed) {
@@ -722,6 +770,7 @@ static int step_train_graphed(Model* m, Table* t, int B, const int* feats, const
     B200_CUDA(cudaMemcpyAsync(m->d_targets.p, targets, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const int* f = m->d_feats.as<int>();
   const float* tg = m->d_targets.as<float>();
+  if (tl_prof) prof_delay_kernel<<<1, 1, 0, st>>>(500000ull);
   if (!m->graph_enabled || tl_prof) return step_on_device(m, t, B, f, tg, nullptr, st);
   const bool match = m->graph_exec && m->graph_B == B && m->graph_table == (const void*)t &&
                      m->graph_mode == m->gemm_mode;
@@ -785,6 +834,48 @@ int b200rec_step(b200rec_model_t m, b200rec_table_t t, int batch_size, const int
   B200_TRY(upload(m->d_feats, feats, (size_t)nnz * sizeof(int), st));
   B200_TRY(upload(m->d_targets, targets, (size_t)batch_size * sizeof(float), st));
   B200_TRY(step_train_graphed(m, t, batch_size, m->d_feats.as<int>(), m->d_targets.as<float>(), st));
+  B200_TRY(download(m->h_scal, m->scal.p, 8 * sizeof(float), st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  B200_TRY(dev_status(((int*)m->h_scal)[4], batch_size, t->rows));
+  if (loss) *loss = m->h_scal[0];
+  return B200REC_OK;
+  B200_GUARD_END
+}
+
+// ---- host-facing step with input prefetch ---------------------------------------------------------------
+int b200rec_stage_batch(b200rec_model_t m, int batch_size, const int* feats, const float* targets) {
+  B200_GUARD_BEGIN
+  B200_REQUIRE(m && feats && targets && batch_size > 0, B200REC_ERR_ARG, "bad argument");
+  B200_REQUIRE(m->stage_count < 2, B200REC_ERR_STATE, "two batches are staged already: call b200rec_step_staged");
+  B200_TRY(use_device(m->device));
+  const int slot = (m->stage_head + m->stage_count) & 1;
+  const long long nnz = (long long)batch_size * m->F;
+  // the slot's previous batch must have been consumed by the step that used it
+  if (m->stage_used[slot]) B200_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_consumed[slot], 0));
+  B200_TRY(upload(m->stage_f[slot], feats, (size_t)nnz * sizeof(int), m->copy_stream));
+  B200_TRY(upload(m->stage_t[slot], targets, (size_t)batch_size * sizeof(float), m->copy_stream));
+  B200_CUDA(cudaEventRecord(m->ev_staged[slot], m->copy_stream));
+  m->stage_B[slot] = batch_size;
+  ++m->stage_count;
+  return B200REC_OK;
+  B200_GUARD_END
+}
+
+int b200rec_step_staged(b200rec_model_t m, b200rec_table_t t, float* loss) {
+  B200_GUARD_BEGIN
+  B200_REQUIRE(m && t, B200REC_ERR_ARG, "NULL argument");
+  B200_REQUIRE(m->stage_count > 0, B200REC_ERR_STATE, "no staged batch: call b200rec_stage_batch first");
+  const int slot = m->stage_head;
+  const int batch_size = m->stage_B[slot];
+  B200_TRY(check_step_args(m, t, batch_size));
+  B200_TRY(use_device(m->device));
+  cudaStream_t st = m->stream;
+  B200_CUDA(cudaStreamWaitEvent(st, m->ev_staged[slot], 0));
+  m->stage_head ^= 1;
+  --m->stage_count;
+  B200_TRY(step_train_graphed(m, t, batch_size, m->stage_f[slot].as<int>(), m->stage_t[slot].as<float>(), st));
+  B200_CUDA(cudaEventRecord(m->ev_consumed[slot], st));
+  m->stage_used[slot] = true;
   B200_TRY(download(m->h_scal, m->scal.p, 8 * sizeof(float), st));
   B200_CUDA(cudaStreamSynchronize(st));
   B200_TRY(dev_status(((int*)m->h_scal)[4], batch_size, t->rows));

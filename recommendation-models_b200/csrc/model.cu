@@ -113,6 +113,9 @@ int b200rec_model_s::init(int kind_, int F_, int K_, const int* fc_, int n_fc, c
   B200_CUDA(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&side3, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&ev_staged[0], &ev_staged[1], &ev_consumed[0], &ev_consumed[1]})
+    B200_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   for (cudaEvent_t* e : {&ev_aux_fork, &ev_aux_pack, &ev_aux_join, &ev_aux_cs[0], &ev_aux_cs[1]})
     B200_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&ev_fork3, cudaEventDisableTiming));
@@ -137,6 +140,7 @@ void b200rec_model_s::destroy() {
   if (side2) cudaStreamSynchronize(side2);
   if (side3) cudaStreamSynchronize(side3);
   if (aux) cudaStreamSynchronize(aux);
+  if (copy_stream) cudaStreamSynchronize(copy_stream);
   DevBuf* bufs[] = {&p_bias, &p_mats, &gmats, &scal, &d_feats, &d_targets, &d_index, &X, &wnz, &S,
                     &first, &second, &branch, &preds, &dlogit, &dXd, &dw, &gA, &gB, &scratch,
                     &uniq, &G, &gwU, &wpack, &wpack_mlp, &s1m, &s2m, &p2p_ctr, &x0, &gx0, &gy, &gnA, &gnB, &pooled, &gpooled, &xL, &s_cross,
@@ -159,6 +163,10 @@ void b200rec_model_s::destroy() {
   if (side2) cudaStreamDestroy(side2);
   if (side3) cudaStreamDestroy(side3);
   if (aux) cudaStreamDestroy(aux);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  for (cudaEvent_t e : {ev_staged[0], ev_staged[1], ev_consumed[0], ev_consumed[1]})
+    if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) { stage_f[i].release(); stage_t[i].release(); }
   for (cudaEvent_t e : {ev_aux_fork, ev_aux_pack, ev_aux_join, ev_aux_cs[0], ev_aux_cs[1]})
     if (e) cudaEventDestroy(e);
   scratch_aux.release();
@@ -239,16 +247,20 @@ int b200rec_model_s::mlp_backward(int B, const float* x_in, const float* mats, f
     const int in = l == 0 ? mlp.in_dim : mlp.dims[l - 1];
     const float* xp = l == 0 ? x_in : acts[l - 1].as<float>();
     // parameter gradients (weight GEMM + split-K reduce + bias column sums) on the auxiliary stream:
-    // only the gradInput GEMMs are on the chain to the embedding gradients
-    B200_CUDA(cudaEventRecord(ev_aux_fork, st));
-    B200_CUDA(cudaStreamWaitEvent(aux, ev_aux_fork, 0));
-    aux_open = true;
+    // only the gradInput GEMMs are on the chain to the embedding gradients.  (Under the per-kernel
+    // profiler everything stays on one stream so that every kernel is timed alone.)
+    cudaStream_t ax = tl_prof ? st : aux;
+    if (ax != st) {
+      B200_CUDA(cudaEventRecord(ev_aux_fork, st));
+      B200_CUDA(cudaStreamWaitEvent(aux, ev_aux_fork, 0));
+      aux_open = true;
+    }
     {
       PackScope aux_pack(&wpack_aux);   // the main stream's GEMMs pack into wpack meanwhile
       B200_TRY(linear_bwd_params(B, out, in, xp, g, 1.0f, false, gm + mlp.w_off[l], gm + mlp.b_off[l],
-                                 scratch_aux, aux, gemm_mode));
+                                 scratch_aux, ax, gemm_mode));
     }
-    B200_CUDA(cudaEventRecord(ev_aux_cs[l & 1], aux));
+    B200_CUDA(cudaEventRecord(ev_aux_cs[l & 1], ax));
     if (l > 0) {
       // g2 held the gradient of layer l + 1: its parameter gradients must have been computed
       if (l + 1 < L) B200_CUDA(cudaStreamWaitEvent(st, ev_aux_cs[(l + 1) & 1], 0));
@@ -352,7 +364,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
     // every Linear weight of the tower, in the forward and (training) the gradInput stage layout, in
     // two launches instead of one per GEMM
     cudaStream_t st_dx = st;
-    if (train) {   // the gradInput images are first needed in the backward: pack them beside the forward
+    if (train && !tl_prof) {   // the gradInput images are first needed in the backward: pack them beside the forward
       B200_CUDA(cudaEventRecord(ev_aux_fork, st));
       B200_CUDA(cudaStreamWaitEvent(aux, ev_aux_fork, 0));
       st_dx = aux;
@@ -360,7 +372,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
     }
     B200_TRY(tc_prepack_linear(prepack, mats, mlp.in_dim, mlp.dims.data(), (int)mlp.dims.size(),
                                mlp.w_off.data(), train, st, st_dx));
-    if (train) {
+    if (st_dx != st) {
       B200_CUDA(cudaEventRecord(ev_aux_pack, aux));
       aux_pack_pending = true;
     }

@@ -68,6 +68,13 @@ struct b200rec_model_s {
   cudaEvent_t ev_aux_fork = nullptr, ev_aux_pack = nullptr, ev_aux_join = nullptr, ev_aux_cs[2] = {nullptr, nullptr};
   bool aux_pack_pending = false, aux_open = false;
   b200rec::DevBuf scratch_aux, wpack_aux;
+  // input prefetch of the host-facing step (b200rec_stage_batch / b200rec_step_staged): two staged
+  // batches at most, copied on their own stream while the previous step computes
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  b200rec::DevBuf stage_f[2], stage_t[2];
+  int stage_B[2] = {0, 0}, stage_head = 0, stage_count = 0;
+  bool stage_used[2] = {false, false};
   float* h_scal = nullptr;  // pinned 16 words: loss, dbias, n_unique, -, err, sorted
   bool params_set = false;
   // CUDA graph of the resident step (one per (B, table, gemm_mode)); captured after one eager warm-up

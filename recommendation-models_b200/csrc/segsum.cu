@@ -21,7 +21,7 @@
 
 namespace b200rec {
 
-static constexpr int LONG_T = 32;
+static constexpr int LONG_T = 32;   // (8 was measured slower: 3 000 one-warp segments instead of 700)
 
 int SegSumWorkspace::reserve(long long n) {
   if (n <= cap_n) return B200REC_OK;
@@ -259,6 +259,7 @@ __device__ __forceinline__ void segsum_long_role(int block, int n_blocks, const 
       // fold the RPW*UNR rows into the accumulator strictly in order (all lanes keep a copy)
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
+        if (base + u * RPW >= len) break;   // warp-uniform: nothing left in this batch
 #pragma unroll
         for (int s = 0; s < RPW; ++s) {
           const int src = s * LPR + sub;

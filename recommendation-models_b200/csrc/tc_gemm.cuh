@@ -511,6 +511,10 @@ struct CinZtProd {
 };
 
 // ---- epilogues: ep(m, n0, v[16], nv, z) for one accumulator row chunk ------------------------------
+// An epilogue with load_aux / apply has its global inputs fetched one chunk ahead by the kernel.
+template <class T, class = void> struct has_aux : std::false_type {};
+template <class T>
+struct has_aux<T, std::void_t<decltype(&T::load_aux)>> : std::true_type {};
 struct EpBiasAct {  // y = act(acc + bias[n])
   float* y; long long ld; const float* bias; bool relu;
   static constexpr bool kRowReduce = false;
@@ -545,17 +549,29 @@ struct EpBiasAct {  // y = act(acc + bias[n])
 struct EpMaskAcc {  // g = acc * (mask > 0) (+ g)
   float* g; long long ld; const float* mask; long long ldm; bool accumulate;
   static constexpr bool kRowReduce = false;
-  __device__ __forceinline__ void operator()(int m, int n0, float* v, int nv, int) const {
+  // the mask chunk of a row is loaded one chunk ahead of its use (aux), so that its latency hides
+  // under the TMEM load / stores of the previous chunk instead of serialising the epilogue
+  __device__ __forceinline__ bool vec_ok(int m, int n0, int nv) const {
+    const float* dst = g + (long long)m * ld + n0;
+    const float* mk = mask ? mask + (long long)m * ldm + n0 : nullptr;
+    return nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+           (!mk || (reinterpret_cast<uintptr_t>(mk) & 15) == 0);
+  }
+  __device__ __forceinline__ void load_aux(int m, int n0, int nv, float4* aux) const {
+    if (!mask || !vec_ok(m, n0, nv)) return;
+    const float* mk = mask + (long long)m * ldm + n0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) aux[q] = __ldg(reinterpret_cast<const float4*>(mk + 4 * q));
+  }
+  __device__ __forceinline__ void apply(int m, int n0, float* v, int nv, int, const float4* aux) const {
     float* dst = g + (long long)m * ld + n0;
     const float* mk = mask ? mask + (long long)m * ldm + n0 : nullptr;
-    const bool vec = nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                     (!mk || (reinterpret_cast<uintptr_t>(mk) & 15) == 0);
-    if (vec) {  // a thread owns 64 contiguous bytes of its row: 128-bit accesses
+    if (vec_ok(m, n0, nv)) {  // a thread owns 64 contiguous bytes of its row: 128-bit accesses
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         if (mk) {
-          const float4 k = __ldg(reinterpret_cast<const float4*>(mk + 4 * q));
+          const float4 k = aux[q];
           if (!(k.x > 0.f)) o.x = 0.f;
           if (!(k.y > 0.f)) o.y = 0.f;
           if (!(k.z > 0.f)) o.z = 0.f;
@@ -578,6 +594,11 @@ struct EpMaskAcc {  // g = acc * (mask > 0) (+ g)
         dst[i] = t;
       }
     }
+  }
+  __device__ __forceinline__ void operator()(int m, int n0, float* v, int nv, int z) const {
+    float4 aux[4];
+    load_aux(m, n0, nv, aux);
+    apply(m, n0, v, nv, z, aux);
   }
 };
 struct EpPartial {  // split-K partial: ws[z][m][n]
@@ -926,12 +947,17 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
     // ---- epilogue: thread = accumulator row (TMEM lane), 16 columns per tcgen05.ld ----------------
     if (nkb > 0) {
       if (tid == 0) TC_TRACE(2, 511, 0);
+      const int row = m0 + (warp & 3) * 32 + lane;
+      const int ncols = min(n_valid, N - n0);
+      [[maybe_unused]] float4 aux[4], aux_next[4];
+      if constexpr (has_aux<Ep>::value) {   // first chunk's global inputs: in flight while the last MMAs drain
+        if (row < M && (pw >> 2) * 16 < ncols)
+          ep.load_aux(row, n0 + (pw >> 2) * 16, min(16, ncols - (pw >> 2) * 16), aux);
+      }
       mbar_wait(bar_empty + 8 * ((nkb - 1) & 1), ((nkb - 1) >> 1) & 1);
       if (tid == 0) TC_TRACE(2, 511, 1);
       tc_fence_after();
       const bool add_s = kc > 0 && nkb > kc;   // result = S + P (the last chunk is still in P)
-      const int row = m0 + (warp & 3) * 32 + lane;
-      const int ncols = min(n_valid, N - n0);
       float v[16];
       if constexpr (Ep::kRowReduce) {
         // x tile -> shared memory (the B ring is free now), then thread = row dots; the two column
@@ -956,6 +982,27 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
         if (pw < 4 && row < M) ep.finish(row, blockIdx.x, acc + red[(warp & 3) * 32 + lane]);
       } else {
+        if constexpr (has_aux<Ep>::value) {
+          for (int ch = pw >> 2; ch * 16 < ncols; ch += 2) {
+            uint32_t pr[16], sr[16];
+            tmem_ld16_nowait(tmem + lane_addr + ch * 16, pr);
+            if (add_s) tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, sr);
+            if (row < M && (ch + 2) * 16 < ncols)
+              ep.load_aux(row, n0 + (ch + 2) * 16, min(16, ncols - (ch + 2) * 16), aux_next);
+            if (add_s) {
+              tmem_wait_ld2(pr, sr);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(pr[i]) + __uint_as_float(sr[i]);
+            } else {
+              tmem_wait_ld1(pr);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(pr[i]);
+            }
+            if (row < M) ep.apply(row, n0 + ch * 16, v, min(16, ncols - ch * 16), blockIdx.z, aux);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) aux[q] = aux_next[q];
+          }
+        } else {
         for (int ch = pw >> 2; ch * 16 < ncols; ch += 2) {
           uint32_t pr[16], sr[16];
           tmem_ld16_nowait(tmem + lane_addr + ch * 16, pr);          // P and S in one TMEM round trip
@@ -970,6 +1017,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(pr[i]);
           }
           if (row < M) ep(row, n0 + ch * 16, v, min(16, ncols - ch * 16), blockIdx.z);
+        }
         }
       }
     }

@@ -118,6 +118,22 @@ class ParRecModel:
                                      L.ptr(targets), C.byref(loss)))
         return float(loss.value) * B
 
+    def stage(self, feats, targets):
+        """Input prefetch: start copying a batch to the GPU (pinned int32 / float32 arrays overlap with
+        the running step; they must stay alive until the matching optimizeStaged returns)."""
+        feats, targets = L.i32(feats), L.f32(targets)
+        L.check(L.lib().b200rec_stage_batch(self.model.handle, targets.shape[0], L.ptr(feats), L.ptr(targets)))
+        self._staged = getattr(self, "_staged", [])
+        self._staged.append((feats, targets))
+
+    def optimizeStaged(self):
+        """optimize() on the batch staged first -> loss * batchSize."""
+        loss = C.c_float(0)
+        L.check(L.lib().b200rec_step_staged(self.model.handle, self.table.handle, C.byref(loss)))
+        feats, targets = self._staged.pop(0)
+        self._last_nnz = feats.shape[0]
+        return float(loss.value) * targets.shape[0]
+
     def predict(self, feats, batchSize):
         feats = L.i32(feats)
         preds = np.zeros(batchSize, np.float32)

@@ -118,3 +118,43 @@ def test_checkpoint_round_trip(gpu_pkg, tmp_path):
     bad = gpu_pkg.ParRecModel(gpu_pkg.make_model("deepfm", F, K, [8]), gpu_pkg.EmbeddingTable(rows, K))
     with pytest.raises(ValueError):
         bad.load(path)
+
+
+def test_staged_step_equals_host_step(gpu_pkg):
+    """b200rec_stage_batch + b200rec_step_staged (input prefetch) give the losses and gradients of
+    b200rec_step on the same batches; the staging depth and order are enforced."""
+    synth = gpu_pkg.synth
+    F, K, rows, B = 39, 16, 39 * 64, 128
+    fc = [32, 16]
+    def fresh():
+        m = gpu_pkg.make_model("deepfm", F, K, fc)
+        t = gpu_pkg.EmbeddingTable(rows, K)
+        t.init_uniform(42, -0.3, 0.3)
+        ps = gpu_pkg.ParRecModel(m, t)
+        ps.setParams(np.array([0.1], np.float32), synth.init_mats(7, m.getMatsSize()))
+        return ps
+    batches = []
+    for s_ in range(5):
+        _, f = synth.make_feats(5, s_, B, F, rows)
+        batches.append((f, synth.make_targets(5, f, B, F)))
+    a, b = fresh(), fresh()
+    want = []
+    for f, t in batches:
+        want.append(a.optimize(f, t))
+        a.applyOptimizer("sgd", 0.05)
+    with pytest.raises(RuntimeError):
+        b.optimizeStaged()                       # nothing staged
+    got = []
+    b.stage(*batches[0])
+    for i in range(len(batches)):
+        if i + 1 < len(batches):
+            b.stage(*batches[i + 1])             # copy of the next batch under this step
+        got.append(b.optimizeStaged())
+        b.applyOptimizer("sgd", 0.05)
+    assert got == want
+    ra, rb = a.stepResults(), b.stepResults()
+    assert np.array_equal(ra["unique"], rb["unique"]) and np.array_equal(ra["emb_grad"], rb["emb_grad"])
+    assert np.array_equal(ra["mats_grad"], rb["mats_grad"])
+    b.stage(*batches[0]); b.stage(*batches[1])
+    with pytest.raises(RuntimeError):
+        b.stage(*batches[2])                     # two staged already
