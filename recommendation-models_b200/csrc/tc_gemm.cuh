@@ -788,8 +788,14 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
   const uint32_t bar_full = smem_u32(&bars[0]);    // +8*st
   const uint32_t bar_empty = smem_u32(&bars[2]);   // +8*st
   const uint32_t bar_bfull = smem_u32(&bars[4]);   // +8*sb
-  const uint32_t bar_drained = smem_u32(&bars[7]);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t bar_drained = smem_u32(&bars[7]);    // second column half of a chunk drained into S
+  const uint32_t bar_half = smem_u32(&bars[8]);       // first column half of a chunk's last stage computed
+  const uint32_t bar_drained0 = smem_u32(&bars[9]);   // first column half drained into S
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  // Accumulation-chunk boundaries are pipelined by column halves [0, h0) / [h0, bn): the chunk's last
+  // stage and the next chunk's first stage issue their MMAs half by half, so that the drain of one
+  // half (P -> S, CUDA cores) runs under the tensor work of the other instead of idling the pipe.
+  const int h0 = ((bn / 16 + 1) / 2) * 16, h1 = bn - h0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM;
   const int n0 = blockIdx.x * n_stride;
@@ -801,6 +807,8 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
     mbar_init(bar_empty, 1); mbar_init(bar_empty + 8, 1);
     mbar_init(bar_bfull, 1); mbar_init(bar_bfull + 8, 1); mbar_init(bar_bfull + 16, 1);
     mbar_init(bar_drained, THREADS);
+    mbar_init(bar_half, 1);
+    mbar_init(bar_drained0, THREADS);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -816,13 +824,14 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     if (leader) {
-      const uint32_t idesc = make_idesc(bn);
+      const uint32_t idesc = make_idesc(bn), idesc0 = make_idesc(h0), idesc1 = make_idesc(h1 > 0 ? h1 : 16);
       int sb = 0, bphase = 0, cpos = 0, cidx = 0;   // B ring slot / its phase, position in / index of the chunk
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb & 1;
         const bool chunk_start = kc > 0 ? (cpos == 0) : (kb == 0);
+        const bool opens = kc > 0 && chunk_start && kb > 0;            // first stage after a boundary
+        const bool closes = kc > 0 && cpos == kc - 1 && kb + 1 < nkb;   // last stage before a boundary
         TC_TRACE(0, kb, 0);
-        if (kc > 0 && chunk_start && kb > 0) mbar_wait(bar_drained, (cidx - 1) & 1);
         mbar_wait(bar_full + 8 * st, (kb >> 1) & 1);
         TC_TRACE(0, kb, 1);
         if (PACKED) mbar_wait(bar_bfull + 8 * sb, bphase);
@@ -833,12 +842,44 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         const uint64_t dah = make_desc(smem_u32(a_hi)), dal = make_desc(smem_u32(a_hi + A_TILE_BYTES));
         const uint64_t dbh = make_desc(smem_u32(b_hi)), dbl = make_desc(smem_u32(b_hi + bn * 128));
         const int ksteps = (s.kvalid(kb) + UK - 1) / UK;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4);
-          mma_tf32(tmem, dah + adv, dbh + adv, idesc, (!chunk_start || ks != 0) ? 1u : 0u);
-          if (PASSES == 3) {
-            mma_tf32(tmem, dal + adv, dbh + adv, idesc, 1u);
-            mma_tf32(tmem, dah + adv, dbl + adv, idesc, 1u);
+        if (opens || closes) {
+          const uint64_t boff = (uint64_t)(h0 * 128 >> 4);   // B rows [h0, bn) of the stage image
+          if (opens) {
+            mbar_wait(bar_drained0, (cidx - 1) & 1);
+            tc_fence_after();
+          }
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4);
+            mma_tf32(tmem, dah + adv, dbh + adv, idesc0, (!chunk_start || ks != 0) ? 1u : 0u);
+            if (PASSES == 3) {
+              mma_tf32(tmem, dal + adv, dbh + adv, idesc0, 1u);
+              mma_tf32(tmem, dah + adv, dbl + adv, idesc0, 1u);
+            }
+          }
+          if (closes) mma_commit(bar_half);
+          if (opens) {
+            mbar_wait(bar_drained, (cidx - 1) & 1);
+            tc_fence_after();
+          }
+          if (h1 > 0) {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4) + boff;
+              const uint64_t ada = (uint64_t)(ks * UK * 4 >> 4);
+              mma_tf32(tmem + h0, dah + ada, dbh + adv, idesc1, (!chunk_start || ks != 0) ? 1u : 0u);
+              if (PASSES == 3) {
+                mma_tf32(tmem + h0, dal + ada, dbh + adv, idesc1, 1u);
+                mma_tf32(tmem + h0, dah + ada, dbl + adv, idesc1, 1u);
+              }
+            }
+          }
+        } else {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4);
+            mma_tf32(tmem, dah + adv, dbh + adv, idesc, (!chunk_start || ks != 0) ? 1u : 0u);
+            if (PASSES == 3) {
+              mma_tf32(tmem, dal + adv, dbh + adv, idesc, 1u);
+              mma_tf32(tmem, dah + adv, dbl + adv, idesc, 1u);
+            }
           }
         }
         mma_commit(bar_empty + 8 * st);
@@ -896,46 +937,53 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
       if (tid == 0) TC_TRACE(1, kb, 3);
       if (kc > 0 && kb > 0 && pcpos == 0) {
         // Stage kb (just produced, so the MMA warp can start it the moment it is released) opens a new
-        // accumulation chunk; the previous one ended with stage kb-1.  Once its MMAs have drained:
-        // S (+)= P with round-to-nearest, then release the MMA warp.  All TMEM
-        // loads of a group of chunks are issued before the first wait (fewer TMEM round trips).
-        mbar_wait(bar_empty + 8 * (P ^ 1), ((kb - 1) >> 1) & 1);
-        tc_fence_after();
+        // accumulation chunk; the previous one ended with stage kb-1, whose MMAs ran as two column
+        // halves.  As each half completes: S (+)= P with round-to-nearest for its columns, then the
+        // MMA warp is released for that half.  All TMEM loads of a group of 16-column pieces are issued
+        // before the first wait (fewer TMEM round trips).
         const bool have_s = kb > kc;
         const int ch0 = pw >> 2;
-        constexpr int DG = PACKED ? 2 : 1;   // chunks per TMEM round trip (register budget)
+        const int bpar = (kb / kc - 1) & 1;        // boundary number: each barrier completes once per boundary
+        constexpr int DG = 1;   // pieces per TMEM round trip (the drain now hides under the other half: registers matter more)
 #pragma unroll 1
-        for (int grp = 0; grp < 8 / DG; ++grp) {
-          if ((ch0 + 2 * DG * grp) * 16 >= bn) break;
-          uint32_t p[DG][16], q[DG][16];
+        for (int half = 0; half < 2; ++half) {   // one copy of the drain code for both halves
+          if (half == 0) mbar_wait(bar_half, bpar);
+          else mbar_wait(bar_empty + 8 * (P ^ 1), ((kb - 1) >> 1) & 1);
+          tc_fence_after();
+          const int c_lo = half ? h0 / 16 : 0, c_hi = half ? bn / 16 : h0 / 16;
+          const int first = c_lo + ((c_lo & 1) != ch0 ? 1 : 0);   // this thread's parity of 16-column pieces
+#pragma unroll 1
+          for (int c = first; c < c_hi; c += 2 * DG) {
+            uint32_t p[DG][16], q[DG][16];
 #pragma unroll
-          for (int i = 0; i < DG; ++i) {
-            const int ch = ch0 + 2 * (grp * DG + i);
-            if (ch * 16 < bn) {
-              tmem_ld16_nowait(tmem + lane_addr + ch * 16, p[i]);
-              if (have_s) tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, q[i]);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < DG; ++i) {
-            const int ch = ch0 + 2 * (grp * DG + i);
-            if (ch * 16 < bn) {
-              if (have_s) {
-                tmem_wait_ld2(p[i], q[i]);
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                  p[i][e] = __float_as_uint(__uint_as_float(p[i][e]) + __uint_as_float(q[i][e]));
-              } else {
-                tmem_wait_ld1(p[i]);
+            for (int i = 0; i < DG; ++i) {
+              const int ch = c + 2 * i;
+              if (ch < c_hi) {
+                tmem_ld16_nowait(tmem + lane_addr + ch * 16, p[i]);
+                if (have_s) tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, q[i]);
               }
-              tmem_st16(tmem + lane_addr + TMEM_S + ch * 16, p[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < DG; ++i) {
+              const int ch = c + 2 * i;
+              if (ch < c_hi) {
+                if (have_s) {
+                  tmem_wait_ld2(p[i], q[i]);
+#pragma unroll
+                  for (int e = 0; e < 16; ++e)
+                    p[i][e] = __float_as_uint(__uint_as_float(p[i][e]) + __uint_as_float(q[i][e]));
+                } else {
+                  tmem_wait_ld1(p[i]);
+                }
+                tmem_st16(tmem + lane_addr + TMEM_S + ch * 16, p[i]);
+              }
             }
           }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(half ? bar_drained : bar_drained0);
+          if (tid == 0) TC_TRACE(2, kb, half ? 0 : 1);
         }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(bar_drained);
-        if (tid == 0) TC_TRACE(2, kb, 0);
       }
       if (kc > 0 && ++pcpos == kc) pcpos = 0;
     };

@@ -13,11 +13,12 @@ def dump(title, nkb):
     a = np.array(buf, dtype=np.int64).reshape(3, 512, 4)
     t0 = a[0, 0, 0]
     print("==", title, "nkb", nkb)
-    print(" kb | MMA: start  full  bfull  issued | PROD: start  waited  stored  arrived | drained")
+    print(" kb | MMA: start  full  bfull  issued | PROD: start  waited  stored  arrived | drained0 drained")
     for kb in range(min(nkb, 24)):
         m, p = a[0, kb] - t0, a[1, kb] - t0
         d = a[2, kb, 0] - t0 if a[2, kb, 0] else 0
-        print(f"{kb:3d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d} | {p[0]:7d} {p[1]:7d} {p[2]:7d} {p[3]:7d} | {d:7d}")
+        d0 = a[2, kb, 1] - t0 if a[2, kb, 1] else 0
+        print(f"{kb:3d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d} | {p[0]:7d} {p[1]:7d} {p[2]:7d} {p[3]:7d} | {d0:7d} {d:7d}")
     e = a[2, 511] - t0
     print(f" epilogue: producers done {e[0]}, last MMA drained {e[1]}, epilogue stored {e[2]}, CTA end {e[3]}")
     m = a[0, :nkb] - t0
