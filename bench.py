@@ -201,11 +201,14 @@ def run_b200(args):
         f, t = pin[i % nb]
         L.check(lib.b200rec_stage_batch(model.handle, B, f.data_ptr(), t.data_ptr()))
 
-    def step_host(i):
-        # batch i was staged during the previous step; start the copy of batch i + 1, then run batch i
-        # and read its loss: every step has one H2D of a batch and one D2H of the loss
+    def step_host(i, first=False):
+        # batch i was staged during the previous step: start the copy of batch i + 1, enqueue step i and
+        # its loss read-back, then wait for and read the loss of step i - 1.  Every step has one H2D of a
+        # batch and one D2H of a loss; the host reads each loss one step late, so the GPU never idles.
         stage_host(i + 1)
-        L.check(lib.b200rec_step_staged(model.handle, table.handle, C.byref(loss)))
+        L.check(lib.b200rec_step_staged_async(model.handle, table.handle))
+        if not first:
+            L.check(lib.b200rec_step_wait(model.handle, table.handle, C.byref(loss)))
         return loss.value
 
     # ---- device-resident timing ------------------------------------------------------------------
@@ -233,12 +236,15 @@ def run_b200(args):
     nw = min(W, 5)
     stage_host(0)
     for i in range(nw):
-        step_host(i)
+        step_host(i, first=(i == 0))
+    L.check(lib.b200rec_step_wait(model.handle, table.handle, C.byref(loss)))   # drain: nothing in flight
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     last = 0.0
     for i in range(Ksteps):
-        last = step_host(nw + i)
+        last = step_host(nw + i, first=(i == 0))
+    L.check(lib.b200rec_step_wait(model.handle, table.handle, C.byref(loss)))   # the last step's loss
+    last = loss.value
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
@@ -308,7 +314,7 @@ def run_b200(args):
                    "seed_params": SEED_PARAMS, "distinct_ids_last_step": U},
         "clocks": clk,
         "e2e": {"value": round(B * Ksteps / e2e_s, 1), "unit": "samples/s", "h2d_bytes_per_step": B * F * 4 + B * 4,
-                "d2h_bytes_per_step": 32, "call": "b200rec_stage_batch (next batch, pinned host ids + labels) + b200rec_step_staged (loss out)",
+                "d2h_bytes_per_step": 32, "call": "b200rec_stage_batch (next batch, pinned host ids + labels) + b200rec_step_staged_async + b200rec_step_wait (every loss read by the host, one step late)",
                 "last_loss": round(float(last), 6)},
         "gpu_launches": int(launches),
         "roofline": roofline,

@@ -194,6 +194,13 @@ int b200rec_model_set_graph(b200rec_model_t m, int enabled);
  * under the step.  At most two batches are staged (B200REC_ERR_STATE otherwise, or when none is). */
 int b200rec_stage_batch(b200rec_model_t m, int batch_size, const int* feats, const float* targets);
 int b200rec_step_staged(b200rec_model_t m, b200rec_table_t t, float* loss);
+/* The same without waiting: _step_staged_async enqueues the step on the batch staged first plus the
+ * read-back of its loss and returns; _step_wait blocks until the OLDEST enqueued step is done and
+ * returns its loss (and the device status: bad ids surface here).  Up to two steps may be in flight,
+ * so the loop "stage(i+1); step_staged_async(i); step_wait(i-1)" keeps the GPU busy while the host
+ * reads every step's loss one step late. */
+int b200rec_step_staged_async(b200rec_model_t m, b200rec_table_t t);
+int b200rec_step_wait(b200rec_model_t m, b200rec_table_t t, float* loss);
 
 /* Predict: preds[B] = sigmoid(logit) (ParRecModel.predict :519-533). */
 int b200rec_predict(b200rec_model_t m, b200rec_table_t t, int batch_size,

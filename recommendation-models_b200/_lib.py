@@ -78,6 +78,8 @@ SIGNATURES = {
     "b200rec_side_rejoin_dev": [vp, C.c_int],
     "b200rec_stage_batch": [vp, C.c_int, vp, vp],
     "b200rec_step_staged": [vp, vp, C.POINTER(C.c_float)],
+    "b200rec_step_staged_async": [vp, vp],
+    "b200rec_step_wait": [vp, vp, C.POINTER(C.c_float)],
     "b200rec_capture_begin": [vp, vp],
     "b200rec_capture_end": [vp, C.POINTER(C.c_int), vp],
     "b200rec_graph_launch": [vp, C.c_int, vp],

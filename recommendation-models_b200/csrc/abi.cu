@@ -861,10 +861,11 @@ int b200rec_stage_batch(b200rec_model_t m, int batch_size, const int* feats, con
   B200_GUARD_END
 }
 
-int b200rec_step_staged(b200rec_model_t m, b200rec_table_t t, float* loss) {
+int b200rec_step_staged_async(b200rec_model_t m, b200rec_table_t t) {
   B200_GUARD_BEGIN
   B200_REQUIRE(m && t, B200REC_ERR_ARG, "NULL argument");
   B200_REQUIRE(m->stage_count > 0, B200REC_ERR_STATE, "no staged batch: call b200rec_stage_batch first");
+  B200_REQUIRE(m->async_count < 2, B200REC_ERR_STATE, "two steps are in flight already: call b200rec_step_wait");
   const int slot = m->stage_head;
   const int batch_size = m->stage_B[slot];
   B200_TRY(check_step_args(m, t, batch_size));
@@ -876,12 +877,35 @@ int b200rec_step_staged(b200rec_model_t m, b200rec_table_t t, float* loss) {
   B200_TRY(step_train_graphed(m, t, batch_size, m->stage_f[slot].as<int>(), m->stage_t[slot].as<float>(), st));
   B200_CUDA(cudaEventRecord(m->ev_consumed[slot], st));
   m->stage_used[slot] = true;
-  B200_TRY(download(m->h_scal, m->scal.p, 8 * sizeof(float), st));
-  B200_CUDA(cudaStreamSynchronize(st));
-  B200_TRY(dev_status(((int*)m->h_scal)[4], batch_size, t->rows));
-  if (loss) *loss = m->h_scal[0];
+  const int a = (m->async_head + m->async_count) & 1;   // result slot: 8 floats of the pinned scalar block each
+  B200_TRY(download(m->h_scal + 8 * a, m->scal.p, 8 * sizeof(float), st));
+  B200_CUDA(cudaEventRecord(m->ev_done[a], st));
+  m->async_B[a] = batch_size;
+  ++m->async_count;
   return B200REC_OK;
   B200_GUARD_END
+}
+
+int b200rec_step_wait(b200rec_model_t m, b200rec_table_t t, float* loss) {
+  B200_GUARD_BEGIN
+  B200_REQUIRE(m && t, B200REC_ERR_ARG, "NULL argument");
+  B200_REQUIRE(m->async_count > 0, B200REC_ERR_STATE, "no step in flight");
+  B200_TRY(use_device(m->device));
+  const int a = m->async_head;
+  B200_CUDA(cudaEventSynchronize(m->ev_done[a]));
+  m->async_head ^= 1;
+  --m->async_count;
+  B200_TRY(dev_status(((int*)(m->h_scal + 8 * a))[4], m->async_B[a], t->rows));
+  if (loss) *loss = m->h_scal[8 * a];
+  return B200REC_OK;
+  B200_GUARD_END
+}
+
+int b200rec_step_staged(b200rec_model_t m, b200rec_table_t t, float* loss) {
+  B200_REQUIRE(m, B200REC_ERR_ARG, "NULL argument");
+  B200_REQUIRE(m->async_count == 0, B200REC_ERR_STATE, "asynchronous steps are in flight: call b200rec_step_wait");
+  B200_TRY(b200rec_step_staged_async(m, t));
+  return b200rec_step_wait(m, t, loss);
 }
 
 int b200rec_predict(b200rec_model_t m, b200rec_table_t t, int batch_size, const int* feats,

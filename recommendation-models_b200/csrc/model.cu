@@ -114,7 +114,7 @@ int b200rec_model_s::init(int kind_, int F_, int K_, const int* fc_, int n_fc, c
   B200_CUDA(cudaStreamCreateWithFlags(&side3, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-  for (cudaEvent_t* e : {&ev_staged[0], &ev_staged[1], &ev_consumed[0], &ev_consumed[1]})
+  for (cudaEvent_t* e : {&ev_staged[0], &ev_staged[1], &ev_consumed[0], &ev_consumed[1], &ev_done[0], &ev_done[1]})
     B200_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   for (cudaEvent_t* e : {&ev_aux_fork, &ev_aux_pack, &ev_aux_join, &ev_aux_cs[0], &ev_aux_cs[1]})
     B200_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
@@ -164,7 +164,7 @@ void b200rec_model_s::destroy() {
   if (side3) cudaStreamDestroy(side3);
   if (aux) cudaStreamDestroy(aux);
   if (copy_stream) cudaStreamDestroy(copy_stream);
-  for (cudaEvent_t e : {ev_staged[0], ev_staged[1], ev_consumed[0], ev_consumed[1]})
+  for (cudaEvent_t e : {ev_staged[0], ev_staged[1], ev_consumed[0], ev_consumed[1], ev_done[0], ev_done[1]})
     if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) { stage_f[i].release(); stage_t[i].release(); }
   for (cudaEvent_t e : {ev_aux_fork, ev_aux_pack, ev_aux_join, ev_aux_cs[0], ev_aux_cs[1]})

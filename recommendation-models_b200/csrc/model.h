@@ -75,6 +75,9 @@ struct b200rec_model_s {
   b200rec::DevBuf stage_f[2], stage_t[2];
   int stage_B[2] = {0, 0}, stage_head = 0, stage_count = 0;
   bool stage_used[2] = {false, false};
+  // steps enqueued by b200rec_step_staged_async whose loss has not been waited for yet (<= 2)
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  int async_B[2] = {0, 0}, async_head = 0, async_count = 0;
   float* h_scal = nullptr;  // pinned 16 words: loss, dbias, n_unique, -, err, sorted
   bool params_set = false;
   // CUDA graph of the resident step (one per (B, table, gemm_mode)); captured after one eager warm-up

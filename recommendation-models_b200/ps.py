@@ -134,6 +134,22 @@ class ParRecModel:
         self._last_nnz = feats.shape[0]
         return float(loss.value) * targets.shape[0]
 
+    def optimizeStagedAsync(self):
+        """Enqueue optimize() on the batch staged first and return at once (at most two in flight);
+        waitLoss() returns the losses in order.  `stage(i+1); optimizeStagedAsync(); waitLoss()` of the
+        previous step keeps the GPU busy while every loss is still read by the host, one step late."""
+        L.check(L.lib().b200rec_step_staged_async(self.model.handle, self.table.handle))
+        feats, targets = self._staged.pop(0)
+        self._last_nnz = feats.shape[0]
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append(targets.shape[0])
+
+    def waitLoss(self):
+        """-> loss * batchSize of the oldest step enqueued by optimizeStagedAsync."""
+        loss = C.c_float(0)
+        L.check(L.lib().b200rec_step_wait(self.model.handle, self.table.handle, C.byref(loss)))
+        return float(loss.value) * self._inflight.pop(0)
+
     def predict(self, feats, batchSize):
         feats = L.i32(feats)
         preds = np.zeros(batchSize, np.float32)

@@ -155,6 +155,21 @@ def test_staged_step_equals_host_step(gpu_pkg):
     ra, rb = a.stepResults(), b.stepResults()
     assert np.array_equal(ra["unique"], rb["unique"]) and np.array_equal(ra["emb_grad"], rb["emb_grad"])
     assert np.array_equal(ra["mats_grad"], rb["mats_grad"])
+    # the same losses through the asynchronous pair, read one step late
+    c = fresh()
+    got_async = []
+    c.stage(*batches[0])
+    for i in range(len(batches)):
+        if i + 1 < len(batches):
+            c.stage(*batches[i + 1])
+        c.optimizeStagedAsync()
+        if i > 0:
+            got_async.append(c.waitLoss())
+        c.applyOptimizer("sgd", 0.05)
+    got_async.append(c.waitLoss())
+    assert got_async == want
+    with pytest.raises(RuntimeError):
+        c.waitLoss()                             # nothing in flight
     b.stage(*batches[0]); b.stage(*batches[1])
     with pytest.raises(RuntimeError):
         b.stage(*batches[2])                     # two staged already
