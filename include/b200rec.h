@@ -277,7 +277,7 @@ int b200rec_step_rows_dev(b200rec_model_t m, int batch_size, const int* slots, c
  * (csrc/p2p.cu).  peer_* are arrays of `world` device pointers, one per rank, to symmetric buffers
  * (the host maps them, e.g. torch symmetric memory or cudaIpc): ids_in[world*cap] int (a ring kept
  * by the caller, reset to -1 ahead of use: 2 deep, or 4 deep when ids are dispatched one step ahead), rows_in[world*cap*K], w_in[world*cap], grad_in, gw_in
- * (same shapes), flags[4*world] int (zero-initialised).  `step` counts from 1 and must increase; pass
+ * (same shapes), flags[5*world] int (zero-initialised).  `step` counts from 1 and must increase; pass
  * step <= 0 for (the model's device step counter - step), see b200rec_p2p_begin_step_dev: 0 = the
  * current step, -1 = the next one (an id dispatch issued one step ahead). */
 /* n_dev (may be NULL): device count of valid ids, e.g. the distinct ids of the batch (dedup before the
@@ -291,13 +291,16 @@ int b200rec_p2p_dispatch_ids_dev(b200rec_model_t m, int64_t nnz, const int* n_de
  * with the -1 padding. */
 int b200rec_p2p_begin_step_dev(b200rec_model_t m, int* ids_next, int64_t n, void* stream);
 
-/* One-shot allreduce (sum, rank order) of the dense gradients over NVLink peer loads: inout is copied
- * to this rank's symmetric buffer peer_bufs[rank], flagged (phase 3), and the sum of all ranks'
- * buffers is written back to inout.  Replaces the worker -> PS push of the dense gradients
- * (rec/model/ParRecModel.scala:247-264) for data-parallel replicas. */
+/* Allreduce (sum, rank order: bit-identical on every rank) of the dense gradients over NVLink peer
+ * memory: inout is copied to this rank's symmetric buffer peer_bufs[rank] (n rounded up to 4 floats,
+ * pad zero) and flagged (phase 3).  peer_out == NULL: one-shot, every rank reads all vectors with
+ * peer loads.  Otherwise two-shot: rank r sums slice r and stores it into every peer_out[q] (phase 4),
+ * then the result is copied back: 2(G-1)/G instead of (G-1) vectors over NVLink per rank.  Replaces
+ * the worker -> PS push of the dense gradients (rec/model/ParRecModel.scala:247-264) for
+ * data-parallel replicas. */
 int b200rec_p2p_allreduce_dev(b200rec_model_t m, int64_t n, int world, int rank, int step, float* inout,
-                              void* const* peer_bufs, void* const* peer_flags, const int* flags_local,
-                              void* stream);
+                              void* const* peer_bufs, void* const* peer_out, void* const* peer_flags,
+                              const int* flags_local, void* stream);
 
 /* Side streams: the sorts of workspace `ws` (0, 1, 2) run on a side stream of the model
  * (b200rec_segsum_sort_dev forks it from `stream`; b200rec_segsum_join_dev / _reduce_dev join it).
@@ -317,7 +320,7 @@ int b200rec_graph_launch(b200rec_model_t m, int graph_id, void* stream);
 /* slot of every non-zero from the slot of its distinct id (the ids' sort of workspace `ws` links them) */
 int b200rec_p2p_compose_dst_dev(b200rec_model_t m, int ws, int64_t nnz, const int* dst_unique, int* dst,
                                 void* stream);
-/* spin (device side) until every rank's flag of `phase` (0 ids, 1 rows, 2 grads, 3 dense) has reached `step` */
+/* spin (device side) until every rank's flag of `phase` (0 ids, 1 rows, 2 grads, 3 dense published, 4 dense reduced) has reached `step` */
 int b200rec_p2p_wait_dev(b200rec_model_t m, const int* flags_local, int phase, int world, int step,
                          void* stream);
 int b200rec_p2p_gather_dev(b200rec_model_t m, b200rec_table_t t, int world, int rank, int cap, int step,

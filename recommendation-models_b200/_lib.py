@@ -72,7 +72,7 @@ SIGNATURES = {
     "b200rec_segsum_join_dev": [vp, C.c_int, vp],
     "b200rec_segsum_inverse_dev": [vp, C.c_int, C.c_int64, vp, vp],
     "b200rec_p2p_begin_step_dev": [vp, vp, C.c_int64, vp],
-    "b200rec_p2p_allreduce_dev": [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp],
+    "b200rec_p2p_allreduce_dev": [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp],
     "b200rec_model_side_stream": [vp, C.c_int, C.POINTER(vp)],
     "b200rec_side_fork_dev": [vp, C.c_int, vp],
     "b200rec_side_rejoin_dev": [vp, C.c_int],

@@ -1187,7 +1187,7 @@ static int fill_p2p(Model* m, int world, int rank, int step, void* const* peer_f
 int b200rec_p2p_wait_dev(b200rec_model_t m, const int* flags_local, int phase, int world, int step,
                          void* stream) {
   B200_GUARD_BEGIN
-  B200_REQUIRE(flags_local && phase >= 0 && phase < 4, B200REC_ERR_ARG, "bad argument");
+  B200_REQUIRE(flags_local && phase >= 0 && phase < 5, B200REC_ERR_ARG, "bad argument");
   P2P c;
   void* none[P2P_MAX] = {};
   B200_TRY(fill_p2p(m, world, 0, step, none, c));
@@ -1208,16 +1208,20 @@ int b200rec_p2p_begin_step_dev(b200rec_model_t m, int* ids_next, int64_t n, void
 }
 
 int b200rec_p2p_allreduce_dev(b200rec_model_t m, int64_t n, int world, int rank, int step, float* inout,
-                              void* const* peer_bufs, void* const* peer_flags, const int* flags_local,
-                              void* stream) {
+                              void* const* peer_bufs, void* const* peer_out, void* const* peer_flags,
+                              const int* flags_local, void* stream) {
   B200_GUARD_BEGIN
   P2P c;
   B200_TRY(fill_p2p(m, world, rank, step, peer_flags, c, 3));
   B200_REQUIRE(inout && peer_bufs && flags_local && n >= 0, B200REC_ERR_ARG, "bad argument");
   B200_TRY(use_device(m->device));
-  PeerF bufs;
-  for (int p = 0; p < world; ++p) bufs.p[p] = (float*)peer_bufs[p];
-  return p2p_allreduce(n, inout, flags_local, c, bufs, stream ? (cudaStream_t)stream : m->stream);
+  PeerF bufs, outs;
+  for (int p = 0; p < world; ++p) {
+    bufs.p[p] = (float*)peer_bufs[p];
+    outs.p[p] = peer_out ? (float*)peer_out[p] : nullptr;
+  }
+  return p2p_allreduce(n, inout, flags_local, c, bufs, peer_out ? &outs : nullptr,
+                       stream ? (cudaStream_t)stream : m->stream);
   B200_GUARD_END
 }
 

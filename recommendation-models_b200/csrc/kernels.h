@@ -111,7 +111,7 @@ int p2p_wait(const int* flags, int phase, int world, int step, const int* step_p
 int p2p_begin_step(int* step_ctr, int* ids_next, long long n, cudaStream_t st);
 // dense gradients: inout -> my symmetric buffer, then the sum over all ranks (rank order) back into inout
 int p2p_allreduce(long long n, float* inout, const int* flags_local, const P2P& c, const PeerF& bufs,
-                  cudaStream_t st);
+                  const PeerF* outs, cudaStream_t st);
 // n_dev (optional): device count of valid ids (<= n); ids beyond it are ignored
 int p2p_plan(ShardPlanWorkspace& ws, long long n, const int* n_dev, long long period, int cap,
              const int* feats, int* dst, int* overflow, const P2P& c, const PeerI& ids_in, cudaStream_t st);

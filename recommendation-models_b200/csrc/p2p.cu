@@ -10,7 +10,8 @@
 //   rows_in[G*cap*K], w_in[G*cap]        rows returned by each owner (block o written by owner o)
 //   grad_in[G*cap*K], gw_in[G*cap]       per-nnz gradients from each source (block s)
 //   dense_in[mats]      this rank's dense gradients, read by every peer (one-shot allreduce, phase 3)
-//   flags  [4][G]       flags[phase][src] = step number, written by src after its data (release.sys)
+//   dense_out[mats]     two-shot allreduce only: the reduced slices, stored by their owners (phase 4)
+//   flags  [5][G]       flags[phase][src] = step number, written by src after its data (release.sys)
 // The step number lives in a device counter (advanced by p2p_begin_step) so that a captured CUDA
 // graph of the whole step can be replayed.
 // A writer kernel ends with: __threadfence_system() by every thread, __syncthreads(), one atomicInc
@@ -124,8 +125,43 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(long long n, float* dst
   }
 }
 
+// Two-shot form for larger groups: rank r sums slice r of all published vectors (rank order) and
+// stores the result into every peer's `out` buffer (flag 4); then everyone copies `out` back.  NVLink
+// bytes per rank: 2 (G-1)/G n instead of (G-1) n.  n4 = float4 count of the zero-padded vectors.
+__global__ void __launch_bounds__(256) p2p_reduce_scatter_kernel(long long n4, P2P c, PeerF bufs, PeerF outs) {
+  const long long lo = n4 * c.rank / c.world, hi = n4 * (c.rank + 1) / c.world;
+  for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v[P2P_MAX];
+#pragma unroll
+    for (int p = 0; p < P2P_MAX; ++p)
+      if (p < c.world) v[p] = __ldcg(reinterpret_cast<const float4*>(bufs.p[p]) + i);
+    float4 a = v[0];
+#pragma unroll
+    for (int p = 1; p < P2P_MAX; ++p)
+      if (p < c.world) {
+        a.x = __fadd_rn(a.x, v[p].x); a.y = __fadd_rn(a.y, v[p].y);
+        a.z = __fadd_rn(a.z, v[p].z); a.w = __fadd_rn(a.w, v[p].w);
+      }
+#pragma unroll
+    for (int p = 0; p < P2P_MAX; ++p)
+      if (p < c.world) reinterpret_cast<float4*>(outs.p[p])[i] = a;
+  }
+  p2p_signal(c, 4);
+}
+
+__global__ void __launch_bounds__(256) p2p_copy_back_kernel(long long n, const float* src, float* dst) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(dst)[i] = __ldcg(reinterpret_cast<const float4*>(src) + i);
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[n4 * 4 + threadIdx.x] = __ldcg(src + n4 * 4 + threadIdx.x);
+}
+
+// bufs: the published vectors (padded to a multiple of 4 floats, pad zero-initialised by the host);
+// outs (may be empty: one-shot): the result buffers of the two-shot form
 int p2p_allreduce(long long n, float* inout, const int* flags_local, const P2P& c, const PeerF& bufs,
-                  cudaStream_t st) {
+                  const PeerF* outs, cudaStream_t st) {
   if (n <= 0) return B200REC_OK;
   ProfTag tag("p2p_allreduce");
   int grid = cdiv(n / 4 > 0 ? n / 4 : 1, 256);
@@ -133,7 +169,17 @@ int p2p_allreduce(long long n, float* inout, const int* flags_local, const P2P& 
   B200_LAUNCH(p2p_publish_kernel, grid, 256, 0, st, n, (const float*)inout, bufs.p[c.rank], c);
   // a one-warp kernel does the spinning: the reduce blocks must not hold SMs while a peer is late
   B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags_local, 3, c.world, c.step, c.step_ptr);
-  B200_LAUNCH(p2p_reduce_kernel, grid, 256, 0, st, n, inout, c, bufs);
+  if (!outs) {
+    B200_LAUNCH(p2p_reduce_kernel, grid, 256, 0, st, n, inout, c, bufs);
+  } else {
+    const long long n4 = (n + 3) / 4;
+    int g2 = cdiv(cdiv(n4, c.world), 256);
+    if (g2 > 148 * 2) g2 = 148 * 2;
+    if (g2 < 1) g2 = 1;
+    B200_LAUNCH(p2p_reduce_scatter_kernel, g2, 256, 0, st, n4, c, bufs, *outs);
+    B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags_local, 4, c.world, c.step, c.step_ptr);
+    B200_LAUNCH(p2p_copy_back_kernel, grid, 256, 0, st, n, (const float*)outs->p[c.rank], inout);
+  }
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }

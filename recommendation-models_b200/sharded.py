@@ -18,6 +18,7 @@ numpy stand-in in tests/ so the exchange logic runs under gloo on CPU with world
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -212,7 +213,12 @@ class P2PShardedParRecModel:
         self.gw_in = symm(n, torch.float32, 0)
         self.n_dense = ops.dense_grads().numel()
         self.dense_in = symm((self.n_dense + 3) // 4 * 4, torch.float32, 0)
-        self.flags = symm(4 * G, torch.int32, 0)
+        # two-shot allreduce (each rank reduces one slice and stores it to every peer) from 4 GPUs up:
+        # 2 (G-1)/G instead of (G-1) gradient vectors over NVLink per rank
+        two_shot = os.environ.get("B200REC_TWO_SHOT")
+        self.two_shot = G >= 4 if two_shot is None else two_shot == "1"
+        self.dense_out = symm((self.n_dense + 3) // 4 * 4, torch.float32, 0) if self.two_shot else None
+        self.flags = symm(5 * G, torch.int32, 0)
         self.dst = [torch.empty(N, dtype=torch.int32, device=dev) for _ in range(2)]       # by step parity
         self.dst_u = [torch.empty(N, dtype=torch.int32, device=dev) for _ in range(2)]
         self.grad_rows = torch.empty(N * dim, dtype=torch.float32, device=dev)   # per-nnz, local order
@@ -299,17 +305,18 @@ class P2PShardedParRecModel:
                                           self.w_in[0].data_ptr(), self.w_in[0].numel(),
                                           targets.data_ptr(), self.grad_rows.data_ptr(),
                                           self.grad_w.data_ptr(), 0, st))
-        # dense gradients: summed over the replicas on the owner-sort side stream, under the embedding
-        # gradient exchange
-        L.check(lib.b200rec_side_fork_dev(m, 1, st))
-        L.check(lib.b200rec_p2p_allreduce_dev(m, self.n_dense, G, r, 0, o._mats_grad_ptr,
-                                              self.dense_in[2], flags_p, flags_t.data_ptr(), self.side[1]))
-        L.check(lib.b200rec_side_rejoin_dev(m, 1))
+        # dense gradients: summed over the replicas on the (now idle) side stream of this batch's sort,
+        # under the embedding-gradient exchange; joined at the end of the step
+        L.check(lib.b200rec_side_fork_dev(m, ws, st))
+        L.check(lib.b200rec_p2p_allreduce_dev(m, self.n_dense, G, r, 0, o._mats_grad_ptr, self.dense_in[2],
+                                              self.dense_out[2] if self.two_shot else None, flags_p,
+                                              flags_t.data_ptr(), self.side[ws]))
         # local pre-reduce per distinct id (in non-zero order), then one push per distinct id
         L.check(lib.b200rec_segsum_reduce_dev(m, ws, self.K, N, self.gbits, 0, feats.data_ptr(),
                                               self.grad_rows.data_ptr(), self.grad_w.data_ptr(),
                                               loc["uniq"].data_ptr(), self.G_loc.data_ptr(),
                                               self.gw_loc.data_ptr(), loc["n"].data_ptr(), st))
+        L.check(lib.b200rec_side_rejoin_dev(m, ws))   # after the call above: it must not wait for the allreduce
         L.check(lib.b200rec_p2p_push_grads_dev(m, N, loc["n"].data_ptr(), G, r, cap, 0,
                                                self.dst_u[p].data_ptr(), self.G_loc.data_ptr(),
                                                self.gw_loc.data_ptr(), self.grad_in[2], self.gw_in[2],
@@ -318,6 +325,7 @@ class P2PShardedParRecModel:
         o.segsum(cur[0], self.grad_in[0], self.gw_in[0], self.unique, self.G, self.gw)   # joins side stream 1
         if lr is not None:
             o.apply_sgd(self.unique, self.G, self.gw, lr)
+        L.check(lib.b200rec_segsum_join_dev(m, ws, st))           # the dense allreduce
         if join_next and next_feats is not None:
             L.check(lib.b200rec_segsum_join_dev(m, 2 - ws, st))   # a graph must end with every fork joined
         loc["feats"] = None
@@ -505,9 +513,15 @@ def bench(args, pkg):
     pin = [(torch.from_numpy(f).pin_memory(), torch.from_numpy(synth.make_targets(B.SEED_DATA, f, batch, F)).pin_memory())
            for f in batches]
     d_f, d_t = torch.empty(batch * F, dtype=torch.int32, device=dev), torch.empty(batch, dtype=torch.float32, device=dev)
-    h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    h_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    n_host = [0]
 
     def host_step(i):
+        # every step: H2D of a batch and D2H of a loss; the host reads each loss one step late so that
+        # the next step is already queued when it blocks
+        k = n_host[0]
+        n_host[0] += 1
         if use_p2p:
             sh.load(*pin[(i + 1) % nb])     # H2D of the next batch, then the replayed step on the staged one
             sh.step()
@@ -518,9 +532,12 @@ def bench(args, pkg):
                 d_t.copy_(t, non_blocking=True)
             sh.optimize(d_f, d_t)
         with ops.stream_ctx():
-            h_loss.copy_(ops.loss(), non_blocking=True)
-        ops.stream.synchronize()
-        return float(h_loss[0])
+            h_loss[k & 1:(k & 1) + 1].copy_(ops.loss(), non_blocking=True)
+            loss_ev[k & 1].record(ops.stream)
+        if k == 0:
+            return 0.0
+        loss_ev[(k - 1) & 1].synchronize()
+        return float(h_loss[(k - 1) & 1])
 
     for i in range(3):
         host_step(i)
@@ -530,6 +547,8 @@ def bench(args, pkg):
     last = 0.0
     for i in range(Ksteps):
         last = host_step(W + i)
+    ops.stream.synchronize()
+    last = float(h_loss[(n_host[0] - 1) & 1])      # the last step's loss
     torch.cuda.synchronize()
     dist.barrier()
     e2e = torch.tensor([time.perf_counter() - t0], device=dev)
@@ -567,7 +586,7 @@ def bench(args, pkg):
             "e2e": {"value": round(batch * world * Ksteps / float(e2e.item()), 1), "unit": "samples/s",
                     "h2d_bytes_per_step": batch * F * 4 + batch * 4, "d2h_bytes_per_step": 4,
                     "call": ("P2PShardedParRecModel.load + step" if use_p2p else "ShardedParRecModel.optimize") +
-                            " (pinned host ids + labels in, loss out), per rank",
+                            " (pinned host ids + labels in, every loss read by the host one step late), per rank",
                     "last_loss": round(last, 6)},
             "gpu_launches": int(launches),
             "exchange_bytes_per_gpu_per_step": {"ids": n_slots * 4, "rows_back": n_slots * (K + 1) * 4,

@@ -144,8 +144,12 @@ def run(rank, world, backend, device=None):
         ops = GpuOps(pkg, model, table, spec, B, cap, torch, dev)
         tf, tt = torch.from_numpy(feats).to(dev), torch.from_numpy(targets).to(dev)
     cls = P2PShardedParRecModel if backend.startswith("p2p") else ShardedParRecModel
+    if backend == "p2p_graph_twoshot":     # the >= 4 GPU form of the dense allreduce, forced on any world size
+        os.environ["B200REC_TWO_SHOT"] = "1"
+    else:
+        os.environ.pop("B200REC_TWO_SHOT", None)
     sh = cls(ops, dist, spec, B, F, K, cap=cap)
-    if backend == "p2p_graph":
+    if backend.startswith("p2p_graph"):
         # replay mode: step 1 runs call by call (buffers take their size), steps 2 and 3 capture the
         # two parities, steps 4 and 5 replay them; the next batch is staged and sorted one step ahead
         sh.load(tf, tt)
@@ -206,7 +210,7 @@ if __name__ == "__main__":
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    for backend in ("nccl", "p2p", "p2p_graph"):
+    for backend in ("nccl", "p2p", "p2p_graph", "p2p_graph_twoshot"):
         u = run(rank, world, backend, device=local)
         print(f"rank {rank}/{world}: sharded step ok ({backend}), {u} owned distinct rows", flush=True)
     dist.barrier()

@@ -15,7 +15,7 @@ def _run(n):
            "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tests", "sharded_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("sharded step ok") == 3 * n, r.stdout
+    assert r.stdout.count("sharded step ok") == 4 * n, r.stdout
 
 
 def test_sharded_world1(gpu_pkg):
