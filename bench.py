@@ -163,7 +163,7 @@ def run_b200(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 or args.force_sharded:
         from recommendation_models_b200 import sharded  # noqa: F401  (registered by load_package)
         return sharded.bench(args, pkg)
 
@@ -415,6 +415,9 @@ def main():
     ap.add_argument("--rows", type=int, default=39 * (1 << 18))
     ap.add_argument("--gemm-mode", type=int, default=None, help="0 fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--force-sharded", dest="force_sharded", action="store_true",
+                    help="run the row-sharded step even on one rank (torchrun --nproc-per-node 1): the exchange "
+                         "kernels then store into the rank's own buffers, which makes them profilable with ncu")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: NVLink peer-memory exchange fused into the kernels, or NCCL all-to-all")
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of the CUDA graph")

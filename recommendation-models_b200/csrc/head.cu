@@ -15,7 +15,9 @@ __global__ void __launch_bounds__(256) head_kernel(Head h, float* part) {
   float li = 0.f, gi = 0.f;
   if (b < h.B) {
     float z = h.br[0][b];
-    for (int i = 1; i < h.n_br; ++i) z += h.br[i][b];
+#pragma unroll
+    for (int i = 1; i < 4; ++i)   // static indices: a dynamic one would spill the parameter struct to local memory
+      if (i < h.n_br) z += h.br[i][b];
     z += __ldg(h.bias);
     const float p = 1.0f / (1.0f + expf(-z));
     if (h.preds) h.preds[b] = p;

@@ -14,7 +14,7 @@
 //   flags  [5][G]       flags[phase][src] = step number, written by src after its data (release.sys)
 // The step number lives in a device counter (advanced by p2p_begin_step) so that a captured CUDA
 // graph of the whole step can be replayed.
-// A writer kernel ends with: __threadfence_system() by every thread, __syncthreads(), one atomicInc
+// A writer kernel ends with: __syncthreads(), then thread 0's __threadfence_system() and one atomicInc
 // per block, and the LAST block stores the step number into every peer's flag.  A one-warp wait kernel
 // spins (acquire.sys) until all G flags of a phase reach the step, trapping after ~2 s.
 #include "kernels.h"
@@ -30,18 +30,36 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   return v;
 }
 
+// peer pointer i of a by-value kernel parameter array.  A dynamic index would make the compiler copy
+// the whole parameter struct to LOCAL memory in every thread (ncu: 4.5 M local store sectors, 77 MB of
+// DRAM writes in the gather kernel); a chain of selects on the constant bank does not.
+template <class T>
+__device__ __forceinline__ T* peer_sel(T* const (&p)[P2P_MAX], int i) {
+  T* r = p[0];
+#pragma unroll
+  for (int k = 1; k < P2P_MAX; ++k)
+    if (i == k) r = p[k];
+  return r;
+}
+
 __device__ __forceinline__ int p2p_step(const P2P& c) { return c.step > 0 ? c.step : *c.step_ptr - c.step; }
 
-// end-of-kernel signal: every thread of every block must call this (convergently)
+// end-of-kernel signal: every thread of every block must call this (convergently).  The block barrier
+// orders every thread's stores before thread 0 (CTA scope); thread 0's system-scope fence is cumulative,
+// so those stores are visible system-wide before its counter increment and, in the last block, before
+// the release stores of the flags.  (One fence per block: a membar.sys per thread made the writer
+// kernels several times slower.)
 __device__ __forceinline__ void p2p_signal(const P2P& c, int phase) {
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned last = gridDim.x * gridDim.y - 1;
     if (atomicInc(c.block_counter, last) == last) {
       __threadfence_system();
       const int step = p2p_step(c);
-      for (int p = 0; p < c.world; ++p) st_release_sys(c.flags[p] + phase * c.world + c.rank, step);
+#pragma unroll
+      for (int p = 0; p < P2P_MAX; ++p)
+        if (p < c.world) st_release_sys(c.flags[p] + phase * c.world + c.rank, step);
     }
   }
 }
@@ -120,7 +138,9 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(long long n, float* dst
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = n4 * 4 + threadIdx.x;
     float a = __ldcg(bufs.p[0] + i);
-    for (int p = 1; p < c.world; ++p) a = __fadd_rn(a, __ldcg(bufs.p[p] + i));
+#pragma unroll
+    for (int p = 1; p < P2P_MAX; ++p)
+      if (p < c.world) a = __fadd_rn(a, __ldcg(bufs.p[p] + i));
     dst[i] = a;
   }
 }
@@ -225,7 +245,7 @@ __global__ void __launch_bounds__(256) p2p_rank_place_kernel(long long n, const 
         atomicOr(overflow, 1);
         dst[i] = o * cap;
       } else {
-        ids_in.p[o][(long long)c.rank * cap + slot] = (int)(id / world);   // store into the owner's memory
+        peer_sel(ids_in.p, o)[(long long)c.rank * cap + slot] = (int)(id / world);   // store into the owner's memory
         dst[i] = o * cap + slot;
       }
     }
@@ -290,8 +310,8 @@ __global__ void __launch_bounds__(256) p2p_gather_kernel(long long rows, int cap
     const int src = (int)(j / cap);
     const long long slot = j - (long long)src * cap;
     const long long o = (long long)c.rank * cap + slot;   // my block in the requester's buffers
-    if (table) st_f4(rows_in.p[src] + o * K + sub * 4, ldg_f4(table + id * K + sub * 4));
-    if (sub == 0) w_in.p[src][o] = __ldg(wtable + id);
+    if (table) st_f4(peer_sel(rows_in.p, src) + o * K + sub * 4, ldg_f4(table + id * K + sub * 4));
+    if (sub == 0) peer_sel(w_in.p, src)[o] = __ldg(wtable + id);
   }
   p2p_signal(c, 1);
 }
@@ -331,8 +351,8 @@ __global__ void __launch_bounds__(256) p2p_push_grads_kernel(long long n, const 
     const int s = dst[i];
     const int o = s / cap;
     const long long slot = (long long)c.rank * cap + (s - o * cap);
-    if (dE) st_f4(grad_in.p[o] + slot * K + sub * 4, ld_stream_f4(dE + i * K + sub * 4));
-    if (sub == 0) gw_in.p[o][slot] = dw[i];
+    if (dE) st_f4(peer_sel(grad_in.p, o) + slot * K + sub * 4, ld_stream_f4(dE + i * K + sub * 4));
+    if (sub == 0) peer_sel(gw_in.p, o)[slot] = dw[i];
   }
   p2p_signal(c, 2);
 }
