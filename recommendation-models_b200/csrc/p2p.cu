@@ -103,11 +103,15 @@ int p2p_begin_step(int* step_ctr, int* ids_next, long long n, cudaStream_t st) {
   return B200REC_OK;
 }
 
+// writer kernels run as few fat blocks (2 per SM): every block ends with a system-scope fence
+constexpr int EX_THREADS = 512;
+constexpr int EX_UNR = 4;
+
 // ---- phase 3: dense gradients, one-shot allreduce over peer loads -----------------------------------
 // Reference: the dense gradients go to the PS like the embedding ones (ParRecModel.scala:247-264);
 // data-parallel replicas need their SUM.  Every rank publishes its vector in symmetric memory and
 // then reads all G vectors, adding them in rank order: all replicas get bit-identical sums.
-__global__ void __launch_bounds__(256) p2p_publish_kernel(long long n, const float* src, float* mine, P2P c) {
+__global__ void __launch_bounds__(EX_THREADS) p2p_publish_kernel(long long n, const float* src, float* mine, P2P c) {
   const long long n4 = n >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(src);
   float4* d4 = reinterpret_cast<float4*>(mine);
@@ -186,7 +190,9 @@ int p2p_allreduce(long long n, float* inout, const int* flags_local, const P2P& 
   ProfTag tag("p2p_allreduce");
   int grid = cdiv(n / 4 > 0 ? n / 4 : 1, 256);
   if (grid > 148 * 4) grid = 148 * 4;
-  B200_LAUNCH(p2p_publish_kernel, grid, 256, 0, st, n, (const float*)inout, bufs.p[c.rank], c);
+  int pgrid = cdiv(n / 4 > 0 ? n / 4 : 1, EX_THREADS);
+  if (pgrid > 148 * 2) pgrid = 148 * 2;
+  B200_LAUNCH(p2p_publish_kernel, pgrid, EX_THREADS, 0, st, n, (const float*)inout, bufs.p[c.rank], c);
   // a one-warp kernel does the spinning: the reduce blocks must not hold SMs while a peer is late
   B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags_local, 3, c.world, c.step, c.step_ptr);
   if (!outs) {
@@ -291,27 +297,56 @@ int p2p_compose(SegSumWorkspace& ws, long long n, const int* dst_unique, int* ds
 }
 
 // ---- phase 1: owner-side gather, rows stored straight into the requesters' buffers -----------------
+// Few fat blocks (2 per SM, 512 threads): every block ends with a system-scope fence, which is the
+// expensive part of a writer kernel; each thread keeps EX_UNR independent id -> row chains in flight.
+static int ex_grid(long long items) {
+  int grid = cdiv(cdiv(items, EX_UNR), EX_THREADS);
+  if (grid > 148 * 2) grid = 148 * 2;
+  return grid < 1 ? 1 : grid;
+}
+
 template <int LPR>
-__global__ void __launch_bounds__(256) p2p_gather_kernel(long long rows, int cap, const int* ids_in,
-                                                         const float* table, const float* wtable, P2P c,
-                                                         PeerF rows_in, PeerF w_in, int* err) {
+__global__ void __launch_bounds__(EX_THREADS) p2p_gather_kernel(long long rows, int cap, const int* ids_in,
+                                                                const float* table, const float* wtable, P2P c,
+                                                                PeerF rows_in, PeerF w_in, int* err) {
   constexpr int K = 4 * LPR;
   const long long n_vec = (long long)c.world * cap * LPR;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_vec;
-       t += (long long)gridDim.x * blockDim.x) {
-    const long long j = t / LPR;          // slot in my ids_in: source * cap + slot
-    const int sub = (int)(t - j * LPR);
-    long long id = ids_in[j];
-    if (id < 0) continue;                 // padding: the requester never reads this slot
-    if (id >= rows) {
-      atomicOr(err, DEV_BAD_ID);
-      id = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; t0 < n_vec; t0 += EX_UNR * stride) {
+    long long id[EX_UNR];
+#pragma unroll
+    for (int u = 0; u < EX_UNR; ++u) {
+      const long long t = t0 + u * stride;
+      id[u] = t < n_vec ? (long long)ids_in[t / LPR] : -1;   // slot in my ids_in: source * cap + slot
+      if (id[u] >= rows) {
+        atomicOr(err, DEV_BAD_ID);
+        id[u] = 0;
+      }
     }
-    const int src = (int)(j / cap);
-    const long long slot = j - (long long)src * cap;
-    const long long o = (long long)c.rank * cap + slot;   // my block in the requester's buffers
-    if (table) st_f4(peer_sel(rows_in.p, src) + o * K + sub * 4, ldg_f4(table + id * K + sub * 4));
-    if (sub == 0) peer_sel(w_in.p, src)[o] = __ldg(wtable + id);
+    float4 v[EX_UNR];
+    float w[EX_UNR];
+#pragma unroll
+    for (int u = 0; u < EX_UNR; ++u) {
+      const int sub = (int)((t0 + u * stride) % LPR);
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w[u] = 0.f;
+      if (id[u] >= 0) {                    // negative = padding: the requester never reads this slot
+        if (table) v[u] = ldg_f4(table + id[u] * K + sub * 4);
+        if (sub == 0) w[u] = __ldg(wtable + id[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EX_UNR; ++u) {
+      if (id[u] < 0) continue;
+      const long long t = t0 + u * stride;
+      const long long j = t / LPR;
+      const int sub = (int)(t - j * LPR);
+      const int src = (int)(j / cap);
+      const long long slot = j - (long long)src * cap;
+      const long long o = (long long)c.rank * cap + slot;   // my block in the requester's buffers
+      if (table) st_f4(peer_sel(rows_in.p, src) + o * K + sub * 4, v[u]);
+      if (sub == 0) peer_sel(w_in.p, src)[o] = w[u];
+    }
   }
   p2p_signal(c, 1);
 }
@@ -320,15 +355,13 @@ int p2p_gather(long long rows, int K, int cap, const int* ids_in, const float* t
                const P2P& c, const PeerF& rows_in, const PeerF& w_in, int* err, cudaStream_t st) {
   ProfTag tag("p2p_gather_rows");
   const long long n = (long long)c.world * cap;
-  int grid = cdiv(n * (K / 4 > 0 ? K / 4 : 1), 256);
-  if (grid > 148 * 16) grid = 148 * 16;
-  if (grid < 1) grid = 1;
+  const int grid = ex_grid(n * (K / 4 > 0 ? K / 4 : 1));
   switch (K) {
-    case 4: B200_LAUNCH(p2p_gather_kernel<1>, grid, 256, 0, st, rows, cap, ids_in, table, wtable, c, rows_in, w_in, err); break;
-    case 8: B200_LAUNCH(p2p_gather_kernel<2>, grid, 256, 0, st, rows, cap, ids_in, table, wtable, c, rows_in, w_in, err); break;
-    case 16: B200_LAUNCH(p2p_gather_kernel<4>, grid, 256, 0, st, rows, cap, ids_in, table, wtable, c, rows_in, w_in, err); break;
-    case 32: B200_LAUNCH(p2p_gather_kernel<8>, grid, 256, 0, st, rows, cap, ids_in, table, wtable, c, rows_in, w_in, err); break;
-    case 64: B200_LAUNCH(p2p_gather_kernel<16>, grid, 256, 0, st, rows, cap, ids_in, table, wtable, c, rows_in, w_in, err); break;
+    case 4: B200_LAUNCH(p2p_gather_kernel<1>, grid, EX_THREADS, 0, st, rows, cap, ids_in, table, wtable, c, rows_in, w_in, err); break;
+    case 8: B200_LAUNCH(p2p_gather_kernel<2>, grid, EX_THREADS, 0, st, rows, cap, ids_in, table, wtable, c, rows_in, w_in, err); break;
+    case 16: B200_LAUNCH(p2p_gather_kernel<4>, grid, EX_THREADS, 0, st, rows, cap, ids_in, table, wtable, c, rows_in, w_in, err); break;
+    case 32: B200_LAUNCH(p2p_gather_kernel<8>, grid, EX_THREADS, 0, st, rows, cap, ids_in, table, wtable, c, rows_in, w_in, err); break;
+    case 64: B200_LAUNCH(p2p_gather_kernel<16>, grid, EX_THREADS, 0, st, rows, cap, ids_in, table, wtable, c, rows_in, w_in, err); break;
     default: set_error("p2p exchange supports embeddingDim in {4,8,16,32,64}, got %d", K); return B200REC_ERR_ARG;
   }
   B200_CHECK_LAUNCH();
@@ -337,22 +370,41 @@ int p2p_gather(long long rows, int K, int cap, const int* ids_in, const float* t
 
 // ---- phase 2: per-nnz gradients stored into the owners' buffers (after the dense backward) ----------
 template <int LPR>
-__global__ void __launch_bounds__(256) p2p_push_grads_kernel(long long n, const int* n_dev, int cap,
-                                                             const int* dst, const float* dE,
-                                                             const float* dw, P2P c, PeerF grad_in,
-                                                             PeerF gw_in) {
+__global__ void __launch_bounds__(EX_THREADS) p2p_push_grads_kernel(long long n, const int* n_dev, int cap,
+                                                                    const int* dst, const float* dE,
+                                                                    const float* dw, P2P c, PeerF grad_in,
+                                                                    PeerF gw_in) {
   constexpr int K = 4 * LPR;
   if (n_dev) n = min(n, (long long)*n_dev);
   const long long n_vec = n * LPR;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_vec;
-       t += (long long)gridDim.x * blockDim.x) {
-    const long long i = t / LPR;
-    const int sub = (int)(t - i * LPR);
-    const int s = dst[i];
-    const int o = s / cap;
-    const long long slot = (long long)c.rank * cap + (s - o * cap);
-    if (dE) st_f4(peer_sel(grad_in.p, o) + slot * K + sub * 4, ld_stream_f4(dE + i * K + sub * 4));
-    if (sub == 0) peer_sel(gw_in.p, o)[slot] = dw[i];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; t0 < n_vec; t0 += EX_UNR * stride) {
+    int s[EX_UNR];
+    float4 v[EX_UNR];
+    float w[EX_UNR];
+#pragma unroll
+    for (int u = 0; u < EX_UNR; ++u) {
+      const long long t = t0 + u * stride;
+      const long long i = t / LPR;
+      const int sub = (int)(t - i * LPR);
+      s[u] = -1;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w[u] = 0.f;
+      if (t < n_vec) {
+        s[u] = dst[i];
+        if (dE) v[u] = ld_stream_f4(dE + i * K + sub * 4);
+        if (sub == 0) w[u] = dw[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EX_UNR; ++u) {
+      if (s[u] < 0) continue;
+      const int sub = (int)((t0 + u * stride) % LPR);
+      const int o = s[u] / cap;
+      const long long slot = (long long)c.rank * cap + (s[u] - o * cap);
+      if (dE) st_f4(peer_sel(grad_in.p, o) + slot * K + sub * 4, v[u]);
+      if (sub == 0) peer_sel(gw_in.p, o)[slot] = w[u];
+    }
   }
   p2p_signal(c, 2);
 }
@@ -360,15 +412,13 @@ __global__ void __launch_bounds__(256) p2p_push_grads_kernel(long long n, const 
 int p2p_push_grads(long long n, const int* n_dev, int K, int cap, const int* dst, const float* dE,
                    const float* dw, const P2P& c, const PeerF& grad_in, const PeerF& gw_in, cudaStream_t st) {
   ProfTag tag("p2p_push_grads");
-  int grid = cdiv(n * (K / 4 > 0 ? K / 4 : 1), 256);
-  if (grid > 148 * 16) grid = 148 * 16;
-  if (grid < 1) grid = 1;
+  const int grid = ex_grid(n * (K / 4 > 0 ? K / 4 : 1));
   switch (K) {
-    case 4: B200_LAUNCH(p2p_push_grads_kernel<1>, grid, 256, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
-    case 8: B200_LAUNCH(p2p_push_grads_kernel<2>, grid, 256, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
-    case 16: B200_LAUNCH(p2p_push_grads_kernel<4>, grid, 256, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
-    case 32: B200_LAUNCH(p2p_push_grads_kernel<8>, grid, 256, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
-    case 64: B200_LAUNCH(p2p_push_grads_kernel<16>, grid, 256, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
+    case 4: B200_LAUNCH(p2p_push_grads_kernel<1>, grid, EX_THREADS, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
+    case 8: B200_LAUNCH(p2p_push_grads_kernel<2>, grid, EX_THREADS, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
+    case 16: B200_LAUNCH(p2p_push_grads_kernel<4>, grid, EX_THREADS, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
+    case 32: B200_LAUNCH(p2p_push_grads_kernel<8>, grid, EX_THREADS, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
+    case 64: B200_LAUNCH(p2p_push_grads_kernel<16>, grid, EX_THREADS, 0, st, n, n_dev, cap, dst, dE, dw, c, grad_in, gw_in); break;
     default: set_error("p2p exchange supports embeddingDim in {4,8,16,32,64}, got %d", K); return B200REC_ERR_ARG;
   }
   B200_CHECK_LAUNCH();

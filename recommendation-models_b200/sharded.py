@@ -440,10 +440,10 @@ def bench(args, pkg):
     cap = None
     if use_p2p:
         # bucket capacity of the dedup'd exchange from the data: largest per-owner count of distinct ids
-        # over the first batches, +30 % (the NCCL path exchanges every non-zero and keeps N/G * 1.25);
+        # over the run's batches, +30 % (the NCCL path exchanges every non-zero and keeps N/G * 1.25);
         # overflow is still flagged on the device and reported in the result line
         need = 0
-        for f in batches[:8]:
+        for f in batches:   # every batch the run will cycle through
             u = np.unique(f)
             need = max(need, int(np.bincount(spec.owner(u), minlength=world).max()))
         t = torch.tensor([need], device=dev)
