@@ -187,6 +187,18 @@ int b200rec_step_dev(b200rec_model_t m, b200rec_table_t t, int batch_size,
 /* The training step replays as a CUDA graph after one eager warm-up per (batch size, table); 0 turns
  * that off (plain stream launches). */
 int b200rec_model_set_graph(b200rec_model_t m, int enabled);
+/* Batch builder (host code): libsvm ("<label> <key>:<value> ...", format 0) or libffm
+ * ("<label> <field>:<key>:<value> ...", format 1) text, one sample per line, to the COO arrays the
+ * path takes -- rec/data/SampleParser.scala:23-51 / :53-85.  Non-zero i of sample r becomes
+ * index[i] = r, feats[i] = key - 1 (keys are 1-based in files, :37 / :69), in file order
+ * (sample-major).  fields (libffm) and values may be NULL.  With every output NULL the call only
+ * counts (*n_samples, *nnz) so the caller can size the arrays.  Malformed text -> B200REC_ERR_ARG
+ * naming the line (the reference throws NumberFormatException); a key outside [1, 2^31] ->
+ * B200REC_ERR_INDEX.  `text` need not be NUL-terminated; blank lines are skipped. */
+int b200rec_parse_samples(int format, const char* text, int64_t n_bytes, int64_t cap_samples,
+                          int64_t cap_nnz, float* targets, int* index, int* feats, int* fields,
+                          float* values, int64_t* n_samples, int64_t* nnz);
+
 /* b200rec_step with input prefetch: _stage_batch copies a batch's ids and labels (pinned host memory,
  * or the copy does not overlap; the arrays must stay valid until the matching _step_staged returns)
  * to the device on a copy stream and returns at once; _step_staged runs the step on the batch staged

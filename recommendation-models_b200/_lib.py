@@ -76,6 +76,8 @@ SIGNATURES = {
     "b200rec_model_side_stream": [vp, C.c_int, C.POINTER(vp)],
     "b200rec_side_fork_dev": [vp, C.c_int, vp],
     "b200rec_side_rejoin_dev": [vp, C.c_int],
+    "b200rec_parse_samples": [C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, c_i64_p,
+                              c_i64_p],
     "b200rec_stage_batch": [vp, C.c_int, vp, vp],
     "b200rec_step_staged": [vp, vp, C.POINTER(C.c_float)],
     "b200rec_step_staged_async": [vp, vp],
