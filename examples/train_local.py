@@ -38,21 +38,21 @@ def main():
     fc = [int(x) for x in a.fcDims.split(",") if x]
     cin = [int(x) for x in a.cinDims.split(",") if x]
     if a.input:
-        lines = open(a.input).read().splitlines()
+        text = open(a.input, "rb").read()
     else:
         _, feats = b.synth.make_feats(1234, 0, a.samples, F, a.inputDim)
-        lines = b.data.to_libsvm(feats, b.synth.make_targets(1234, feats, a.samples, F), F)
+        text = "\n".join(b.data.to_libsvm(feats, b.synth.make_targets(1234, feats, a.samples, F), F)).encode()
+    # the whole file through the native parser (b200rec_parse_samples), then mini-batches of whole samples
+    index, cols_all, _, targets_all = b.data.parse_text(text, "libsvm")
+    if len(targets_all) * F != len(cols_all) or not np.array_equal(index, np.repeat(np.arange(len(targets_all)), F)):
+        raise ValueError("every sample needs exactly nFields features")
     model = b.make_model(a.model, F, K, fc, cin if a.model == "xdeepfm" else (), a.crossDepth)
     table = b.EmbeddingTable(a.inputDim, K if a.model != "lr" else 0)
     table.init_uniform(42)
     ps = b.ParRecModel(model, table)
     ps.setParams(np.array([0.0], np.float32), b.synth.init_mats(42, model.getMatsSize()))
-    batches = []
-    for i in range(0, len(lines), a.batchSize):
-        index, cols, _, targets = b.data.parse(lines[i:i + a.batchSize], "libsvm")
-        if len(targets) * F != len(cols):
-            raise ValueError("every sample needs exactly nFields features")
-        batches.append((cols, targets))
+    batches = [(cols_all[i * F:(i + a.batchSize) * F], targets_all[i:i + a.batchSize])
+               for i in range(0, len(targets_all), a.batchSize)]
     for epoch in range(1, a.epochs + 1):
         t0 = time.time()
         loss_sum, n = 0.0, 0
