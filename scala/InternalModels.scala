@@ -48,3 +48,39 @@ class InternalDCNModel(nFields: Int, embeddingDim: Int, crossDepth: Int, fcDims:
 
 class InternalPNNModel(nFields: Int, embeddingDim: Int, fcDims: Array[Int])
   extends B200InternalModel(Kind.PNN, nFields, embeddingDim, fcDims, Array.empty, 0)
+
+/** The resident replacement of ParRecModel's pull / optimize / push cycle
+  * (rec/model/ParRecModel.scala:439-478): table and dense params live on the GPU, a step is one call.
+  * `stage` + `stepAsync` + `waitLoss` is the asynchronous form (cf. asyncPullEmbeddings /
+  * asyncPushEmbedding, :193-196, :261-264): the next batch is copied under the running step and every
+  * loss still reaches the JVM, one step late.  Arrays passed to `stage` must be direct / pinned
+  * buffers that stay alive until the matching `waitLoss` (JNA `Memory`), not JVM heap arrays. */
+class B200ResidentTrainer(model: Pointer, table: Pointer) {
+  def optimize(batchSize: Int, feats: Array[Int], targets: Array[Float]): Float = {
+    val loss = new FloatByReference()
+    check(lib.b200rec_step(model, table, batchSize, feats, targets, loss))
+    loss.getValue * batchSize                       // ParRecModel.scala:477 returns loss * batchSize
+  }
+  def stage(batchSize: Int, feats: Pointer, targets: Pointer): Unit =
+    check(lib.b200rec_stage_batch(model, batchSize, feats, targets))
+  def stepAsync(): Unit = check(lib.b200rec_step_staged_async(model, table))
+  def waitLoss(): Float = {
+    val loss = new FloatByReference()
+    check(lib.b200rec_step_wait(model, table, loss))
+    loss.getValue
+  }
+}
+
+/** rec/data/SampleParser.scala:23-85 through the native, multi-threaded parser. */
+object B200SampleParser {
+  def parse(text: Array[Byte], libffm: Boolean): (Array[Int], Array[Int], Array[Float], Array[Float]) = {
+    val ns = new com.sun.jna.ptr.LongByReference(); val nz = new com.sun.jna.ptr.LongByReference()
+    check(lib.b200rec_parse_samples(if (libffm) 1 else 0, text, text.length, 0, 0, null, null, null, null, null, ns, nz))
+    val targets = new Array[Float](ns.getValue.toInt)
+    val index = new Array[Int](nz.getValue.toInt); val feats = new Array[Int](nz.getValue.toInt)
+    val values = new Array[Float](nz.getValue.toInt)
+    check(lib.b200rec_parse_samples(if (libffm) 1 else 0, text, text.length, targets.length, index.length,
+      targets, index, feats, null, values, ns, nz))
+    (index, feats, values, targets)
+  }
+}
