@@ -754,6 +754,7 @@ __global__ void __launch_bounds__(THREADS) pack_linear_multi_kernel(PackJobs job
 // barriers: full[0..1] (256 arrivals), empty[0..1] (tcgen05.commit), bfull[0..2] (tx bytes), drained.
 // ----------------------------------------------------------------------------------------------------
 constexpr int WS_THREADS = 32 + THREADS;
+constexpr int KC_SHORT = 8;
 #ifdef B200_TC_TRACE
 // debug timeline of CTA (0,0,0): [role][kb][slot] clock64 stamps (built only into libb200rec_trace.so)
 __device__ long long g_tc_trace[3 * 512 * 4];
@@ -801,6 +802,10 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
   const int n0 = blockIdx.x * n_stride;
   const Sched s = sched.for_split(blockIdx.z);
   const int nkb = s.nkb();
+  // A contraction of at most KC_SHORT K-blocks (K <= 256) stays in ONE accumulation: the truncation
+  // drift is linear in K (5.7e-5 at K = 8192 -> 1.8e-6 at 256, the level of the 3xTF32 split itself),
+  // so the P -> S drain would buy nothing (CIN dx0 runs 7-stage CTAs).
+  if (nkb <= KC_SHORT) kc = 0;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_full, THREADS); mbar_init(bar_full + 8, THREADS);
