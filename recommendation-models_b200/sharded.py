@@ -179,9 +179,10 @@ class ShardedParRecModel:
 class P2PShardedParRecModel:
     """The same step with the exchange over NVLink peer memory (csrc/p2p.cu) instead of NCCL: kernels
     store ids / rows / gradients straight into the peers' symmetric buffers and order them with
-    release/acquire flags; the dense gradients are summed by a one-shot allreduce over peer loads.
-    No NCCL call is left in the step, so the whole step (side-stream sorts included) is captured in
-    a CUDA graph per step parity and replayed (`load` + `step`).  Buffers come from torch symmetric
+    release/acquire flags; the dense gradients are summed over peer memory too (one-shot up to 3
+    GPUs, reduce-scatter + broadcast from 4).  No NCCL call is left in the step, so the whole step
+    (side-stream sorts, the next batch's id dispatch and the allreduce included) is captured in a
+    CUDA graph per position in the 4-deep ids ring and replayed (`load` + `step`).  Buffers come from torch symmetric
     memory (plumbing: it maps every rank's allocation into this process)."""
 
     def __init__(self, ops, dist, spec, batch, n_fields, dim, cap=None, group=None):
@@ -207,9 +208,9 @@ class P2PShardedParRecModel:
         # ids ring, 4 deep: while step t runs, peers may already store the ids of step t + 1 (dispatched
         # one step ahead), buffer t - 1 may still be read by a slower owner, and buffer t + 3 is reset
         self.ids_in = [symm(n, torch.int32, -1) for _ in range(4)]
-        self.rows_in = symm(n * dim, torch.float32, 0)
+        self.rows_in = symm(max(1, n * dim), torch.float32, 0)
         self.w_in = symm(n, torch.float32, 0)
-        self.grad_in = symm(n * dim, torch.float32, 0)
+        self.grad_in = symm(max(1, n * dim), torch.float32, 0)
         self.gw_in = symm(n, torch.float32, 0)
         self.n_dense = ops.dense_grads().numel()
         self.dense_in = symm((self.n_dense + 3) // 4 * 4, torch.float32, 0)
