@@ -3,6 +3,8 @@
 //   rec/model/encoder/HigherOrderEncoder.scala:34-58) and the CIN layer forward / backward
 //   (rec/model/xdeepfm/CINEncoder.scala:60-103,150-157).
 #include "tc_gemm.cuh"
+#include "tc_cin_fused.cuh"
+#include <cstdlib>
 #include "gemm_simt.cuh"
 #include "kernels.h"
 
@@ -243,6 +245,39 @@ int tc_cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x
                        tc::EpBiasAct{x_out, C, b, true}, passes, st);
 }
 
+// Both CIN input gradients from one persistent short-K GEMM per row tile (tc_cin_fused.cuh) whenever the
+// layer fits it (F <= 40 fields, C <= 256); B200REC_CIN_FUSED=0 keeps the two-GEMM path below.
+static bool cin_fused_enabled() {
+  static const bool on = [] { const char* e = std::getenv("B200REC_CIN_FUSED"); return !(e && e[0] == '0'); }();
+  return on;
+}
+static int tc_cin_bwd_inputs_fused(int R, int F, int H, int C, const float* x0, const float* x_in,
+                                   const float* W, const float* gy, float* gx_in, bool gx_in_acc, float* gx0,
+                                   int passes, cudaStream_t st) {
+  const int nkb = cdiv(C, BK), n_tiles = cdiv(H, DZ_JT);
+  B200_REQUIRE(tl_pack, B200REC_ERR_STATE, "no weight-pack buffer bound to this thread");
+  B200_TRY(tl_pack->reserve((size_t)n_tiles * nkb * DZ_B_STAGE));
+  char* blob = tl_pack->as<char>();
+  B200_LAUNCH_NAMED("tc_pack_weights", dz_pack_kernel, dim3(n_tiles, nkb), THREADS, 0, st, F, H, C, W, blob);
+  RowProd<4, KPlain> ap{gy, C, R, BM, (C % 4 == 0) && aligned16(gy)};
+  const int smem = dz_smem_bytes();
+  if (passes == 3) {
+    auto k = cin_dz_kernel<3>;
+    static bool attr_done = false;
+    if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_done = true; }
+    B200_LAUNCH_NAMED("tc_cin_dz", k, cdiv(R, BM), WS_THREADS, smem, st, R, F, H, C, x0, x_in, ap, (const char*)blob,
+                      gx_in, gx_in_acc, gx0);
+  } else {
+    auto k = cin_dz_kernel<1>;
+    static bool attr_done = false;
+    if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_done = true; }
+    B200_LAUNCH_NAMED("tc_cin_dz", k, cdiv(R, BM), WS_THREADS, smem, st, R, F, H, C, x0, x_in, ap, (const char*)blob,
+                      gx_in, gx_in_acc, gx0);
+  }
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
 // layer backward (gy already ReLU-masked):
 //   gW[c, (i,j)] = sum_r gy[r,c] x0[r,i] x_in[r,j]          (split-K over r, fixed-order reduce)
 //   gx0[r,i]    += sum_j (gy W)[r,(i,j)] x_in[r,j]           (one N tile per field, row-dot epilogue)
@@ -268,6 +303,8 @@ int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x
     B200_TRY(splitk_reduce(ws, splits, MN, 1.0f, false, gW, st));
     B200_TRY(colsum(R, C, gy, 1.0f, false, gb, ws + (size_t)splits * MN, st));
   }
+  if (cin_fused_enabled() && F <= DZ_FP && C <= KC_SHORT * BK)
+    return tc_cin_bwd_inputs_fused(R, F, H, C, x0, x_in, W, gy, gx_in, gx_in_acc, gx0, passes, st);
   {  // ---- gx0: per field i, T_i[r, j] = sum_c gy[r,c] W[c, i*H + j];  gx0[r,i] += <T_i[r,:], x_in[r,:]>
      //      (one N tile per field: full-width MMAs; T = dZ stays in TMEM, the x tile is staged in smem)
     const int bn = round16(H);
