@@ -283,6 +283,8 @@ def run_b200(args):
                 ach = amount / (ms_step * 1e-3) / 1e9
                 row.update(bound="hbm", achieved=round(ach, 1), peak=pk["hbm"], unit="GB/s",
                            frac=round(ach / pk["hbm"], 4), algorithmic_bytes=amount)
+                if ach > pk["hbm"]:
+                    row["note"] = "above the HBM copy peak: part of the operands was still in L2 from the producing kernel"
             else:
                 ach = amount / (ms_step * 1e-3) / 1e12
                 row.update(bound="tensor", achieved=round(ach, 2), peak=tf32_peak, unit="TFLOP/s",
