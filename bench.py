@@ -3,8 +3,12 @@
 excluded) for DeepFM / xDeepFM on synthetic Criteo-shaped data (BASELINE.json), plus the roofline
 of the dominant kernel and the CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model deepfm|xdeepfm|fm|dcn|pnn|lr]
-    python bench.py --impl reference ...        # the CPU restatement of the reference path
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model both|deepfm|xdeepfm|fm|dcn|pnn|lr]
+    python bench.py --impl reference ...        # the CPU baseline of the reference path
+
+Default (--model both): the line's value / e2e / roofline / cpu_baseline are DeepFM (BASELINE configs[1] at
+N = 1, configs[4] -- the 100 M-row row-sharded table -- at N > 1) and the key "xdeepfm" holds the same
+record for xDeepFM (configs[2]) measured in the same invocation: BASELINE.json's metric names both.
 
 One "step" = ParRecModel.optimize for one batch (rec/model/ParRecModel.scala:439-478) without the PS
 RPC: lookup (gather) -> forward -> backward -> per-id gradient scatter-add.
@@ -150,13 +154,30 @@ def algorithmic_work(kind, fc, cin, depth, B, U):
     return w
 
 
+def default_rows(args):
+    """BASELINE configs[1] (N = 1): 39 * 2^18 ids; configs[4] (row-sharded, N > 1): 100 M ids."""
+    if args.rows:
+        return args.rows
+    return 39 * (1 << 18) if args.gpus == 1 else 100_000_000
+
+
+def model_list(args):
+    return ["deepfm", "xdeepfm"] if args.model == "both" else [args.model]
+
+
+def workload(name, args, rows):
+    """config.workload -- the SAME string in the B200 arm and the reference arm."""
+    kind, fc, cin, depth = MODELS[name]
+    base = f"{name} k={K} F={F} fc={fc} cin={cin} depth={depth}"
+    if args.gpus == 1:
+        return f"{base} batch={args.batch} table_rows={rows}"
+    return f"{base} per-GPU batch={args.batch} table_rows={rows} row-sharded over {args.gpus} GPUs"
+
+
 def run_b200(args):
     import torch
     import __graft_entry__ as g
     pkg = g.load_package()
-    L = pkg._lib
-    synth = pkg.synth
-    rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world != args.gpus:
@@ -166,9 +187,20 @@ def run_b200(args):
     if world > 1 or args.force_sharded:
         from recommendation_models_b200 import sharded  # noqa: F401  (registered by load_package)
         return sharded.bench(args, pkg)
+    names = model_list(args)
+    out = measure_1gpu(args, names[0], pkg, torch, local)
+    for extra in names[1:]:
+        out[extra] = measure_1gpu(args, extra, pkg, torch, local)
+    print(json.dumps(out))
 
-    kind, fc, cin, depth = MODELS[args.model]
-    B, rows = args.batch, args.rows
+
+def measure_1gpu(args, name, pkg, torch, local):
+    """One model on one GPU: device-timed value, e2e through the host-facing calls, per-kernel roofline,
+    the literal drop-in call with host arrays, CPU baseline."""
+    L = pkg._lib
+    synth = pkg.synth
+    kind, fc, cin, depth = MODELS[name]
+    B, rows = args.batch, default_rows(args)
     model = pkg.make_model(kind, F, K, fc, cin, depth, device=local)
     if args.gemm_mode is not None:
         model.setGemmMode(args.gemm_mode)
@@ -249,6 +281,34 @@ def run_b200(args):
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
 
+    # ---- the literal drop-in call: Internal<M>Model.backward with HOST arrays (DeepFM.scala:83-124) ---
+    # index / weights / bias / embedding / mats / targets go in over PCIe, the four gradient arrays and the
+    # loss come back, every call (the reference's PS-worker flow keeps all of them on the host)
+    dropin = None
+    if kind != "lr":
+        nd = max(3, min(Ksteps, 10))
+        feats0 = batches[0][0]
+        index = np.repeat(np.arange(B, dtype=np.int32), F)
+        emb0 = synth.table_rows(SEED_PARAMS, feats0, K).reshape(-1)
+        w0 = synth.wtable_rows(SEED_PARAMS, feats0)
+        tg = batches[0][1]
+        mt = mats if mats.size else None
+        times = []
+        for i in range(nd + 2):
+            a = (w0.copy(), np.array([0.1], np.float32), emb0.copy(), None if mt is None else mt.copy())
+            t0 = time.perf_counter()
+            model.backward(B, index, a[0], a[1], a[2], a[3], tg)
+            if i >= 2:
+                times.append(time.perf_counter() - t0)
+        nbytes_in = index.nbytes + w0.nbytes + 4 + emb0.nbytes + mats.nbytes + tg.nbytes
+        nbytes_out = w0.nbytes + 4 + emb0.nbytes + mats.nbytes + 4
+        dropin = {"value": round(B / statistics.median(times), 1), "unit": "samples/s",
+                  "ms_per_call": round(1e3 * statistics.median(times), 4), "calls": nd,
+                  "h2d_bytes_per_step": int(nbytes_in), "d2h_bytes_per_step": int(nbytes_out),
+                  "call": "b200rec_backward(batchSize, index, weights, bias, embedding, mats, targets) with pageable host "
+                          "arrays in and the gradients written back over them (INTEGRATION.md section 2, row 1); rows "
+                          "already gathered by the caller, as in the reference's PS-worker flow"}
+
     # ---- per-kernel pass for the roofline (separate from the timed region above) -------------------
     L.profile_begin()
     for i in range(Ksteps):
@@ -261,11 +321,11 @@ def run_b200(args):
     pk = peaks()
     work = algorithmic_work(kind, fc, cin, depth, B, U)
     by_phase = {}
-    for tag, name, cnt, ms in prof:
+    for tag, kname, cnt, ms in prof:
         d = by_phase.setdefault(tag, dict(ms=0.0, launches=0, kernels={}))
         d["ms"] += ms
         d["launches"] += cnt
-        k = d["kernels"].setdefault(name, [0, 0.0])
+        k = d["kernels"].setdefault(kname, [0, 0.0])
         k[0] += cnt
         k[1] += ms
     kernels = []
@@ -295,7 +355,7 @@ def run_b200(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     dom = next((r for r in kernels if "bound" in r), None)
     if os.path.exists(tpath) and dom:
-        traffic = json.load(open(tpath)).get(args.model, {}).get(dom["phase"])
+        traffic = json.load(open(tpath)).get(name, {}).get(dom["phase"])
     roofline = None
     if dom:
         roofline = dict(kernel=dom["phase"], bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"],
@@ -308,8 +368,8 @@ def run_b200(args):
         "unit": "samples/s", "n_gpus": 1, "steps": Ksteps, "warmup": W,
         "ms_per_step": round(ms_total / Ksteps, 5), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} k={K} F={F} fc={fc} cin={cin} depth={depth} batch={B} "
-                               f"table_rows={rows} (BASELINE configs[{ {'deepfm': 1, 'xdeepfm': 2}.get(args.model, 3)}])",
+        "config": {"workload": workload(name, args, rows),
+                   "baseline_config": {"deepfm": "configs[1]", "xdeepfm": "configs[2]", "fm": "configs[0]"}.get(name, "configs[3]"),
                    "global_batch": B, "ids": "power-law, one per field, new batch every step",
                    "l2": f"table {rows * K * 4 / 1e6:.0f} MB > 126 MB L2; distinct ids per step; no explicit flush",
                    "parallelism": "1 GPU", "gemm_mode": args.gemm_mode, "cuda_graph": not args.no_graph, "seed_data": SEED_DATA,
@@ -318,91 +378,80 @@ def run_b200(args):
         "e2e": {"value": round(B * Ksteps / e2e_s, 1), "unit": "samples/s", "h2d_bytes_per_step": B * F * 4 + B * 4,
                 "d2h_bytes_per_step": 32, "call": "b200rec_stage_batch (next batch, pinned host ids + labels) + b200rec_step_staged_async + b200rec_step_wait (every loss read by the host, one step late)",
                 "last_loss": round(float(last), 6)},
+        "e2e_dropin": dropin,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "kernels": kernels,
     }
-    if not args.no_cpu:
-        out["cpu_baseline"] = cpu_reference(args, budget_s=args.cpu_seconds)["cpu_baseline"]
-    print(json.dumps(out))
     model.close()
     table.close()
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_reference(args, name, budget_s=args.cpu_seconds)["cpu_baseline"]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
-# The reference arm: the CPU restatement of the reference's path (oracle/refport.py), all host
-# threads (numpy/OpenBLAS for the sgemm BigDL would send to MKL).  The reference itself is Scala on
-# a JVM with un-vendored BigDL/Angel jars and cannot be built or run here.
+# The reference arm: the CPU baseline of the reference's path (oracle/cbaseline.{cpp,py}; BASELINE.md
+# section 3): fastutil-style open-addressing hash maps for the gather and the scatter-add, the BigDL module graph
+# pass by pass with MKL sgemm (torch-CPU), per-step copies of the dense params.  Two variants: 1
+# thread (the reference's own configuration) and all usable host threads; the line's value is the
+# FASTER one.  The reference itself is Scala on a JVM with un-vendored BigDL/Angel jars and cannot be
+# built or run here.
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(args, budget_s=15.0, steps=None, warmup=1):
+def cpu_reference(args, name, budget_s=12.0, steps=None, warmup=1):
     import __graft_entry__ as g
     pkg = g.load_package()
     synth = pkg.synth
-    from oracle import refport
-    kind, fc, cin, depth = MODELS[args.model]
-    B, rows = args.batch, args.rows
+    from oracle import cbaseline
+    kind, fc, cin, depth = MODELS[name]
+    B, rows = args.batch, default_rows(args)
     # bounded sample: full batches for the MLP-only models; CIN at B=8192 needs a 4 GB Z per layer
     # on the CPU (the reference materialises it, CINEncoder.scala:152), so it is sampled at B/16.
     Bs = B if kind != "xdeepfm" else max(64, B // 16)
-    o = refport.Model(kind, F, K, fc, cin, depth)
-    mats = synth.init_mats(SEED_PARAMS, o.mats_size())
-    times = []
-    n_done = 0
-    t_start = time.perf_counter()
-    step = 0
-    while True:
-        index, feats = synth.make_feats(SEED_DATA, step, Bs, F, rows)
-        targets = synth.make_targets(SEED_DATA, feats, Bs, F)
-        ids = np.unique(feats)
-        # the PS pull (rows of the distinct ids) is outside the path: untimed
-        E = synth.table_rows(SEED_PARAMS, ids, K)
-        wv = synth.wtable_rows(SEED_PARAMS, ids)
-        t0 = time.perf_counter()
-        pos = np.searchsorted(ids, feats)
-        emb = refport.make_embeddings(E, pos) if kind != "lr" else None       # makeEmbeddings
-        ww = refport.make_weights(wv, pos)                                     # makeWeights
-        bias = np.array([0.1], np.float32)
-        m = mats.copy() if mats.size else None                                 # makeMats (per-step copy)
-        o.backward(Bs, index, ww, bias, emb, m, targets)                       # Internal<M>Model.backward
-        if emb is not None:
-            refport.make_embedding_grad(emb, feats, K)                         # makeEmbeddingGrad
-        refport.make_weights_grad(ww, feats)                                   # makeWeightsGrad
-        dt = time.perf_counter() - t0
-        step += 1
-        if step > warmup:
-            times.append(dt)
-            n_done += 1
-        if steps is not None and n_done >= steps:
-            break
-        if time.perf_counter() - t_start > budget_s and n_done >= 2:
-            break
-    sec = sum(times)
-    value = Bs * n_done / sec
-    cores = os.cpu_count()
-    return dict(value=value, ms_per_step=1e3 * sec / n_done, steps=n_done, Bs=Bs,
-                cpu_baseline=dict(value=round(value, 1), unit="samples/s", cores=cores, kind="port",
-                                  sample=f"{n_done} steps of batch {Bs} ({args.model}; numpy/OpenBLAS, all host threads)"))
+    ncores = cbaseline.host_threads()
+    common = (kind, F, K, fc, cin, depth, Bs, rows, synth, SEED_DATA, SEED_PARAMS)
+    r_all = cbaseline.run_steps(*common, threads=ncores, budget_s=budget_s * 0.65, max_steps=steps, warmup=warmup)
+    r_one = cbaseline.run_steps(*common, threads=1, budget_s=budget_s * 0.35, max_steps=None if steps is None else max(2, steps // 4),
+                                warmup=1)
+    best = r_all if r_all["value"] >= r_one["value"] else r_one
+    def slim(r):
+        return dict(value=round(r["value"], 1), ms_per_step=round(r["ms_per_step"], 3), steps=r["steps"],
+                    threads=r["threads"], phases_ms=r["phases_ms"])
+    return dict(value=best["value"], ms_per_step=best["ms_per_step"], steps=best["steps"], Bs=Bs,
+                cpu_baseline=dict(value=round(best["value"], 1), unit="samples/s", cores=best["threads"], kind="port",
+                                  sample=f"{best['steps']} steps of batch {Bs} ({name}; C++ open-addressing hash maps for "
+                                         f"gather / scatter-add, BigDL module graph with {best['blas']}; the faster of the "
+                                         f"1-thread and the {ncores}-thread variant)",
+                                  host_threads_available=ncores,
+                                  variants={"threads_1": slim(r_one), "threads_all": slim(r_all)}))
+
+
+def reference_record(args, name):
+    rows = default_rows(args)
+    # each step is one bounded sample of the same workload; the run is bounded to ~1.5 minutes per model
+    r = cpu_reference(args, name, steps=args.steps, warmup=min(args.warmup, 2), budget_s=90.0)
+    return {
+        "impl": "reference", "metric": "train samples/sec (fwd+bwd)", "value": round(r["value"], 1),
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+        "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload(name, args, rows), "global_batch": args.batch * args.gpus,
+                   "note": "CPU baseline of the reference path on this box's host cores (one process; a multi-GPU run is "
+                           "compared with the same single host); the Scala/BigDL/Angel reference cannot be built or run "
+                           "here (no JVM, un-vendored jars)"},
+        "cpu_baseline": r["cpu_baseline"],
+        "e2e": {"value": round(r["value"], 1), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    kind, fc, cin, depth = MODELS[args.model]
-    # each step is one full batch of the same workload; the run is bounded to ~2 minutes
-    r = cpu_reference(args, steps=args.steps, warmup=min(args.warmup, 3), budget_s=120.0)
-    out = {
-        "impl": "reference", "metric": "train samples/sec (fwd+bwd)", "value": round(r["value"], 1),
-        "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
-        "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} k={K} F={F} fc={fc} cin={cin} depth={depth} batch={args.batch} "
-                               f"table_rows={args.rows}", "global_batch": args.batch,
-                   "note": "CPU restatement of the reference path (oracle port); the Scala/BigDL/Angel reference "
-                           "cannot be built or run here (no JVM, un-vendored jars)"},
-        "cpu_baseline": r["cpu_baseline"],
-        "e2e": {"value": round(r["value"], 1), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
+    names = model_list(args)
+    out = reference_record(args, names[0])
+    for extra in names[1:]:
+        out[extra] = reference_record(args, extra)
     print(json.dumps(out))
 
 
@@ -412,9 +461,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="deepfm", choices=list(MODELS))
+    ap.add_argument("--model", default="both", choices=["both"] + list(MODELS),
+                    help="both = DeepFM as the headline record + an 'xdeepfm' sub-record (BASELINE.json's metric names both)")
     ap.add_argument("--batch", type=int, default=8192)
-    ap.add_argument("--rows", type=int, default=39 * (1 << 18))
+    ap.add_argument("--rows", type=int, default=0, help="table rows; default 39*2^18 at N=1, 100 000 000 at N>1")
     ap.add_argument("--gemm-mode", type=int, default=None, help="0 fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--force-sharded", dest="force_sharded", action="store_true",
@@ -423,7 +473,7 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: NVLink peer-memory exchange fused into the kernels, or NCCL all-to-all")
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of the CUDA graph")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=16.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -264,7 +264,10 @@ int b200rec_segsum_inverse_dev(b200rec_model_t m, int ws, int64_t nnz, int* inv_
 /* ---- row-sharded table: the PS pull / push as NCCL all-to-all of fixed-capacity slot buffers -------
  * The Angel PS range-shards the matrices over PS nodes (ColumnRangePartitioner,
  * rec/model/ParRecModel.scala:77,81,98,116); workers pull rows (:174-177,193-196) and push gradients
- * (:247-250,261-264).  Here GPU `owner(id) = (id + id / period) % world` holds row `id / world`.
+ * (:247-250,261-264).  Here GPU `owner(id) = (id + id / period) % world` holds row `id / world`
+ * (period > 0, a multiple of world: balanced under per-field power-law ids), or -- period < 0, the
+ * reference's own ColumnRangePartitioner layout -- GPU `id / (-period)` holds row `id % (-period)`:
+ * contiguous ranges of -period rows per rank.
  * The collectives themselves are issued by the host (torch.distributed / NCCL) between these calls. */
 /* Fill a shard: local row q of `rank` holds the hash-initialised values of its global id. */
 int b200rec_table_init_uniform_sharded(b200rec_table_t t, uint64_t seed, float lo, float hi, int rank,
@@ -327,7 +330,12 @@ int b200rec_side_rejoin_dev(b200rec_model_t m, int ws);
  * not executed; every buffer must already have its final size (run the step eagerly once before). */
 int b200rec_capture_begin(b200rec_model_t m, void* stream);
 int b200rec_capture_end(b200rec_model_t m, int* graph_id, void* stream);
+/* B200REC_ERR_STATE when a workspace of the library was reallocated after the capture (the graph would
+ * replay freed addresses): run the step eagerly once and capture again. */
 int b200rec_graph_launch(b200rec_model_t m, int graph_id, void* stream);
+/* Count of device-buffer reallocations in this process; a captured graph (the library's own of the
+ * resident step, or a caller's) is valid only while it is unchanged. */
+int b200rec_alloc_epoch(int64_t* epoch);
 
 /* slot of every non-zero from the slot of its distinct id (the ids' sort of workspace `ws` links them) */
 int b200rec_p2p_compose_dst_dev(b200rec_model_t m, int ws, int64_t nnz, const int* dst_unique, int* dst,
@@ -362,6 +370,21 @@ int b200rec_table_apply_optimizer_dev(b200rec_table_t t, int optimizer, float lr
 /* Dense params of the handle (bias, mats) with the gradients of its last step. */
 int b200rec_model_apply_optimizer_dev(b200rec_model_t m, int optimizer, float lr, float p1, float p2,
                                       int64_t step, void* stream);
+/* The same two calls with the 1-based update count read from DEVICE memory (*step_dev) when the kernel
+ * runs: what a replayed CUDA graph needs (AsyncAdam.numUpdates lives on the host in the reference,
+ * rec/optim/AsyncAdam.scala:12,16-18).  b200rec_model_step_counter returns the model's own counter,
+ * advanced by b200rec_p2p_begin_step_dev. */
+int b200rec_table_apply_optimizer_stepdev_dev(b200rec_table_t t, int optimizer, float lr, float p1, float p2,
+                                              const int* step_dev, int64_t n_unique_cap,
+                                              const int* n_unique, const int* unique,
+                                              const float* emb_grad, const float* w_grad, void* stream);
+int b200rec_model_apply_optimizer_stepdev_dev(b200rec_model_t m, int optimizer, float lr, float p1, float p2,
+                                              const int* step_dev, void* stream);
+int b200rec_model_step_counter(b200rec_model_t m, int** step_dev);
+/* Deferred status of the table's device kernels since the last call: an id outside [0, rows) seen by a
+ * lookup / owner-side gather / optimizer kernel (never applied: such rows are skipped) ->
+ * B200REC_ERR_INDEX.  reset != 0 clears the word.  Synchronises `stream` (NULL: the table's stream). */
+int b200rec_table_status(b200rec_table_t t, int reset, void* stream);
 
 /* ---- the reference's own BigDL modules (updateOutput / updateGradInput / accGradParameters) */
 /* nn/Scatter.scala:17-36  output[index[i], :] += input[i, :]  (i ascending; bit-exact order). */

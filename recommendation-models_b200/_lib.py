@@ -99,6 +99,12 @@ SIGNATURES = {
     "b200rec_table_apply_optimizer_dev": [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_int64, vp, vp, vp,
                                           vp, vp],
     "b200rec_model_apply_optimizer_dev": [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int64, vp],
+    "b200rec_table_apply_optimizer_stepdev_dev": [vp, C.c_int, C.c_float, C.c_float, C.c_float, vp, C.c_int64, vp, vp,
+                                                  vp, vp, vp],
+    "b200rec_model_apply_optimizer_stepdev_dev": [vp, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp],
+    "b200rec_model_step_counter": [vp, C.POINTER(vp)],
+    "b200rec_table_status": [vp, C.c_int, vp],
+    "b200rec_alloc_epoch": [c_i64_p],
     "b200rec_scatter_update_output": [C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp, vp],
     "b200rec_scatter_update_grad_input": [C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp, vp],
     "b200rec_gather_update_output": [C.c_int] * 5 + [vp] * 5,

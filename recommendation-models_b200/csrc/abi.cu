@@ -20,6 +20,7 @@ namespace b200rec {
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_alloc_epoch{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -110,6 +111,10 @@ static int dev_status(int word, int batch_size, long long rows) {
   if (word & DEV_BAD_ID) {
     set_error("feature id outside the table's %lld rows", rows);
     return B200REC_ERR_INDEX;
+  }
+  if (word & DEV_PEER_TIMEOUT) {
+    set_error("a peer GPU's exchange flag did not arrive within B200REC_P2P_TIMEOUT_MS: the step's results are invalid");
+    return B200REC_ERR_STATE;
   }
   return B200REC_OK;
 }
@@ -467,9 +472,10 @@ int b200rec_model_sync(b200rec_model_t m) {
   B200_TRY(use_device(m->device));
   B200_CUDA(cudaStreamSynchronize(m->stream));
   B200_CUDA(cudaStreamSynchronize(m->side));
-  int word = 0;
-  B200_CUDA(cudaMemcpy(&word, m->scal.as<int>() + 4, sizeof(int), cudaMemcpyDeviceToHost));
-  return dev_status(word, m->last_B, 0);
+  int word[3] = {0, 0, 0};   // [4] err of the last run, [5] sortedness, [6] sticky exchange status
+  B200_CUDA(cudaMemcpy(word, m->scal.as<int>() + 4, 3 * sizeof(int), cudaMemcpyDeviceToHost));
+  if (word[2]) B200_CUDA(cudaMemset(m->scal.as<int>() + 6, 0, sizeof(int)));
+  return dev_status(word[0] | word[2], m->last_B, 0);
 }
 
 // ---- table ---------------------------------------------------------------------------------------
@@ -772,13 +778,21 @@ static int step_train_graphed(Model* m, Table* t, int B, const int* feats, const
   const float* tg = m->d_targets.as<float>();
   if (tl_prof) prof_delay_kernel<<<1, 1, 0, st>>>(500000ull);
   if (!m->graph_enabled || tl_prof) return step_on_device(m, t, B, f, tg, nullptr, st);
+  // The graph bakes in the addresses of the handle's workspaces.  Any call that grew one of them since
+  // the capture (b200rec_predict with a larger batch, b200rec_forward / _backward, step_rows ...) freed
+  // the old block: the allocation epoch moved and the graph must not be replayed.
+  const long long epoch = g_alloc_epoch.load();
   const bool match = m->graph_exec && m->graph_B == B && m->graph_table == (const void*)t &&
-                     m->graph_mode == m->gemm_mode;
+                     m->graph_mode == m->gemm_mode && m->graph_epoch == epoch;
   if (!match) {
-    if (m->graph_warm_B != B) {  // eager warm-up: allocations and attribute calls happen here
-      m->graph_warm_B = B;
+    if (m->graph_warm_B != B || m->graph_warm_epoch != epoch) {
+      // eager warm-up: allocations and attribute calls happen here; the capture follows once a whole
+      // eager step has run without moving the epoch again
       if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
-      return step_on_device(m, t, B, f, tg, nullptr, st);
+      const int s0 = step_on_device(m, t, B, f, tg, nullptr, st);
+      m->graph_warm_B = B;
+      m->graph_warm_epoch = g_alloc_epoch.load();
+      return s0;
     }
     if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
@@ -800,6 +814,13 @@ static int step_train_graphed(Model* m, Table* t, int B, const int* feats, const
     m->graph_nodes = (int)(g_launches.load() - l0);   // launches recorded, not executed, by the capture
     g_launches.fetch_sub(m->graph_nodes);
     m->graph_B = B; m->graph_table = (const void*)t; m->graph_mode = m->gemm_mode;
+    m->graph_epoch = g_alloc_epoch.load();
+    if (m->graph_epoch != epoch) {   // a workspace grew inside the capture: the graph is stale already
+      cudaGraphExecDestroy(m->graph_exec);
+      m->graph_exec = nullptr;
+      m->graph_warm_epoch = -1;
+      return step_on_device(m, t, B, f, tg, nullptr, st);
+    }
     m->last_B = B; m->last_nnz = nnz;
   }
   B200_CUDA(cudaGraphLaunch(m->graph_exec, st));
@@ -1105,8 +1126,8 @@ int b200rec_table_init_uniform_sharded(b200rec_table_t t, uint64_t seed, float l
                                        int world, int64_t period) {
   B200_REQUIRE(t, B200REC_ERR_ARG, "NULL table");
   B200_REQUIRE(world >= 1 && rank >= 0 && rank < world, B200REC_ERR_ARG, "bad rank %d / world %d", rank, world);
-  B200_REQUIRE(period >= world && period % world == 0, B200REC_ERR_ARG,
-               "shard period must be a positive multiple of the world size");
+  B200_REQUIRE(shard_period_ok(world, period), B200REC_ERR_ARG,
+               "shard period must be a positive multiple of the world size, or negative (-rows per rank: contiguous ranges)");
   B200_TRY(use_device(t->device));
   B200_TRY(table_init_uniform_sharded(t->emb.as<float>(), t->w.as<float>(), t->rows, t->dim ? t->dim : 1,
                                       seed, lo, hi, rank, world, period, t->stream));
@@ -1192,7 +1213,8 @@ int b200rec_p2p_wait_dev(b200rec_model_t m, const int* flags_local, int phase, i
   void* none[P2P_MAX] = {};
   B200_TRY(fill_p2p(m, world, 0, step, none, c));
   B200_TRY(use_device(m->device));
-  return p2p_wait(flags_local, phase, world, step, c.step_ptr, stream ? (cudaStream_t)stream : m->stream);
+  return p2p_wait(flags_local, phase, world, step, c.step_ptr, m->scal.as<int>() + 6,
+                  stream ? (cudaStream_t)stream : m->stream);
   B200_GUARD_END
 }
 
@@ -1220,7 +1242,7 @@ int b200rec_p2p_allreduce_dev(b200rec_model_t m, int64_t n, int world, int rank,
     bufs.p[p] = (float*)peer_bufs[p];
     outs.p[p] = peer_out ? (float*)peer_out[p] : nullptr;
   }
-  return p2p_allreduce(n, inout, flags_local, c, bufs, peer_out ? &outs : nullptr,
+  return p2p_allreduce(n, inout, flags_local, c, bufs, peer_out ? &outs : nullptr, m->scal.as<int>() + 6,
                        stream ? (cudaStream_t)stream : m->stream);
   B200_GUARD_END
 }
@@ -1275,7 +1297,7 @@ int b200rec_capture_end(b200rec_model_t m, int* graph_id, void* stream) {
     set_error("graph capture failed: %s", cudaGetErrorString(e));
     return B200REC_ERR_CUDA;
   }
-  m->user_graphs.push_back({exec, nodes});
+  m->user_graphs.push_back({exec, nodes, g_alloc_epoch.load()});
   *graph_id = (int)m->user_graphs.size() - 1;
   return B200REC_OK;
 }
@@ -1283,8 +1305,22 @@ int b200rec_capture_end(b200rec_model_t m, int* graph_id, void* stream) {
 int b200rec_graph_launch(b200rec_model_t m, int graph_id, void* stream) {
   B200_REQUIRE(m && graph_id >= 0 && graph_id < (int)m->user_graphs.size(), B200REC_ERR_ARG, "bad graph id");
   B200_TRY(use_device(m->device));
-  B200_CUDA(cudaGraphLaunch(m->user_graphs[graph_id].first, stream ? (cudaStream_t)stream : m->stream));
-  g_launches.fetch_add(m->user_graphs[graph_id].second, std::memory_order_relaxed);
+  auto& g = m->user_graphs[graph_id];
+  // a workspace of the library was freed since the capture: the graph holds a dangling pointer
+  if (!g.exec || g.epoch != g_alloc_epoch.load()) {
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    set_error("graph %d is stale: device buffers were reallocated after its capture; run the step eagerly "
+              "once and capture again", graph_id);
+    return B200REC_ERR_STATE;
+  }
+  B200_CUDA(cudaGraphLaunch(g.exec, stream ? (cudaStream_t)stream : m->stream));
+  g_launches.fetch_add(g.nodes, std::memory_order_relaxed);
+  return B200REC_OK;
+}
+
+int b200rec_alloc_epoch(int64_t* epoch) {
+  B200_REQUIRE(epoch, B200REC_ERR_ARG, "epoch is NULL");
+  *epoch = (int64_t)g_alloc_epoch.load();
   return B200REC_OK;
 }
 
@@ -1348,8 +1384,8 @@ int b200rec_table_apply_sgd_dev(b200rec_table_t t, int64_t n_unique_cap, const i
                                 float lr, void* stream) {
   B200_REQUIRE(t && n_unique && unique, B200REC_ERR_ARG, "NULL argument");
   B200_TRY(use_device(t->device));
-  return apply_sgd(t->dim ? t->dim : 1, n_unique_cap, n_unique, unique, t->dim ? emb_grad : nullptr,
-                   w_grad, lr, t->emb.as<float>(), t->w.as<float>(),
+  return apply_sgd(t->dim ? t->dim : 1, t->rows, n_unique_cap, n_unique, unique, t->dim ? emb_grad : nullptr,
+                   w_grad, lr, t->emb.as<float>(), t->w.as<float>(), t->err.as<int>(),
                    stream ? (cudaStream_t)stream : t->stream);
 }
 
@@ -1361,10 +1397,10 @@ static int zeroed(DevBuf& b, size_t bytes, cudaStream_t st) {
   return B200REC_OK;
 }
 
-int b200rec_table_apply_optimizer_dev(b200rec_table_t t, int optimizer, float lr, float p1, float p2,
-                                      int64_t step, int64_t n_unique_cap, const int* n_unique,
-                                      const int* unique, const float* emb_grad, const float* w_grad,
-                                      void* stream) {
+static int table_apply_optimizer(b200rec_table_t t, int optimizer, float lr, float p1, float p2,
+                                 int64_t step, const int* step_dev, int64_t n_unique_cap,
+                                 const int* n_unique, const int* unique, const float* emb_grad,
+                                 const float* w_grad, void* stream) {
   B200_GUARD_BEGIN
   B200_REQUIRE(t && n_unique && unique, B200REC_ERR_ARG, "NULL argument");
   B200_REQUIRE(optimizer >= B200REC_OPT_SGD && optimizer <= B200REC_OPT_ADAM, B200REC_ERR_ARG,
@@ -1380,14 +1416,59 @@ int b200rec_table_apply_optimizer_dev(b200rec_table_t t, int optimizer, float lr
     B200_TRY(zeroed(t->s2e, ne, st));
     B200_TRY(zeroed(t->s2w, nw, st));
   }
-  return opt_rows(optimizer, t->dim ? t->dim : 1, n_unique_cap, n_unique, unique, t->dim ? emb_grad : nullptr,
-                  w_grad, lr, p1, p2, step, t->emb.as<float>(), t->w.as<float>(), t->s1e.as<float>(),
-                  t->s2e.as<float>(), t->s1w.as<float>(), t->s2w.as<float>(), st);
+  return opt_rows(optimizer, t->dim ? t->dim : 1, t->rows, n_unique_cap, n_unique, unique,
+                  t->dim ? emb_grad : nullptr, w_grad, lr, p1, p2, step, step_dev, t->emb.as<float>(),
+                  t->w.as<float>(), t->s1e.as<float>(), t->s2e.as<float>(), t->s1w.as<float>(),
+                  t->s2w.as<float>(), t->err.as<int>(), st);
   B200_GUARD_END
 }
 
-int b200rec_model_apply_optimizer_dev(b200rec_model_t m, int optimizer, float lr, float p1, float p2,
-                                      int64_t step, void* stream) {
+int b200rec_table_apply_optimizer_dev(b200rec_table_t t, int optimizer, float lr, float p1, float p2,
+                                      int64_t step, int64_t n_unique_cap, const int* n_unique,
+                                      const int* unique, const float* emb_grad, const float* w_grad,
+                                      void* stream) {
+  return table_apply_optimizer(t, optimizer, lr, p1, p2, step, nullptr, n_unique_cap, n_unique, unique,
+                               emb_grad, w_grad, stream);
+}
+
+int b200rec_table_apply_optimizer_stepdev_dev(b200rec_table_t t, int optimizer, float lr, float p1, float p2,
+                                              const int* step_dev, int64_t n_unique_cap,
+                                              const int* n_unique, const int* unique,
+                                              const float* emb_grad, const float* w_grad, void* stream) {
+  B200_REQUIRE(step_dev, B200REC_ERR_ARG, "step_dev is NULL");
+  return table_apply_optimizer(t, optimizer, lr, p1, p2, 0, step_dev, n_unique_cap, n_unique, unique,
+                               emb_grad, w_grad, stream);
+}
+
+// The device status word of the table (ids outside the table seen by a lookup / gather / optimizer
+// kernel since the last call); reset != 0 clears it.  Synchronises `stream` (NULL: the table's).
+int b200rec_table_status(b200rec_table_t t, int reset, void* stream) {
+  B200_REQUIRE(t, B200REC_ERR_ARG, "NULL table");
+  B200_TRY(use_device(t->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : t->stream;
+  int word = 0;
+  B200_CUDA(cudaMemcpyAsync(&word, t->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (reset) B200_CUDA(cudaMemsetAsync(t->err.p, 0, sizeof(int), st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  return dev_status(word, 0, t->rows);
+}
+
+// The model's device step counter (advanced by b200rec_p2p_begin_step_dev): lets an optimizer call
+// inside a replayed CUDA graph read the update count from the device.
+int b200rec_model_step_counter(b200rec_model_t m, int** step_dev) {
+  B200_REQUIRE(m && step_dev, B200REC_ERR_ARG, "NULL argument");
+  B200_TRY(use_device(m->device));
+  if (!m->p2p_ctr.p) {
+    B200_TRY(m->p2p_ctr.reserve(16));
+    B200_CUDA(cudaMemset(m->p2p_ctr.p, 0, 16));
+    B200_CUDA(cudaDeviceSynchronize());
+  }
+  *step_dev = m->p2p_ctr.as<int>() + 1;
+  return B200REC_OK;
+}
+
+static int model_apply_optimizer(b200rec_model_t m, int optimizer, float lr, float p1, float p2,
+                                 int64_t step, const int* step_dev, void* stream) {
   B200_GUARD_BEGIN
   B200_REQUIRE(m, B200REC_ERR_ARG, "NULL model");
   B200_REQUIRE(m->params_set && m->last_B > 0, B200REC_ERR_STATE, "no step has produced gradients yet");
@@ -1399,13 +1480,24 @@ int b200rec_model_apply_optimizer_dev(b200rec_model_t m, int optimizer, float lr
   if (optimizer != B200REC_OPT_SGD) B200_TRY(zeroed(m->s1m, n, st));
   if (optimizer == B200REC_OPT_ADAM) B200_TRY(zeroed(m->s2m, n, st));
   if (m->mats_len)
-    B200_TRY(opt_dense(optimizer, m->mats_len, m->gmats.as<float>(), lr, p1, p2, step, m->p_mats.as<float>(),
-                       m->s1m.as<float>(), m->s2m.as<float>(), st));
+    B200_TRY(opt_dense(optimizer, m->mats_len, m->gmats.as<float>(), lr, p1, p2, step, step_dev,
+                       m->p_mats.as<float>(), m->s1m.as<float>(), m->s2m.as<float>(), st));
   // bias: gradient at gmats[mats_len], slots at s*m[mats_len]
-  return opt_dense(optimizer, 1, m->gmats.as<float>() + m->mats_len, lr, p1, p2, step, m->p_bias.as<float>(),
-                   m->s1m.p ? m->s1m.as<float>() + m->mats_len : nullptr,
+  return opt_dense(optimizer, 1, m->gmats.as<float>() + m->mats_len, lr, p1, p2, step, step_dev,
+                   m->p_bias.as<float>(), m->s1m.p ? m->s1m.as<float>() + m->mats_len : nullptr,
                    m->s2m.p ? m->s2m.as<float>() + m->mats_len : nullptr, st);
   B200_GUARD_END
+}
+
+int b200rec_model_apply_optimizer_dev(b200rec_model_t m, int optimizer, float lr, float p1, float p2,
+                                      int64_t step, void* stream) {
+  return model_apply_optimizer(m, optimizer, lr, p1, p2, step, nullptr, stream);
+}
+
+int b200rec_model_apply_optimizer_stepdev_dev(b200rec_model_t m, int optimizer, float lr, float p1, float p2,
+                                              const int* step_dev, void* stream) {
+  B200_REQUIRE(step_dev, B200REC_ERR_ARG, "step_dev is NULL");
+  return model_apply_optimizer(m, optimizer, lr, p1, p2, 0, step_dev, stream);
 }
 
 // ---- the reference's own BigDL modules -------------------------------------------------------------

@@ -98,12 +98,19 @@ struct ProfTag {  // names the phase the following launches belong to
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- device buffer that grows on demand ---------------------------------------------------------
+// g_alloc_epoch counts the times a buffer that already held memory was FREED (grown or released).
+// A captured CUDA graph bakes device pointers in: every graph remembers the epoch of its capture and
+// is re-captured (never replayed) once the epoch has moved, so a replay cannot touch freed memory.
+extern std::atomic<long long> g_alloc_epoch;
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   int reserve(size_t bytes) {
     if (bytes <= cap) return B200REC_OK;
-    if (p) cudaFree(p);
+    if (p) {
+      cudaFree(p);
+      g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
+    }
     p = nullptr;
     cap = 0;
     size_t want = bytes + bytes / 8 + 256;
@@ -116,7 +123,10 @@ struct DevBuf {
     return B200REC_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaFree(p);
+      g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
+    }
     p = nullptr;
     cap = 0;
   }

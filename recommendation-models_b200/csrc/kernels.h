@@ -6,7 +6,7 @@ namespace b200rec {
 
 // ---------------------------------------------------------------- sparse.cu (HBM-bound) ------
 // Device-side status word written by kernels that validate ids / indices.
-enum DevErr : int { DEV_OK = 0, DEV_BAD_ID = 1, DEV_BAD_INDEX = 2 };
+enum DevErr : int { DEV_OK = 0, DEV_BAD_ID = 1, DEV_BAD_INDEX = 2, DEV_PEER_TIMEOUT = 4, DEV_OVERFLOW = 8 };
 
 struct SparseFwd {
   int B = 0, F = 0, K = 0;
@@ -85,6 +85,22 @@ int segsum_inverse(SegSumWorkspace& ws, long long n, int* inv, cudaStream_t st);
 // ---------------------------------------------------------------- shard.cu (row-sharded table) --
 // owner(id) = (id + id / period) % world, local row = id / world (period is a multiple of world, so
 // the `world` consecutive ids of a block rotate over the ranks: a bijection id <-> (owner, row)).
+// period < 0 selects the reference's own partitioning instead: CONTIGUOUS RANGES of -period rows per rank
+// (ColumnRangePartitioner, rec/model/ParRecModel.scala:77,81,98,116): owner = id / rows_per_rank.
+__host__ __device__ inline int shard_owner(long long id, int world, long long period) {
+  if (period < 0) {
+    const long long o = id / (-period);
+    return (int)(o < world ? o : world - 1);
+  }
+  return (int)((id + id / period) % world);
+}
+__host__ __device__ inline long long shard_local_row(long long id, int world, long long period) {
+  if (period < 0) return id - (long long)shard_owner(id, world, period) * (-period);
+  return id / world;
+}
+__host__ __device__ inline bool shard_period_ok(int world, long long period) {
+  return period < 0 || (period >= world && period % world == 0);
+}
 struct ShardPlanWorkspace {
   DevBuf keys, keys_sorted, vals, perm, offsets, cub_tmp;
   int reserve(long long n);
@@ -107,11 +123,12 @@ struct P2P {
   unsigned* block_counter;   // local, zero-initialised; wraps back to 0 through atomicInc
   int* flags[P2P_MAX];       // every rank's flags[3][world]
 };
-int p2p_wait(const int* flags, int phase, int world, int step, const int* step_ptr, cudaStream_t st);
+// status (may be NULL): sticky device word; DEV_PEER_TIMEOUT is set when a peer's flag does not arrive in time
+int p2p_wait(const int* flags, int phase, int world, int step, const int* step_ptr, int* status, cudaStream_t st);
 int p2p_begin_step(int* step_ctr, int* ids_next, long long n, cudaStream_t st);
 // dense gradients: inout -> my symmetric buffer, then the sum over all ranks (rank order) back into inout
 int p2p_allreduce(long long n, float* inout, const int* flags_local, const P2P& c, const PeerF& bufs,
-                  const PeerF* outs, cudaStream_t st);
+                  const PeerF* outs, int* status, cudaStream_t st);
 // n_dev (optional): device count of valid ids (<= n); ids beyond it are ignored
 int p2p_plan(ShardPlanWorkspace& ws, long long n, const int* n_dev, long long period, int cap,
              const int* feats, int* dst, int* overflow, const P2P& c, const PeerI& ids_in, cudaStream_t st);
@@ -123,15 +140,18 @@ int p2p_push_grads(long long n, const int* n_dev, int K, int cap, const int* dst
 int table_init_uniform_sharded(float* table, float* wtable, long long rows, int K, uint64_t seed,
                                float lo, float hi, int rank, int world, long long period,
                                cudaStream_t st);
-int apply_sgd(int K, long long cap, const int* n_unique, const int* unique, const float* G,
-              const float* gw, float lr, float* table, float* wtable, cudaStream_t st);
+int apply_sgd(int K, long long rows, long long cap, const int* n_unique, const int* unique, const float* G,
+              const float* gw, float lr, float* table, float* wtable, int* err, cudaStream_t st);
 
 // ---------------------------------------------------------------- optim.cu ----------------------
-int opt_rows(int kind, int K, long long cap, const int* n_unique, const int* unique, const float* G,
-             const float* gw, float lr, float p1, float p2, long long step, float* table, float* wtable,
-             float* s1e, float* s2e, float* s1w, float* s2w, cudaStream_t st);
+// step_dev (may be NULL): device update counter used instead of `step` (CUDA-graph replays); ids outside
+// [0, rows) are skipped and flagged in err (DEV_BAD_ID)
+int opt_rows(int kind, int K, long long rows, long long cap, const int* n_unique, const int* unique,
+             const float* G, const float* gw, float lr, float p1, float p2, long long step,
+             const int* step_dev, float* table, float* wtable, float* s1e, float* s2e, float* s1w,
+             float* s2w, int* err, cudaStream_t st);
 int opt_dense(int kind, long long n, const float* g, float lr, float p1, float p2, long long step,
-              float* w, float* s1, float* s2, cudaStream_t st);
+              const int* step_dev, float* w, float* s1, float* s2, cudaStream_t st);
 
 // ---------------------------------------------------------------- dense.cu (SIMT fp32) --------
 // y[M,N] = act(x[M,K] W[N,K]^T + b[N])   (BigDL Linear + optional ReLU)

@@ -153,7 +153,7 @@ void b200rec_model_s::destroy() {
   seg3.release();
   plan.release();
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
-  for (auto& g : user_graphs) cudaGraphExecDestroy(g.first);
+  for (auto& g : user_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   graph_exec = nullptr;
   if (h_scal) cudaFreeHost(h_scal);
   if (ev_fork) cudaEventDestroy(ev_fork);

@@ -83,6 +83,7 @@ struct b200rec_model_s {
   // CUDA graph of the resident step (one per (B, table, gemm_mode)); captured after one eager warm-up
   cudaGraphExec_t graph_exec = nullptr;
   int graph_B = 0, graph_mode = -1, graph_nodes = 0, graph_warm_B = 0;
+  long long graph_epoch = -1, graph_warm_epoch = -1;   // g_alloc_epoch at capture / at the eager warm-up
   const void* graph_table = nullptr;
   bool graph_enabled = true;
   int gemm_mode = 0;  // 0 fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32 tcgen05
@@ -99,7 +100,8 @@ struct b200rec_model_s {
   bool join_pending[3] = {false, false, false};   // a side-stream sort was forked and not joined yet
   bool capturing = false;                        // b200rec_capture_begin .. _end
   long long capture_l0 = 0;
-  std::vector<std::pair<cudaGraphExec_t, int>> user_graphs;   // (executable, kernel nodes)
+  struct UserGraph { cudaGraphExec_t exec; int nodes; long long epoch; };
+  std::vector<UserGraph> user_graphs;   // executable, kernel nodes, g_alloc_epoch at capture
   DevBuf x0, gx0, gy, gnA, gnB, pooled, gpooled;
   DevBuf xL, s_cross, g_xL;
   DevBuf ip, gip, pre, hbuf;

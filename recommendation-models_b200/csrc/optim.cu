@@ -44,11 +44,32 @@ __device__ __forceinline__ float opt_update(int kind, float w, float g, float* s
   }
 }
 
-__global__ void __launch_bounds__(256) opt_rows_kernel(int kind, int K, const int* n_unique,
+// Adam's bias corrections from a DEVICE update counter (a replayed CUDA graph carries no host step
+// number): thread 0 of the block computes them once in double, like bias_corrections() on the host.
+__device__ __forceinline__ void device_corrections(int kind, float p1, float p2, const int* step_dev,
+                                                   float& c1, float& c2) {
+  __shared__ float sc[2];
+  if (step_dev == nullptr) return;   // uniform: the corrections came from the host
+  if (threadIdx.x == 0) {
+    const int step = *step_dev;
+    sc[0] = 1.f; sc[1] = 1.f;
+    if (kind == B200REC_OPT_ADAM && step > 0) {
+      sc[0] = (float)(1.0 / (1.0 - pow((double)p2, (double)step)));
+      sc[1] = (float)(1.0 / (1.0 - pow((double)p1, (double)step)));
+    }
+  }
+  __syncthreads();
+  c1 = sc[0]; c2 = sc[1];
+}
+
+__global__ void __launch_bounds__(256) opt_rows_kernel(int kind, int K, long long rows, const int* n_unique,
                                                        const int* unique, const float* G,
                                                        const float* gw, float lr, float p1, float p2,
-                                                       float c1, float c2, float* table, float* wtable,
-                                                       float* s1e, float* s2e, float* s1w, float* s2w) {
+                                                       float c1, float c2, const int* step_dev,
+                                                       float* table, float* wtable,
+                                                       float* s1e, float* s2e, float* s1w, float* s2w,
+                                                       int* err) {
+  device_corrections(kind, p1, p2, step_dev, c1, c2);
   const int U = *n_unique;
   const int KK = K + 1;  // column K = the first-order weight
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)U * KK;
@@ -56,6 +77,10 @@ __global__ void __launch_bounds__(256) opt_rows_kernel(int kind, int K, const in
     const long long seg = t / KK;
     const int k = (int)(t - seg * KK);
     const long long id = unique[seg];
+    if (id < 0 || id >= rows) {   // the reference throws on such an id; never write outside the table
+      if (err && k == 0) atomicOr(err, DEV_BAD_ID);
+      continue;
+    }
     if (k < K) {
       if (!G) continue;
       const long long o = id * K + k;
@@ -70,8 +95,10 @@ __global__ void __launch_bounds__(256) opt_rows_kernel(int kind, int K, const in
 }
 
 __global__ void __launch_bounds__(256) opt_dense_kernel(int kind, long long n, const float* g, float lr,
-                                                        float p1, float p2, float c1, float c2, float* w,
+                                                        float p1, float p2, float c1, float c2,
+                                                        const int* step_dev, float* w,
                                                         float* s1, float* s2) {
+  device_corrections(kind, p1, p2, step_dev, c1, c2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     w[i] = opt_update(kind, w[i], g[i], s1 ? s1 + i : nullptr, s2 ? s2 + i : nullptr, lr, p1, p2, c1, c2);
@@ -86,30 +113,31 @@ static void bias_corrections(int kind, float p1, float p2, long long step, float
   }
 }
 
-int opt_rows(int kind, int K, long long cap, const int* n_unique, const int* unique, const float* G,
-             const float* gw, float lr, float p1, float p2, long long step, float* table, float* wtable,
-             float* s1e, float* s2e, float* s1w, float* s2w, cudaStream_t st) {
+int opt_rows(int kind, int K, long long rows, long long cap, const int* n_unique, const int* unique,
+             const float* G, const float* gw, float lr, float p1, float p2, long long step,
+             const int* step_dev, float* table, float* wtable, float* s1e, float* s2e, float* s1w,
+             float* s2w, int* err, cudaStream_t st) {
   if (cap <= 0) return B200REC_OK;
   float c1, c2;
   bias_corrections(kind, p1, p2, step, &c1, &c2);
   int grid = cdiv(cap * (K + 1), 256);
   if (grid > 148 * 16) grid = 148 * 16;
   ProfTag tag("optimizer");
-  B200_LAUNCH(opt_rows_kernel, grid, 256, 0, st, kind, K, n_unique, unique, G, gw, lr, p1, p2, c1, c2,
-              table, wtable, s1e, s2e, s1w, s2w);
+  B200_LAUNCH(opt_rows_kernel, grid, 256, 0, st, kind, K, rows, n_unique, unique, G, gw, lr, p1, p2, c1, c2,
+              step_dev, table, wtable, s1e, s2e, s1w, s2w, err);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }
 
 int opt_dense(int kind, long long n, const float* g, float lr, float p1, float p2, long long step,
-              float* w, float* s1, float* s2, cudaStream_t st) {
+              const int* step_dev, float* w, float* s1, float* s2, cudaStream_t st) {
   if (n <= 0) return B200REC_OK;
   float c1, c2;
   bias_corrections(kind, p1, p2, step, &c1, &c2);
   int grid = cdiv(n, 256);
   if (grid > 148 * 16) grid = 148 * 16;
   ProfTag tag("optimizer");
-  B200_LAUNCH(opt_dense_kernel, grid, 256, 0, st, kind, n, g, lr, p1, p2, c1, c2, w, s1, s2);
+  B200_LAUNCH(opt_dense_kernel, grid, 256, 0, st, kind, n, g, lr, p1, p2, c1, c2, step_dev, w, s1, s2);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }

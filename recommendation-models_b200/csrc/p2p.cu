@@ -5,8 +5,9 @@
 // Reference: the worker <-> PS pull / push of rec/model/ParRecModel.scala:174-177,193-196 (pull
 // embedding rows of the batch's ids) and :247-250,261-264 (push their gradients).  Buffers are
 // symmetric allocations (same layout on every rank; the host passes the peer-mapped pointers):
-//   ids_in [2][G*cap]   local rows requested by each source (block s written by source s; -1 padding;
-//                       double-buffered by step parity so the owner can reset the next one)
+//   ids_in [4][G*cap]   local rows requested by each source (block s written by source s; -1 padding).
+//                       A ring of 4: ids are dispatched one step ahead, so while step t runs peers may
+//                       already write buffer t+1, a slow owner may still read t-1, and t+3 is reset
 //   rows_in[G*cap*K], w_in[G*cap]        rows returned by each owner (block o written by owner o)
 //   grad_in[G*cap*K], gw_in[G*cap]       per-nnz gradients from each source (block s)
 //   dense_in[mats]      this rank's dense gradients, read by every peer (one-shot allreduce, phase 3)
@@ -16,7 +17,10 @@
 // graph of the whole step can be replayed.
 // A writer kernel ends with: __syncthreads(), then thread 0's __threadfence_system() and one atomicInc
 // per block, and the LAST block stores the step number into every peer's flag.  A one-warp wait kernel
-// spins (acquire.sys) until all G flags of a phase reach the step, trapping after ~2 s.
+// spins (acquire.sys) until all G flags of a phase reach the step; after B200REC_P2P_TIMEOUT_MS it gives up
+// and sets DEV_PEER_TIMEOUT in the handle's status word (no trap: a late peer must not kill the job).
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace b200rec {
@@ -64,24 +68,51 @@ __device__ __forceinline__ void p2p_signal(const P2P& c, int phase) {
   }
 }
 
-// threads 0..world-1 spin until every source's flag of `phase` reaches the step; then the block syncs
-__device__ __forceinline__ void p2p_wait_block(const int* flags, int phase, int world, int step) {
+// threads 0..world-1 spin until every source's flag of `phase` reaches the step; then the block syncs.
+// A peer that is merely LATE (data-loader hiccup, first graph capture, checkpoint save on its host) must
+// not kill the job: the wait is bounded by wall time (globaltimer, B200REC_P2P_TIMEOUT_MS, default 30 s)
+// and on expiry it sets DEV_PEER_TIMEOUT in the handle's sticky status word and returns -- the host
+// reports it (b200rec_model_sync / the sharded step's check) instead of every rank dying on a trap.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void p2p_wait_block(const int* flags, int phase, int world, int step,
+                                               unsigned long long timeout_ns, int* status) {
   const int s = threadIdx.x;
   if (s < world) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(flags + phase * world + s) < step)
-      if (clock64() - t0 > 4000000000LL) __trap();   // a lost peer must fail the launch, not hang
+    if (ld_acquire_sys(flags + phase * world + s) < step) {
+      const unsigned long long t0 = global_ns();
+      unsigned spins = 0;
+      while (ld_acquire_sys(flags + phase * world + s) < step) {
+        if ((++spins & 63u) == 0 && global_ns() - t0 > timeout_ns) {
+          if (status) atomicOr(status, DEV_PEER_TIMEOUT);
+          break;
+        }
+      }
+    }
   }
   __syncthreads();
 }
 
-__global__ void p2p_wait_kernel(const int* flags, int phase, int world, int step, const int* step_ptr) {
-  p2p_wait_block(flags, phase, world, step > 0 ? step : *step_ptr - step);
+static unsigned long long p2p_timeout_ns() {
+  static unsigned long long v = [] {
+    const char* e = getenv("B200REC_P2P_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 30000.0;
+    return (unsigned long long)((ms > 1.0 ? ms : 1.0) * 1e6);
+  }();
+  return v;
 }
 
-int p2p_wait(const int* flags, int phase, int world, int step, const int* step_ptr, cudaStream_t st) {
+__global__ void p2p_wait_kernel(const int* flags, int phase, int world, int step, const int* step_ptr,
+                                unsigned long long timeout_ns, int* status) {
+  p2p_wait_block(flags, phase, world, step > 0 ? step : *step_ptr - step, timeout_ns, status);
+}
+
+int p2p_wait(const int* flags, int phase, int world, int step, const int* step_ptr, int* status, cudaStream_t st) {
   ProfTag tag("p2p_wait");
-  B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags, phase, world, step, step_ptr);
+  B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags, phase, world, step, step_ptr, p2p_timeout_ns(), status);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -185,7 +216,7 @@ __global__ void __launch_bounds__(256) p2p_copy_back_kernel(long long n, const f
 // bufs: the published vectors (padded to a multiple of 4 floats, pad zero-initialised by the host);
 // outs (may be empty: one-shot): the result buffers of the two-shot form
 int p2p_allreduce(long long n, float* inout, const int* flags_local, const P2P& c, const PeerF& bufs,
-                  const PeerF* outs, cudaStream_t st) {
+                  const PeerF* outs, int* status, cudaStream_t st) {
   if (n <= 0) return B200REC_OK;
   ProfTag tag("p2p_allreduce");
   int grid = cdiv(n / 4 > 0 ? n / 4 : 1, 256);
@@ -194,7 +225,7 @@ int p2p_allreduce(long long n, float* inout, const int* flags_local, const P2P& 
   if (pgrid > 148 * 2) pgrid = 148 * 2;
   B200_LAUNCH(p2p_publish_kernel, pgrid, EX_THREADS, 0, st, n, (const float*)inout, bufs.p[c.rank], c);
   // a one-warp kernel does the spinning: the reduce blocks must not hold SMs while a peer is late
-  B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags_local, 3, c.world, c.step, c.step_ptr);
+  B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags_local, 3, c.world, c.step, c.step_ptr, p2p_timeout_ns(), status);
   if (!outs) {
     B200_LAUNCH(p2p_reduce_kernel, grid, 256, 0, st, n, inout, c, bufs);
   } else {
@@ -203,7 +234,7 @@ int p2p_allreduce(long long n, float* inout, const int* flags_local, const P2P& 
     if (g2 > 148 * 2) g2 = 148 * 2;
     if (g2 < 1) g2 = 1;
     B200_LAUNCH(p2p_reduce_scatter_kernel, g2, 256, 0, st, n4, c, bufs, *outs);
-    B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags_local, 4, c.world, c.step, c.step_ptr);
+    B200_LAUNCH(p2p_wait_kernel, 1, 32, 0, st, flags_local, 4, c.world, c.step, c.step_ptr, p2p_timeout_ns(), status);
     B200_LAUNCH(p2p_copy_back_kernel, grid, 256, 0, st, n, (const float*)outs->p[c.rank], inout);
   }
   B200_CHECK_LAUNCH();
@@ -234,7 +265,7 @@ __global__ void __launch_bounds__(256) p2p_rank_place_kernel(long long n, const 
     int o = -1;
     if (i < n) {
       id = feats[i];
-      o = (int)((id + id / period) % world);
+      o = shard_owner(id, world, period);
     }
     int my_rank = 0;
     for (int q = 0; q < world; ++q) {
@@ -248,10 +279,12 @@ __global__ void __launch_bounds__(256) p2p_rank_place_kernel(long long n, const 
       for (int w = 0; w < warp; ++w) before += wcnt[w][o];
       const int slot = block_offsets[blockIdx.x * world + o] + before + my_rank;   // position within owner o
       if (slot >= cap) {
+        // the bucket is full: flag it (the host raises) and give the id NO slot -- its rows read as zero
+        // and its gradient is dropped, never another id's slot
         atomicOr(overflow, 1);
-        dst[i] = o * cap;
+        dst[i] = -1;
       } else {
-        peer_sel(ids_in.p, o)[(long long)c.rank * cap + slot] = (int)(id / world);   // store into the owner's memory
+        peer_sel(ids_in.p, o)[(long long)c.rank * cap + slot] = (int)shard_local_row(id, world, period);   // store into the owner's memory
         dst[i] = o * cap + slot;
       }
     }

@@ -363,25 +363,29 @@ int segsum_reduce(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
 
 // rec/optim/AsyncSGD.scala:10-31 applies w -= lr * g on the PS (textbook SGD; Angel's PSF source
 // is third-party, parity unpinned).  Touched rows only.
-__global__ void apply_sgd_kernel(int K, const int* n_unique, const int* unique, const float* G,
-                                 const float* gw, float lr, float* table, float* wtable) {
+__global__ void apply_sgd_kernel(int K, long long rows, const int* n_unique, const int* unique, const float* G,
+                                 const float* gw, float lr, float* table, float* wtable, int* err) {
   const int U = *n_unique;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)U * K;
        t += (long long)gridDim.x * blockDim.x) {
     const long long seg = t / K;
     const int k = (int)(t - seg * K);
     const long long id = unique[seg];
+    if (id < 0 || id >= rows) {   // never write outside the table (the reference throws on such ids)
+      if (err && k == 0) atomicOr(err, DEV_BAD_ID);
+      continue;
+    }
     if (G) table[id * K + k] -= lr * G[t];
     if (k == 0 && gw && wtable) wtable[id] -= lr * gw[seg];
   }
 }
 
-int apply_sgd(int K, long long cap, const int* n_unique, const int* unique, const float* G,
-              const float* gw, float lr, float* table, float* wtable, cudaStream_t st) {
+int apply_sgd(int K, long long rows, long long cap, const int* n_unique, const int* unique, const float* G,
+              const float* gw, float lr, float* table, float* wtable, int* err, cudaStream_t st) {
   if (cap <= 0) return B200REC_OK;
   int grid = cdiv(cap * K, 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  B200_LAUNCH(apply_sgd_kernel, grid, 256, 0, st, K, n_unique, unique, G, gw, lr, table, wtable);
+  B200_LAUNCH(apply_sgd_kernel, grid, 256, 0, st, K, rows, n_unique, unique, G, gw, lr, table, wtable, err);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }

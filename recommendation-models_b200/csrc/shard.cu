@@ -38,7 +38,7 @@ constexpr int CS_ITEMS = 2048;   // items per block
 constexpr int CS_MAXW = 32;
 
 __device__ __forceinline__ int owner_of(long long id, int world, long long period) {
-  return (int)((id + id / period) % world);
+  return shard_owner(id, world, period);
 }
 
 __global__ void __launch_bounds__(256) shard_hist_kernel(long long n, const int* n_dev, int world,
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) shard_rank_kernel(long long n, const int*
   }
 }
 
-__global__ void shard_place_kernel(long long n, int world, int cap, const int* feats,
+__global__ void shard_place_kernel(long long n, int world, long long period, int cap, const int* feats,
                                    const unsigned* owner_sorted, const unsigned* perm,
                                    const int* offsets, int* send_ids, int* dst, int* overflow) {
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -144,12 +144,12 @@ __global__ void shard_place_kernel(long long n, int world, int cap, const int* f
   const int o = (int)owner_sorted[p];
   const int slot = (int)p - offsets[o];
   const long long i = perm[p];
-  if (slot >= cap) {  // bucket overflow: reported, the row is dropped (dst points at slot 0)
+  if (slot >= cap) {  // bucket overflow: flagged (the host raises); the non-zero gets NO slot (zero row, gradient dropped)
     atomicOr(overflow, 1);
-    dst[i] = o * cap;
+    dst[i] = -1;
     return;
   }
-  send_ids[(long long)o * cap + slot] = feats[i] / world;
+  send_ids[(long long)o * cap + slot] = (int)shard_local_row(feats[i], world, period);
   dst[i] = o * cap + slot;
 }
 
@@ -159,8 +159,9 @@ static int shard_sort_impl(ShardPlanWorkspace& ws, long long n, const int* n_dev
                            long long period, const int* feats, int* send_ids, long long n_send,
                            cudaStream_t st) {
   B200_REQUIRE(world >= 1 && world <= CS_MAXW, B200REC_ERR_ARG, "world size %d out of range", world);
-  B200_REQUIRE(period >= world && period % world == 0, B200REC_ERR_ARG,
-               "shard period %lld must be a positive multiple of the world size %d", period, world);
+  B200_REQUIRE(shard_period_ok(world, period), B200REC_ERR_ARG,
+               "shard period %lld must be a positive multiple of the world size %d (or negative: -rows per rank of "
+               "a contiguous-range partition)", period, world);
   B200_TRY(ws.reserve(n));
   const int n_blocks = cdiv(n > 0 ? n : 1, CS_ITEMS);
   B200_TRY(ws.keys.reserve((size_t)n_blocks * world * sizeof(int) + 64));   // block counts / offsets
@@ -178,8 +179,9 @@ static int shard_sort_impl(ShardPlanWorkspace& ws, long long n, const int* n_dev
 int shard_hist_scan(ShardPlanWorkspace& ws, long long n, const int* n_dev, int world, long long period,
                     const int* feats, cudaStream_t st) {
   B200_REQUIRE(world >= 1 && world <= CS_MAXW, B200REC_ERR_ARG, "world size %d out of range", world);
-  B200_REQUIRE(period >= world && period % world == 0, B200REC_ERR_ARG,
-               "shard period %lld must be a positive multiple of the world size %d", period, world);
+  B200_REQUIRE(shard_period_ok(world, period), B200REC_ERR_ARG,
+               "shard period %lld must be a positive multiple of the world size %d (or negative: -rows per rank of "
+               "a contiguous-range partition)", period, world);
   B200_TRY(ws.reserve(n));
   const int n_blocks = cdiv(n > 0 ? n : 1, CS_ITEMS);
   B200_TRY(ws.keys.reserve((size_t)n_blocks * world * sizeof(int) + 64));
@@ -201,7 +203,7 @@ int shard_plan(ShardPlanWorkspace& ws, long long n, int world, long long period,
   ProfTag tag("shard_plan");
   B200_TRY(shard_sort_impl(ws, n, nullptr, world, period, feats, send_ids, (long long)world * cap, st));
   if (n > 0)
-    B200_LAUNCH(shard_place_kernel, cdiv(n, 256), 256, 0, st, n, world, cap, feats,
+    B200_LAUNCH(shard_place_kernel, cdiv(n, 256), 256, 0, st, n, world, period, cap, feats,
                 ws.keys_sorted.as<unsigned>(), ws.perm.as<unsigned>(), ws.offsets.as<int>(), send_ids,
                 dst, overflow);
   B200_CHECK_LAUNCH();

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) fm_fwd_kernel(SparseFwd a) {
           long long x = a.feats[base + f];
           if (x < 0 || x >= a.rows) {
             if (a.err) atomicOr(a.err, DEV_BAD_ID);
-            x = 0;
+            x = x < 0 ? -1 : 0;   // negative (e.g. a slot dropped by a full exchange bucket): a ZERO row, never another id's
           }
           id[u] = x;
         }
@@ -60,8 +60,10 @@ __global__ void __launch_bounds__(256) fm_fwd_kernel(SparseFwd a) {
         w[u] = 0.f;
         if (ok[u]) {
           if (GATHER) {
-            v[u] = ldg_f4(a.table + id[u] * K + sub * 4);
-            if (sub == 0 && a.wtable) w[u] = __ldg(a.wtable + id[u]);
+            if (id[u] >= 0) {
+              v[u] = ldg_f4(a.table + id[u] * K + sub * 4);
+              if (sub == 0 && a.wtable) w[u] = __ldg(a.wtable + id[u]);
+            }
           } else {
             v[u] = ld_stream_f4(a.emb_in + (base + f) * K + sub * 4);
             if (sub == 0 && a.w_in) w[u] = __ldg(a.w_in + base + f);
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(256) emb_grad_kernel(SparseBwd a, long long n_
       g.z = fmaf(c, s.z - v.z, g.z); g.w = fmaf(c, s.w - v.w, g.w);
     }
     const long long orow = a.out_slot ? (long long)a.out_slot[row] : row;
+    if (orow < 0) continue;   // no slot (full exchange bucket, already flagged): the gradient is dropped
     st_f4(a.dE + orow * K + sub * 4, g);
     if (sub == 0 && a.dw) {
       const int bi = a.index ? a.index[row] : b;
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(256) emb_grad_generic_kernel(SparseBwd a, long
     float g = a.dX ? a.dX[t] : 0.f;
     if (a.S) g = fmaf(a.dlogit[b] / (float)K, a.S[(long long)b * K + k] - a.X[t], g);
     const long long orow = a.out_slot ? (long long)a.out_slot[row] : row;
+    if (orow < 0) continue;
     a.dE[orow * K + k] = g;
     if (k == 0 && a.dw) a.dw[orow] = a.dlogit[a.index ? a.index[row] : b];
   }
@@ -232,8 +236,10 @@ __global__ void __launch_bounds__(256) emb_grad_generic_kernel(SparseBwd a, long
 __global__ void dw_only_kernel(long long n, int F, const int* index, const float* dlogit,
                                const int* out_slot, float* dw) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    dw[out_slot ? out_slot[i] : i] = dlogit[index ? index[i] : (int)(i / F)];
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long o = out_slot ? (long long)out_slot[i] : i;
+    if (o >= 0) dw[o] = dlogit[index ? index[i] : (int)(i / F)];
+  }
 }
 
 int sparse_bwd(const SparseBwd& a, cudaStream_t st) {

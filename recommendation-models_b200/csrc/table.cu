@@ -49,10 +49,15 @@ __global__ void __launch_bounds__(256) table_init_sharded_kernel(float* table, f
        t += (long long)gridDim.x * blockDim.x) {
     const long long q = t / K;
     const int k = (int)(t - q * K);
-    const long long base = q * world;
-    long long tt = ((long long)rank - (base / period)) % world;
-    if (tt < 0) tt += world;
-    const uint64_t g = (uint64_t)(base + tt);
+    uint64_t g;
+    if (period < 0) {   // contiguous ranges of -period rows per rank
+      g = (uint64_t)((long long)rank * (-period) + q);
+    } else {
+      const long long base = q * world;
+      long long tt = ((long long)rank - (base / period)) % world;
+      if (tt < 0) tt += world;
+      g = (uint64_t)(base + tt);
+    }
     table[t] = hash_uniform(seed, g * (uint64_t)K + (uint64_t)k, lo, span);
     if (k == 0 && wtable) wtable[q] = hash_uniform(seed + 1, g, lo, span);
   }

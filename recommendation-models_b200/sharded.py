@@ -26,25 +26,44 @@ from . import _lib as L
 
 
 class ShardSpec:
-    """owner(id) = (id + id // period) % world ; local row = id // world  (csrc/shard.cu)."""
+    """Which rank owns which table row (csrc/kernels.h: shard_owner / shard_local_row).
 
-    def __init__(self, rows_global, world, rank, period=None):
+    mode "mod" (default): owner(id) = (id + id // period) % world, local row = id // world -- a
+    rotation of id % world every `period` ids, balanced under per-field power-law ids.
+    mode "range": the reference's own layout (ColumnRangePartitioner, rec/model/ParRecModel.scala:
+    77,81,98,116): contiguous ranges of rows_local ids per rank, owner = id // rows_local.  Kept for
+    fidelity; the hot first ids of a field all land on one rank, so buckets are unbalanced and `cap`
+    must be sized for it.  The C ABI takes it as a NEGATIVE period (-rows per rank)."""
+
+    def __init__(self, rows_global, world, rank, period=None, mode="mod"):
         self.rows_global, self.world, self.rank = int(rows_global), int(world), int(rank)
+        self.mode = mode
+        self.rows_local = (self.rows_global + world - 1) // world
+        if mode == "range":
+            self.period = -int(self.rows_local)
+            return
+        assert mode == "mod", mode
         if period is None:
             period = max(world, (self.rows_global // 39 // world) * world)
         assert period >= world and period % world == 0
         self.period = int(period)
-        self.rows_local = (self.rows_global + world - 1) // world
 
     def owner(self, ids):
         ids = np.asarray(ids, np.int64)
+        if self.mode == "range":
+            return np.minimum(ids // self.rows_local, self.world - 1).astype(np.int64)
         return ((ids + ids // self.period) % self.world).astype(np.int64)
 
     def local_row(self, ids):
-        return np.asarray(ids, np.int64) // self.world
+        ids = np.asarray(ids, np.int64)
+        if self.mode == "range":
+            return ids - self.owner(ids) * self.rows_local
+        return ids // self.world
 
     def global_id(self, rank, q):
         q = np.asarray(q, np.int64)
+        if self.mode == "range":
+            return rank * self.rows_local + q
         base = q * self.world
         return base + (rank - base // self.period) % self.world
 
@@ -127,11 +146,82 @@ class GpuOps:
                                                      self.n_unique.data_ptr(), unique.data_ptr(),
                                                      G.data_ptr(), gw.data_ptr(), lr, self.stream_ptr))
 
+    def step_counter(self):
+        """Device pointer of the model's update counter (advanced by b200rec_p2p_begin_step_dev)."""
+        p = C.c_void_p()
+        L.check(self.lib.b200rec_model_step_counter(self.model.handle, C.byref(p)))
+        return p.value
+
+    def apply_optimizer(self, name, lr, p1, p2, unique, G, gw, step=None, step_dev=None):
+        """The PS-side update (rec/optim/Async*.scala): the owned touched rows AND the replicated dense
+        params (every replica applies the same allreduced gradient).  `step_dev`: device update counter
+        (graph replays); else the host `step`."""
+        kind = L.OPTIMIZERS[name]
+        p1 = {"momentum": 0.9, "adagrad": 0.9, "adam": 0.99}.get(name, 0.0) if p1 is None else p1
+        p2 = 0.9 if p2 is None else p2
+        if step_dev is not None:
+            L.check(self.lib.b200rec_table_apply_optimizer_stepdev_dev(
+                self.table.handle, kind, lr, p1, p2, step_dev, unique.numel(), self.n_unique.data_ptr(),
+                unique.data_ptr(), G.data_ptr(), gw.data_ptr(), self.stream_ptr))
+            L.check(self.lib.b200rec_model_apply_optimizer_stepdev_dev(self.model.handle, kind, lr, p1, p2, step_dev,
+                                                                       self.stream_ptr))
+        else:
+            L.check(self.lib.b200rec_table_apply_optimizer_dev(
+                self.table.handle, kind, lr, p1, p2, int(step), unique.numel(), self.n_unique.data_ptr(),
+                unique.data_ptr(), G.data_ptr(), gw.data_ptr(), self.stream_ptr))
+            L.check(self.lib.b200rec_model_apply_optimizer_dev(self.model.handle, kind, lr, p1, p2, int(step),
+                                                               self.stream_ptr))
+
+    def status(self):
+        """Synchronise and raise what the device flagged since the last call: a full exchange bucket
+        (RuntimeError: results of that step are invalid), a feature id outside the table or a peer that
+        never signalled (B200RecError)."""
+        self.stream.synchronize()
+        if int(self.overflow.item()):
+            self.overflow.zero_()
+            raise RuntimeError(
+                f"exchange bucket overflow: one (source, owner) bucket received more than cap={self.cap} distinct ids; "
+                "that step's rows / gradients are incomplete.  Build the sharded model with a larger cap "
+                "(cap = batch * nFields can never overflow)")
+        L.check(self.lib.b200rec_table_status(self.table.handle, 1, self.stream_ptr))
+        L.check(self.lib.b200rec_model_sync(self.model.handle))
+
     def stream_ctx(self):
         return self.torch.cuda.stream(self.stream)
 
 
-class ShardedParRecModel:
+class _OptimizerMixin:
+    """Optimizer choice of the sharded step (rec/optim/OptimUtils.scala:5-12; the reference's examples run
+    Adam, rec/example/DeepFMLocalExample.scala:32) and the host-visible status check."""
+
+    optimizer = None          # (name, lr, p1, p2)
+    check_every = 64          # steps between automatic status checks (0: only explicit check() calls)
+    _since_check = 0
+
+    def set_optimizer(self, name, lr, p1=None, p2=None):
+        name = name.lower()
+        if name not in L.OPTIMIZERS:
+            raise ValueError(f"unknown optimizer {name!r} (OptimUtils.scala:6-11 raises MatchError)")
+        self.optimizer = (name, float(lr), p1, p2)
+        if hasattr(self, "graphs"):
+            self.graphs.clear()
+            self.warm = False      # the optimizer slots are allocated in an eager step, not inside a capture
+
+    def check(self):
+        """Raise if any step since the last check overflowed an exchange bucket, saw an id outside the
+        table or lost a peer.  Synchronises; optimize() / step() call it every `check_every` steps."""
+        self._since_check = 0
+        st = getattr(self.ops, "status", None)
+        if st is not None:
+            st()
+
+    def _auto_check(self):
+        self._since_check += 1
+        if self.check_every and self._since_check >= self.check_every:
+            self.check()
+
+
+class ShardedParRecModel(_OptimizerMixin):
     """optimize() over a row-sharded table.  `dist` is torch.distributed (nccl on GPUs, gloo in the
     CPU tests); `ops` does the arithmetic."""
 
@@ -172,11 +262,16 @@ class ShardedParRecModel:
             o.segsum(self.recv_ids, self.recv_grad_rows, self.recv_grad_w, self.unique, self.G, self.gw)
             for wk in work:
                 wk.wait()
-            if lr is not None:
+            self.step_no = getattr(self, "step_no", 0) + 1
+            if self.optimizer is not None:
+                name, olr, p1, p2 = self.optimizer
+                o.apply_optimizer(name, olr, p1, p2, self.unique, self.G, self.gw, step=self.step_no)
+            elif lr is not None:
                 o.apply_sgd(self.unique, self.G, self.gw, lr)
+        self._auto_check()
 
 
-class P2PShardedParRecModel:
+class P2PShardedParRecModel(_OptimizerMixin):
     """The same step with the exchange over NVLink peer memory (csrc/p2p.cu) instead of NCCL: kernels
     store ids / rows / gradients straight into the peers' symmetric buffers and order them with
     release/acquire flags; the dense gradients are summed over peer memory too (one-shot up to 3
@@ -245,6 +340,7 @@ class P2PShardedParRecModel:
         self.s_targets = [torch.zeros(batch, dtype=torch.float32, device=dev) for _ in range(2)]
         self.loaded = [False, False]
         self.graphs = {}
+        self.graph_epoch = -1
         self.use_graph = True      # False: step() launches call by call (per-kernel profiling)
         self.warm = False
         torch.cuda.synchronize()
@@ -283,6 +379,10 @@ class P2PShardedParRecModel:
         cur, rst = self.ids_in[t % 4], self.ids_in[(t + 3) % 4]
         flags_t, _, flags_p = self.flags
         loc = self.loc[ws]
+        # a look-ahead dispatch of THIS batch (issued during the previous step on the side stream with
+        # "device counter + 1" as its step) must have read the counter before it is advanced below
+        if loc["feats"] is feats:
+            L.check(lib.b200rec_segsum_join_dev(m, ws, st))
         L.check(lib.b200rec_p2p_begin_step_dev(m, rst[0].data_ptr(), rst[0].numel(), st))
         if loc["feats"] is not feats:
             if loc["dispatched"] == t:
@@ -324,9 +424,14 @@ class P2PShardedParRecModel:
                                                flags_p, st))
         L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 2, G, 0, st))
         o.segsum(cur[0], self.grad_in[0], self.gw_in[0], self.unique, self.G, self.gw)   # joins side stream 1
-        if lr is not None:
-            o.apply_sgd(self.unique, self.G, self.gw, lr)
         L.check(lib.b200rec_segsum_join_dev(m, ws, st))           # the dense allreduce
+        if self.optimizer is not None:
+            # owner-side update of the touched rows + the replicated dense params; the update count is the
+            # device step counter, so the captured graph replays with the right Adam bias correction
+            name, olr, p1, p2 = self.optimizer
+            o.apply_optimizer(name, olr, p1, p2, self.unique, self.G, self.gw, step_dev=o.step_counter())
+        elif lr is not None:
+            o.apply_sgd(self.unique, self.G, self.gw, lr)
         if join_next and next_feats is not None:
             L.check(lib.b200rec_segsum_join_dev(m, 2 - ws, st))   # a graph must end with every fork joined
         loc["feats"] = None
@@ -341,6 +446,7 @@ class P2PShardedParRecModel:
             self._body(self.step_no, feats, targets, lr, next_feats, False)
         self.loaded = [False, False]
         self.warm = True
+        self._auto_check()
 
     # ---- replay mode -------------------------------------------------------------------------------
     def load(self, feats, targets):
@@ -368,6 +474,13 @@ class P2PShardedParRecModel:
         have_next = self.loaded[p ^ 1]
         feats, targets = self.s_feats[p], self.s_targets[p]
         nxt = self.s_feats[p ^ 1] if have_next else None
+        ep = C.c_int64(0)
+        L.check(lib.b200rec_alloc_epoch(C.byref(ep)))
+        if self.graphs and ep.value != self.graph_epoch:
+            # a workspace of the library was reallocated since the captures (e.g. a predict with a larger
+            # batch on this handle): the graphs hold freed addresses -- drop them, run eagerly, re-capture
+            self.graphs.clear()
+            self.warm = False
         with o.stream_ctx():
             if self.loc[ws]["feats"] is not feats:        # first step after load(): nothing prefetched
                 self._sort_local(ws, feats)
@@ -378,7 +491,7 @@ class P2PShardedParRecModel:
                 self.warm = True
             else:
                 pre = self.loc[ws]["dispatched"] == t
-                key = (t % 4, lr, have_next, pre)
+                key = (t % 4, lr, self.optimizer, have_next, pre)
                 if key not in self.graphs:
                     gid = C.c_int(-1)
                     L.check(lib.b200rec_capture_begin(m, o.stream_ptr))
@@ -387,6 +500,8 @@ class P2PShardedParRecModel:
                     finally:
                         rc = lib.b200rec_capture_end(m, C.byref(gid), o.stream_ptr)
                     L.check(rc)
+                    L.check(lib.b200rec_alloc_epoch(C.byref(ep)))
+                    self.graph_epoch = ep.value
                     self.graphs[key] = gid.value
                     self.loc[ws]["feats"] = feats         # the capture recorded, it did not run
                 self.step_no = t
@@ -395,34 +510,67 @@ class P2PShardedParRecModel:
         self.loaded[p] = False
         if have_next:
             self.loc[2 - ws]["feats"], self.loc[2 - ws]["dispatched"] = nxt, t + 1
+        self._auto_check()
 
 
 # ------------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1, launched by torchrun): weak scaling, per-GPU batch fixed
 # ------------------------------------------------------------------------------------------------------
 def bench(args, pkg):
+    """DeepFM on the 100 M-row row-sharded table (BASELINE configs[4]) as the headline record and, with
+    --model both, xDeepFM (configs[2]) on the same kind of table as the "xdeepfm" sub-record."""
     import json
     import os
     import sys
-    import time
 
     import torch
     import torch.distributed as dist
 
     import bench as B
 
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
     # NCCL prints its version banner on stdout when NCCL_DEBUG is set; stdout must carry the one JSON
-    # line only: point fd 1 at stderr until the communicators exist (end of the warm-up)
+    # line only: fd 1 points at stderr until the line is printed
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=dev)
+    names = B.model_list(args)
+    out = _bench_model(args, pkg, names[0], torch, dist, dev)
+    for extra in names[1:]:
+        sub = _bench_model(args, pkg, extra, torch, dist, dev)
+        if rank == 0:
+            out[extra] = sub
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    # torch's caching allocator still holds blocks last used on the library's stream; leave the teardown
+    # to process exit instead of destroying that stream under it
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
+
+
+_KEEP = []   # handles of finished bench legs: torch's allocator may still hold blocks tied to their streams
+
+
+def _bench_model(args, pkg, name, torch, dist, dev):
+    import os
+    import sys
+    import time
+
+    import bench as B
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     synth = pkg.synth
-    kind, fc, cin, depth = B.MODELS[args.model]
+    kind, fc, cin, depth = B.MODELS[name]
     F, K = B.F, B.K
-    batch, rows = args.batch, args.rows
+    batch, rows = args.batch, B.default_rows(args)
     spec = ShardSpec(rows, world, rank)
     model = pkg.make_model(kind, F, K, fc, cin, depth, device=local)
     if args.gemm_mode is not None:
@@ -438,23 +586,15 @@ def bench(args, pkg):
     nb = min(W + Ksteps, 32)
     # every rank draws its own batches: global step index = s * world + rank
     batches = [synth.make_feats(B.SEED_DATA, s * world + rank, batch, F, rows)[1] for s in range(nb)]
-    cap = None
-    if use_p2p:
-        # bucket capacity of the dedup'd exchange from the data: largest per-owner count of distinct ids
-        # over the run's batches, +30 % (the NCCL path exchanges every non-zero and keeps N/G * 1.25);
-        # overflow is still flagged on the device and reported in the result line
-        need = 0
-        for f in batches:   # every batch the run will cycle through
-            u = np.unique(f)
-            need = max(need, int(np.bincount(spec.owner(u), minlength=world).max()))
-        t = torch.tensor([need], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        cap = (int(t.item() * 1.3) + 1024 + 15) // 16 * 16
+    # bucket capacity: NOT read off the benchmark's batches.  A bucket holds the distinct ids one source
+    # sends one owner: at most its non-zeros, N/G on average under the rotated-mod owner map, so
+    # N/G * 1.25 + 1024 (the class default) is > 25 sigma of a hash-uniform split; an overflow is
+    # flagged on the device and raised by check() below
     sh = None
     if use_p2p:
         # every rank must take the same path: agree on whether symmetric memory came up everywhere
         try:
-            sh = P2PShardedParRecModel(ops, dist, spec, batch, F, K, cap=cap)
+            sh = P2PShardedParRecModel(ops, dist, spec, batch, F, K, cap=None)
             ok = torch.ones(1, device=dev)
         except Exception as e:  # noqa: BLE001  (no peer mapping on this box -> NCCL exchange)
             sys.stderr.write(f"rank {rank}: peer-memory exchange unavailable ({e!r}); using NCCL all-to-all\n")
@@ -486,10 +626,8 @@ def bench(args, pkg):
     for i in range(W):
         run_step(i)
     torch.cuda.synchronize()
+    sh.check()
     dist.barrier()
-    sys.stdout.flush()
-    os.dup2(saved_stdout, 1)
-    os.close(saved_stdout)
     clocks = B.ClockSampler(local)
     clocks.start()
     time.sleep(0.25)
@@ -563,11 +701,13 @@ def bench(args, pkg):
     for i in range(min(Ksteps, 10)):
         run_step(W + i)
     prof = L.profile_end()
+    sh.check()
     dist.barrier()
+    out = None
     if rank == 0:
         nsteps = min(Ksteps, 10)
         by_phase = {}
-        for tag, name, cnt, t in prof:
+        for tag, kname, cnt, t in prof:
             by_phase[tag] = by_phase.get(tag, 0.0) + t / nsteps
         n_slots = world * sh.cap
         out = {
@@ -575,12 +715,14 @@ def bench(args, pkg):
             "unit": "samples/s", "n_gpus": world, "steps": Ksteps, "warmup": W,
             "ms_per_step": round(ms_total / Ksteps, 5), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.model} k={K} F={F} fc={fc} cin={cin} depth={depth} per-GPU batch={batch} "
-                                   f"table_rows={rows} row-sharded over {world} GPUs (BASELINE configs[2]/[4])",
+            "config": {"workload": B.workload(name, args, rows),
+                       "baseline_config": {"deepfm": "configs[4]", "xdeepfm": "configs[2]"}.get(name, "configs[3]"),
                        "global_batch": batch * world, "parallelism": f"table row-sharded x{world} "
                        f"({'NVLink peer-memory stores fused into the gather / gradient kernels' if use_p2p else 'NCCL all-to-all'}), "
-                       f"dense dp{world} ({'one-shot allreduce over NVLink peer loads' if use_p2p else 'NCCL allreduce'})",
+                       f"dense dp{world} ({'allreduce over NVLink peer memory' if use_p2p else 'NCCL allreduce'})",
+                       "table_bytes_per_gpu": int(spec.rows_local) * (K + 1) * 4,
                        "exchange": "p2p" if use_p2p else "nccl", "cuda_graph": bool(graphed), "bucket_capacity": sh.cap,
+                       "bucket_capacity_rule": "N/G * 1.25 + 1024 (not derived from the timed batches); overflow raises",
                        "bucket_overflow": int(ovf.item()),
                        "l2": "table shard > L2; new ids every step; no explicit flush", "gemm_mode": args.gemm_mode},
             "clocks": clk,
@@ -595,11 +737,7 @@ def bench(args, pkg):
                                                 "dense_allreduce": (model.matsLen() + 1) * 4},
             "kernels_rank0_ms_per_step": {k: round(v, 5) for k, v in sorted(by_phase.items(), key=lambda kv: -kv[1])},
         }
-        print(json.dumps(out), flush=True)
-    # torch's caching allocator still holds blocks last used on the library's stream; leave the teardown
-    # to process exit instead of destroying that stream under it
     torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
-    sys.stdout.flush()
-    os._exit(0)
+    _KEEP.append((model, table, ps, ops, sh, dev_b, pin))
+    return out

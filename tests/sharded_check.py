@@ -125,8 +125,9 @@ def run(rank, world, backend, device=None):
     from oracle import refport
     from recommendation_models_b200.sharded import GpuOps, P2PShardedParRecModel, ShardedParRecModel, ShardSpec
     synth = pkg.synth
-    spec = ShardSpec(ROWS, world, rank)
-    cap = int(B * F / world * 1.5) + 64
+    spec = ShardSpec(ROWS, world, rank, mode="range" if backend == "p2p_range" else "mod")
+    # contiguous ranges put whole fields on one rank: buckets are unbalanced, size them for the worst case
+    cap = B * F if backend == "p2p_range" else int(B * F / world * 1.5) + 64
     _, feats = synth.make_feats(SEED_DATA, rank, B, F, ROWS)
     targets = synth.make_targets(SEED_DATA, feats, B, F)
     if backend == "gloo":
@@ -176,7 +177,7 @@ def run(rank, world, backend, device=None):
     tot_e, tot_w, egm, egb, losses = expected(synth, refport, spec)
     # ids this rank owns, ascending local row
     owned = sorted(fid for fid in tot_e if spec.owner([fid])[0] == rank)
-    exp_rows = np.array([fid // world for fid in owned])
+    exp_rows = np.array([int(spec.local_row([fid])[0]) for fid in owned])
     order = np.argsort(exp_rows)
     assert np.array_equal(uniq, exp_rows[order]), "distinct owned rows differ"
     assert np.array_equal(spec.global_id(rank, uniq), np.array(owned)[order])
@@ -189,6 +190,126 @@ def run(rank, world, backend, device=None):
     assert abs(gb - egb) <= 2e-5 * abs(egb) + 1e-6, "bias grad"
     assert abs(loss - losses[rank]) <= 1e-5 * abs(losses[rank]), "loss"
     return U
+
+
+def _gpu_setup(pkg, torch, spec, rank, world, device, cap):
+    from recommendation_models_b200.sharded import GpuOps
+    synth = pkg.synth
+    dev = torch.device("cuda", device)
+    torch.cuda.set_device(dev)
+    model = pkg.make_model(KIND, F, K, FC, CIN, device=device)
+    table = pkg.EmbeddingTable(spec.rows_local, K, device=device)
+    pkg._lib.check(pkg.lib().b200rec_table_init_uniform_sharded(table.handle, SEED_PARAMS, -0.05, 0.05, rank,
+                                                                world, spec.period))
+    ps = pkg.ParRecModel(model, table)
+    ps.setParams(np.array([0.1], np.float32), synth.init_mats(SEED_PARAMS, model.getMatsSize()))
+    return dev, model, table, ps, GpuOps(pkg, model, table, spec, B, cap, torch, dev)
+
+
+def run_adam(rank, world, device, graphed=True, steps=4):
+    """`steps` sharded training steps with Adam (the reference examples' optimizer,
+    rec/example/DeepFMLocalExample.scala:32) on the owner-side rows and the replicated dense params,
+    replayed as CUDA graphs (the update count comes from the device step counter), against the oracle
+    run on the global table: every rank's batch, gradients summed over ranks, one update per step."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from oracle import refport
+    from recommendation_models_b200.sharded import P2PShardedParRecModel, ShardSpec
+    synth = pkg.synth
+    spec = ShardSpec(ROWS, world, rank)
+    cap = int(B * F / world * 1.5) + 64
+    dev, model, table, ps, ops = _gpu_setup(pkg, torch, spec, rank, world, device, cap)
+    sh = P2PShardedParRecModel(ops, dist, spec, B, F, K, cap=cap)
+    sh.use_graph = graphed
+    lr = 0.01
+    sh.set_optimizer("adam", lr)
+    batches = []
+    for t in range(steps + 1):
+        _, f = synth.make_feats(SEED_DATA, t * world + rank, B, F, ROWS)
+        batches.append((torch.from_numpy(f).to(dev), torch.from_numpy(synth.make_targets(SEED_DATA, f, B, F)).to(dev)))
+    sh.load(*batches[0])
+    for t in range(steps):
+        sh.load(*batches[t + 1])
+        sh.step()
+    sh.check()
+    if graphed:
+        assert len(sh.graphs) >= 2
+    # ---- oracle on the global table ----------------------------------------------------------------------
+    ids_all = np.arange(ROWS)
+    E = synth.table_rows(SEED_PARAMS, ids_all, K)
+    W = synth.wtable_rows(SEED_PARAMS, ids_all)
+    o = refport.Model(KIND, F, K, FC, CIN)
+    mats = synth.init_mats(SEED_PARAMS, o.mats_size())
+    bias = np.array([0.1], np.float32)
+    stE, stW, stM, stB = {}, {}, {}, {}
+    for t in range(steps):
+        GE, GW = np.zeros_like(E), np.zeros_like(W)
+        gm_tot, gb_tot = np.zeros_like(mats), np.zeros_like(bias)
+        touched = np.zeros(ROWS, bool)
+        for r in range(world):
+            index, f = synth.make_feats(SEED_DATA, t * world + r, B, F, ROWS)
+            tg = synth.make_targets(SEED_DATA, f, B, F)
+            emb, w = E[f].reshape(-1).copy(), W[f].copy()
+            gb, gm = bias.copy(), mats.copy()
+            o.backward(B, index, w, gb, emb, gm, tg)
+            u, G = refport.make_embedding_grad(emb, f, K)
+            _, gw = refport.make_weights_grad(w, f)
+            GE[u] += G
+            GW[u] += gw
+            touched[u] = True
+            gm_tot += gm
+            gb_tot += gb
+        u = np.nonzero(touched)[0]
+        sub = lambda st: {k: v[u] for k, v in st.items()}
+        se, sw = sub(stE), sub(stW)
+        E[u] = refport.optimizer_update("adam", E[u], GE[u], se, lr, step=t + 1)
+        W[u] = refport.optimizer_update("adam", W[u], GW[u], sw, lr, step=t + 1)
+        for st, s_new, shape in ((stE, se, E.shape), (stW, sw, W.shape)):
+            for k, v in s_new.items():
+                st.setdefault(k, np.zeros(shape, np.float32))[u] = v
+        mats = refport.optimizer_update("adam", mats, gm_tot, stM, lr, step=t + 1)
+        bias = refport.optimizer_update("adam", bias, gb_tot, stB, lr, step=t + 1)
+    gE, gW = table.read(0, spec.rows_local)
+    gid = spec.global_id(rank, np.arange(spec.rows_local))
+    ok = gid < ROWS
+    tol = lambda want: 1e-3 * np.abs(want).max()
+    assert np.abs(gE[ok] - E[gid[ok]]).max() <= tol(E), ("table", np.abs(gE[ok] - E[gid[ok]]).max())
+    assert np.abs(gW[ok] - W[gid[ok]]).max() <= tol(W), "weights"
+    gbias, gmats = ps.getParams()
+    assert np.abs(gmats - mats).max() <= tol(mats), ("mats", np.abs(gmats - mats).max())
+    assert abs(gbias[0] - bias[0]) <= 1e-3 * abs(bias[0]) + 1e-5, "bias"
+    return int(ok.sum())
+
+
+def run_overflow(rank, world, device):
+    """A bucket capacity that cannot hold the batch's distinct ids: the step must not alias another id's
+    slot, and check() must raise (on every rank, as every rank overflows)."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from recommendation_models_b200.sharded import P2PShardedParRecModel, ShardSpec
+    synth = pkg.synth
+    spec = ShardSpec(ROWS, world, rank)
+    cap = 16                                     # 64 * 39 non-zeros -> hundreds of distinct ids per owner
+    dev, model, table, ps, ops = _gpu_setup(pkg, torch, spec, rank, world, device, cap)
+    sh = P2PShardedParRecModel(ops, dist, spec, B, F, K, cap=cap)
+    sh.check_every = 0
+    _, f = synth.make_feats(SEED_DATA, rank, B, F, ROWS)
+    tf, tt = torch.from_numpy(f).to(dev), torch.from_numpy(synth.make_targets(SEED_DATA, f, B, F)).to(dev)
+    sh.optimize(tf, tt)
+    try:
+        sh.check()
+    except RuntimeError as e:
+        assert "overflow" in str(e)
+    else:
+        raise AssertionError("bucket overflow was not reported")
+    sh.check()                                   # the flag is cleared once reported
+    loss = float(ops.loss().item())
+    assert np.isfinite(loss)
+    return cap
 
 
 def _cpu_worker(rank, world, port, q):
@@ -210,9 +331,13 @@ if __name__ == "__main__":
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    for backend in ("nccl", "p2p", "p2p_graph", "p2p_graph_twoshot"):
+    for backend in ("nccl", "p2p", "p2p_graph", "p2p_graph_twoshot", "p2p_range"):
         u = run(rank, world, backend, device=local)
         print(f"rank {rank}/{world}: sharded step ok ({backend}), {u} owned distinct rows", flush=True)
+    u = run_adam(rank, world, local)
+    print(f"rank {rank}/{world}: sharded step ok (p2p_graph + adam, 4 steps), {u} owned rows compared", flush=True)
+    u = run_overflow(rank, world, local)
+    print(f"rank {rank}/{world}: sharded step ok (overflow raised at cap {u})", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.stdout.flush()

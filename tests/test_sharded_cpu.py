@@ -21,6 +21,21 @@ def test_owner_mapping_is_a_bijection(pkg):
         assert counts.max() <= int(np.ceil(39 / world)) + 2, counts
 
 
+def test_range_partition_is_a_bijection(pkg):
+    """mode="range": the reference's ColumnRangePartitioner layout (ParRecModel.scala:77,81,98,116)."""
+    from recommendation_models_b200.sharded import ShardSpec
+    for rows, world in [(39 * 256, 2), (1000, 4), (1001, 8)]:
+        specs = [ShardSpec(rows, world, r, mode="range") for r in range(world)]
+        assert specs[0].period == -specs[0].rows_local
+        ids = np.arange(rows)
+        own, loc = specs[0].owner(ids), specs[0].local_row(ids)
+        assert np.all(np.diff(own) >= 0) and own.max() == world - 1      # contiguous, ascending ranges
+        assert loc.max() < specs[0].rows_local
+        for r in range(world):
+            m = own == r
+            assert np.array_equal(specs[r].global_id(r, loc[m]), ids[m])
+
+
 @pytest.mark.parametrize("world", [2])
 def test_sharded_step_gloo(pkg, world):
     import socket
