@@ -232,8 +232,16 @@ int b200rec_step_results(b200rec_model_t m, float* loss, int64_t* n_unique, int*
 int b200rec_step_result_ptrs(b200rec_model_t m, float** loss, int** n_unique, int** unique,
                              float** emb_grad, float** w_grad, float** bias_grad,
                              float** mats_grad);
-/* Per-nnz gradients of the last step before dedup: dE[nnz*K], dw[nnz] (device pointers). */
+/* Per-nnz gradients of the last step before dedup: dE[nnz*K], dw[nnz] (device pointers) -- what
+ * GradUtil.embeddingGrad / weightsGrad leave in the `embedding` / `weights` buffers
+ * (rec/util/GradUtil.scala:7-42). */
 int b200rec_step_nnz_grad_ptrs(b200rec_model_t m, float** emb_grad, float** w_grad);
+/* Variant of the resident step's scatter-add that computes the per-nnz gradient inside the segment
+ * reduce instead of reading the array an elementwise kernel wrote (csrc/segsum.cu; bit-identical sums).
+ * It saves the dE round trip through HBM but gathers two arrays at sorted-id positions instead of one;
+ * measured slower on B200, so it is OFF by default.  keep_nnz_grads != 0 makes the fused
+ * form store the per-nnz gradients too (b200rec_step_nnz_grad_ptrs stays valid). */
+int b200rec_model_set_fused_scatter(b200rec_model_t m, int enabled, int keep_nnz_grads);
 /* Split step for a row-sharded table: the caller gathered rows itself (all-to-all)
  * and hands over device buffers emb[B*F*K], w[B*F]; grads are written in place (per nnz). */
 int b200rec_step_gathered_dev(b200rec_model_t m, int batch_size, float* emb, float* w,
@@ -428,6 +436,66 @@ int b200rec_linear_update_grad_input(int device, int batch_size, int in_dim, int
 int b200rec_linear_acc_grad_parameters(int device, int batch_size, int in_dim, int out_dim,
                                        const float* x, const float* gy, float scale,
                                        float* grad_w, float* grad_b);
+
+/* ---- the encoders: the dense branch of each model as the reference exposes it ------------------------
+ * forward(input: Tensor[B, nFields*embeddingDim]) -> Tensor[B,1] and backward(input, gradOutput) ->
+ * gradInput, with the parameter gradients copied over `mats` at the parameters' own offsets
+ * (BackwardUtil.linearBackward / biasBackward, rec/util/BackwardUtil.scala:6-42):
+ *   higher_order  rec/model/encoder/HigherOrderEncoder.scala:18-32   handle kind B200REC_DEEPFM
+ *                 (nFields * embeddingDim = inputDim; for PNN's own tower over fcDims.head create the
+ *                 handle with nFields = fcDims.head, embeddingDim = 1, fcDims = fcDims.tail)
+ *   cin           rec/model/xdeepfm/CINEncoder.scala:36,60           handle kind B200REC_XDEEPFM
+ *   cross         rec/model/dcn/CrossEncoder.scala:40,57             handle kind B200REC_DCN
+ *   product       rec/model/pnn/ProductEncoder.scala:34,43           handle kind B200REC_PNN; output and
+ *                 gradOutput are [B, fcDims.head], mats is the encoder's own prefix [W_z | W_p | c]
+ * `mats` points at the encoder's first parameter (the reference's mats + start); its length is
+ * b200rec_encoder_mats_len.  The BigDL method triple is kept for each:
+ *   _update_output        = forward;
+ *   _update_grad_input    = gradInput only (parameters untouched);
+ *   _acc_grad_parameters  = grad_mats += scale * parameter gradients, same layout as mats (accumulates,
+ *                           like BigDL's gradWeight);
+ *   _backward             = the reference encoder's backward: gradInput out, `mats` OVERWRITTEN with the
+ *                           gradients.
+ * Host arrays; each call runs the branch's forward (+ backward) on the handle's stream and returns. */
+int b200rec_encoder_mats_len(b200rec_model_t m, int64_t* len);
+int b200rec_higher_order_update_output(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                       float* output);
+int b200rec_higher_order_update_grad_input(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                           const float* grad_output, float* grad_input);
+int b200rec_higher_order_acc_grad_parameters(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                             const float* grad_output, float scale, float* grad_mats);
+int b200rec_higher_order_backward(b200rec_model_t m, int batch_size, const float* input, float* mats,
+                                  const float* grad_output, float* grad_input);
+int b200rec_cin_update_output(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                              float* output);
+int b200rec_cin_update_grad_input(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                  const float* grad_output, float* grad_input);
+int b200rec_cin_acc_grad_parameters(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                    const float* grad_output, float scale, float* grad_mats);
+int b200rec_cin_backward(b200rec_model_t m, int batch_size, const float* input, float* mats,
+                         const float* grad_output, float* grad_input);
+int b200rec_cross_update_output(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                float* output);
+int b200rec_cross_update_grad_input(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                    const float* grad_output, float* grad_input);
+int b200rec_cross_acc_grad_parameters(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                      const float* grad_output, float scale, float* grad_mats);
+int b200rec_cross_backward(b200rec_model_t m, int batch_size, const float* input, float* mats,
+                           const float* grad_output, float* grad_input);
+int b200rec_product_update_output(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                  float* output);
+int b200rec_product_update_grad_input(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                      const float* grad_output, float* grad_input);
+int b200rec_product_acc_grad_parameters(b200rec_model_t m, int batch_size, const float* input, const float* mats,
+                                        const float* grad_output, float scale, float* grad_mats);
+int b200rec_product_backward(b200rec_model_t m, int batch_size, const float* input, float* mats,
+                             const float* grad_output, float* grad_input);
+/* nn/DuplicateTable.scala:13-56, the fan-out container of SecondOrderEncoder: forward hands the same
+ * tensor to every branch (no data movement: the kernels read it in place; inside the models the fan-out
+ * is fused), updateGradInput sums the branches' input gradients in branch order into a zeroed tensor
+ * (:22-33).  grad_outputs: n_branches x len, branch-major. */
+int b200rec_duplicate_table_update_grad_input(int device, int n_branches, int64_t len,
+                                              const float* grad_outputs, float* grad_input);
 
 #ifdef __cplusplus
 }

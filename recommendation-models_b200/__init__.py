@@ -9,6 +9,7 @@ from . import _lib
 from ._lib import B200RecError, device_count, launch_count, lib
 from .models import (InternalDCNModel, InternalDeepFMModel, InternalFMModel, InternalLRModel,
                      InternalPNNModel, InternalXDeepFMModel, make_model)
-from .nn import DotProduct2, FirstOrderEncoder, Gather, Linear, Scatter, SecondOrderEncoder
+from .nn import (CINEncoder, CrossEncoder, DotProduct2, DuplicateTable, FirstOrderEncoder, Gather, HigherOrderEncoder,
+                 Linear, ProductEncoder, Scatter, SecondOrderEncoder)
 from .ps import EmbeddingTable, ParRecModel, distinct, scatter_add
 from . import data, metrics, sharded, synth

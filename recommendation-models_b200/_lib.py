@@ -65,6 +65,7 @@ SIGNATURES = {
     "b200rec_step_results": [vp, c_float_p, c_i64_p, vp, vp, vp, c_float_p, vp],
     "b200rec_step_result_ptrs": [vp] + [C.POINTER(vp)] * 7,
     "b200rec_step_nnz_grad_ptrs": [vp, C.POINTER(vp), C.POINTER(vp)],
+    "b200rec_model_set_fused_scatter": [vp, C.c_int, C.c_int],
     "b200rec_step_gathered_dev": [vp, C.c_int, vp, vp, vp, vp],
     "b200rec_segsum_dev": [vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp],
     "b200rec_segsum_sort_dev": [vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp],
@@ -105,6 +106,24 @@ SIGNATURES = {
     "b200rec_model_step_counter": [vp, C.POINTER(vp)],
     "b200rec_table_status": [vp, C.c_int, vp],
     "b200rec_alloc_epoch": [c_i64_p],
+    "b200rec_encoder_mats_len": [vp, c_i64_p],
+    "b200rec_duplicate_table_update_grad_input": [C.c_int, C.c_int, C.c_int64, vp, vp],
+    "b200rec_higher_order_update_output": [vp, C.c_int, vp, vp, vp],
+    "b200rec_higher_order_update_grad_input": [vp, C.c_int, vp, vp, vp, vp],
+    "b200rec_higher_order_acc_grad_parameters": [vp, C.c_int, vp, vp, vp, C.c_float, vp],
+    "b200rec_higher_order_backward": [vp, C.c_int, vp, vp, vp, vp],
+    "b200rec_cin_update_output": [vp, C.c_int, vp, vp, vp],
+    "b200rec_cin_update_grad_input": [vp, C.c_int, vp, vp, vp, vp],
+    "b200rec_cin_acc_grad_parameters": [vp, C.c_int, vp, vp, vp, C.c_float, vp],
+    "b200rec_cin_backward": [vp, C.c_int, vp, vp, vp, vp],
+    "b200rec_cross_update_output": [vp, C.c_int, vp, vp, vp],
+    "b200rec_cross_update_grad_input": [vp, C.c_int, vp, vp, vp, vp],
+    "b200rec_cross_acc_grad_parameters": [vp, C.c_int, vp, vp, vp, C.c_float, vp],
+    "b200rec_cross_backward": [vp, C.c_int, vp, vp, vp, vp],
+    "b200rec_product_update_output": [vp, C.c_int, vp, vp, vp],
+    "b200rec_product_update_grad_input": [vp, C.c_int, vp, vp, vp, vp],
+    "b200rec_product_acc_grad_parameters": [vp, C.c_int, vp, vp, vp, C.c_float, vp],
+    "b200rec_product_backward": [vp, C.c_int, vp, vp, vp, vp],
     "b200rec_scatter_update_output": [C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp, vp],
     "b200rec_scatter_update_grad_input": [C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp, vp],
     "b200rec_gather_update_output": [C.c_int] * 5 + [vp] * 5,

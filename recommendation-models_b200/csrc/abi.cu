@@ -474,7 +474,8 @@ int b200rec_model_sync(b200rec_model_t m) {
   B200_CUDA(cudaStreamSynchronize(m->side));
   int word[3] = {0, 0, 0};   // [4] err of the last run, [5] sortedness, [6] sticky exchange status
   B200_CUDA(cudaMemcpy(word, m->scal.as<int>() + 4, 3 * sizeof(int), cudaMemcpyDeviceToHost));
-  if (word[2]) B200_CUDA(cudaMemset(m->scal.as<int>() + 6, 0, sizeof(int)));
+  // a deferred error is reported once
+  if (word[0] | word[2]) B200_CUDA(cudaMemset(m->scal.as<int>() + 4, 0, 3 * sizeof(int)));
   return dev_status(word[0] | word[2], m->last_B, 0);
 }
 
@@ -747,14 +748,23 @@ static int step_on_device(Model* m, Table* t, int B, const int* feats, const flo
     a.dbias_out = scal + 1;
     a.gmats_out = m->gmats.as<float>();
     a.loss_out = scal + 0;
+    a.defer_sparse_bwd = m->fused_scatter;
   }
   B200_TRY(m->run(a, st));
   if (train) {
     B200_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
-    sg.dE = has_emb ? m->X.as<float>() : nullptr;
-    sg.dw = m->dw.as<float>();
     sg.G = has_emb ? m->G.as<float>() : nullptr;
     sg.gw = m->gwU.as<float>();
+    if (m->deferred.valid) {
+      // makeEmbeddingGrad / makeWeightsGrad with the per-nnz gradient computed inside the reduce
+      sg.fused = true;
+      sg.fX = m->deferred.X; sg.fS = m->deferred.S; sg.fdX = m->deferred.dX; sg.fdlogit = m->deferred.dlogit;
+      sg.fF = m->F;
+      if (m->keep_nnz_grads) { sg.keep_dE = m->X.as<float>(); sg.keep_dw = m->dw.as<float>(); }
+    } else {
+      sg.dE = has_emb ? m->X.as<float>() : nullptr;
+      sg.dw = m->dw.as<float>();
+    }
     B200_TRY(segsum_reduce(m->seg, sg, st));
   }
   return B200REC_OK;
@@ -991,6 +1001,16 @@ int b200rec_step_result_ptrs(b200rec_model_t m, float** loss, int** n_unique, in
   if (emb_grad) *emb_grad = m->G.as<float>();
   if (w_grad) *w_grad = m->gwU.as<float>();
   if (mats_grad) *mats_grad = m->gmats.as<float>();
+  return B200REC_OK;
+}
+
+int b200rec_model_set_fused_scatter(b200rec_model_t m, int enabled, int keep_nnz_grads) {
+  B200_REQUIRE(m, B200REC_ERR_ARG, "NULL model");
+  m->fused_scatter = enabled != 0;
+  m->keep_nnz_grads = keep_nnz_grads != 0;
+  // the captured graph of the resident step bakes the choice in
+  if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+  m->graph_warm_epoch = -1;
   return B200REC_OK;
 }
 
@@ -1518,6 +1538,130 @@ struct OpCtx {
     return dev_status(word[0], batch_size, 0);
   }
 };
+
+// ---- encoders: HigherOrderEncoder / CINEncoder / CrossEncoder / ProductEncoder .forward / .backward ------
+// The reference's encoders take the [B, F*K] embedding tensor and return the [B,1] branch output
+// ([B, fcDims.head] for ProductEncoder); backward returns gradInput and copies the parameter gradients
+// over `mats` at the parameters' offsets (BackwardUtil.linearBackward).  The handle's kind selects the
+// encoder: DEEPFM -> HigherOrderEncoder, XDEEPFM -> CINEncoder, DCN -> CrossEncoder, PNN -> ProductEncoder.
+static long long encoder_mats_len(const Model* m) {
+  if (m->kind == B200REC_PNN) {
+    const long long P = (long long)m->F * (m->F - 1) / 2, O = m->fc[0];
+    return (long long)m->D * O + P * O + 1;      // [W_z][W_p][c]  (ProductEncoder.scala:72-108)
+  }
+  return m->mats_len;
+}
+
+// what: 0 forward, 1 gradInput, 2 accGradParameters, 3 backward (gradInput + grads over mats)
+static int encoder_call(b200rec_model_t m, int want_kind, const char* name, int what, int B,
+                        const float* input, const float* mats_in, float* mats_out, const float* grad_output,
+                        float scale, float* output, float* grad_input, float* grad_mats) {
+  B200_GUARD_BEGIN
+  B200_REQUIRE(m, B200REC_ERR_ARG, "NULL model");
+  B200_REQUIRE(m->kind == want_kind, B200REC_ERR_ARG, "%s needs a handle created with kind %d (this one is kind %d)",
+               name, want_kind, m->kind);
+  B200_REQUIRE(B > 0, B200REC_ERR_ARG, "batchSize must be positive");
+  B200_REQUIRE(input && mats_in, B200REC_ERR_ARG, "NULL input / mats");
+  if (what == 0) B200_REQUIRE(output, B200REC_ERR_ARG, "NULL output");
+  if (what >= 1) B200_REQUIRE(grad_output, B200REC_ERR_ARG, "NULL gradOutput");
+  if (what == 1 || what == 3) B200_REQUIRE(grad_input, B200REC_ERR_ARG, "NULL gradInput");
+  if (what == 2) B200_REQUIRE(grad_mats, B200REC_ERR_ARG, "NULL grad_mats");
+  B200_TRY(use_device(m->device));
+  cudaStream_t st = m->stream;
+  const size_t f = sizeof(float);
+  const long long n_in = (long long)B * m->D, n_mats = encoder_mats_len(m);
+  const long long n_out = m->kind == B200REC_PNN ? (long long)B * m->fc[0] : B;
+  B200_TRY(upload(m->X, input, (size_t)n_in * f, st));
+  B200_TRY(m->stage_a.reserve((size_t)(m->mats_len > 0 ? m->mats_len : 1) * f));
+  B200_CUDA(cudaMemcpyAsync(m->stage_a.p, mats_in, (size_t)n_mats * f, cudaMemcpyHostToDevice, st));
+  B200_TRY(m->enc_o.reserve((size_t)n_out * f));
+  RunArgs a;
+  a.B = B; a.nnz = (long long)B * m->F;
+  a.emb = m->X.as<float>();
+  a.mats = m->stage_a.as<float>();
+  a.encoder_only = true;
+  a.enc_out = m->enc_o.as<float>();
+  a.gmats_out = m->gmats.as<float>();
+  if (what >= 1) {
+    B200_TRY(upload(m->enc_go, grad_output, (size_t)n_out * f, st));
+    B200_TRY(m->enc_dx.reserve((size_t)n_in * f));
+    a.enc_grad = m->enc_go.as<float>();
+    a.enc_dx = m->enc_dx.as<float>();
+  }
+  B200_TRY(m->run(a, st));
+  if (what == 0) B200_TRY(download(output, m->enc_o.p, (size_t)n_out * f, st));
+  if (what == 1 || what == 3) B200_TRY(download(grad_input, m->enc_dx.p, (size_t)n_in * f, st));
+  std::vector<float> g;
+  if (what == 2) {
+    g.resize((size_t)n_mats);
+    B200_TRY(download(g.data(), m->gmats.p, (size_t)n_mats * f, st));
+  }
+  if (what == 3) B200_TRY(download(mats_out, m->gmats.p, (size_t)n_mats * f, st));
+  B200_TRY(download(m->h_scal, m->scal.p, 8 * f, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  B200_TRY(dev_status(((int*)m->h_scal)[4], B, 0));
+  if (what == 2)   // accGradParameters ACCUMULATES (BigDL: gradWeight += scale * ...)
+    for (long long i = 0; i < n_mats; ++i) grad_mats[i] += scale * g[(size_t)i];
+  return B200REC_OK;
+  B200_GUARD_END
+}
+
+int b200rec_encoder_mats_len(b200rec_model_t m, int64_t* len) {
+  B200_REQUIRE(m && len, B200REC_ERR_ARG, "NULL argument");
+  *len = encoder_mats_len(m);
+  return B200REC_OK;
+}
+
+#define B200_ENCODER_ABI(NAME, KIND)                                                                             \
+  int b200rec_##NAME##_update_output(b200rec_model_t m, int batch_size, const float* input, const float* mats,   \
+                                     float* output) {                                                            \
+    return encoder_call(m, KIND, #NAME, 0, batch_size, input, mats, nullptr, nullptr, 0.f, output, nullptr,      \
+                        nullptr);                                                                                \
+  }                                                                                                              \
+  int b200rec_##NAME##_update_grad_input(b200rec_model_t m, int batch_size, const float* input,                  \
+                                         const float* mats, const float* grad_output, float* grad_input) {       \
+    return encoder_call(m, KIND, #NAME, 1, batch_size, input, mats, nullptr, grad_output, 0.f, nullptr,          \
+                        grad_input, nullptr);                                                                    \
+  }                                                                                                              \
+  int b200rec_##NAME##_acc_grad_parameters(b200rec_model_t m, int batch_size, const float* input,                \
+                                           const float* mats, const float* grad_output, float scale,             \
+                                           float* grad_mats) {                                                   \
+    return encoder_call(m, KIND, #NAME, 2, batch_size, input, mats, nullptr, grad_output, scale, nullptr,        \
+                        nullptr, grad_mats);                                                                     \
+  }                                                                                                              \
+  int b200rec_##NAME##_backward(b200rec_model_t m, int batch_size, const float* input, float* mats,              \
+                                const float* grad_output, float* grad_input) {                                   \
+    return encoder_call(m, KIND, #NAME, 3, batch_size, input, mats, mats, grad_output, 0.f, nullptr, grad_input, \
+                        nullptr);                                                                                \
+  }
+B200_ENCODER_ABI(higher_order, B200REC_DEEPFM)
+B200_ENCODER_ABI(cin, B200REC_XDEEPFM)
+B200_ENCODER_ABI(cross, B200REC_DCN)
+B200_ENCODER_ABI(product, B200REC_PNN)
+#undef B200_ENCODER_ABI
+
+// nn/DuplicateTable.scala:13-56: the fan-out container.  Forward hands the SAME input to every branch
+// (nothing to compute: the model kernels read the tensor in place); its backward is the sum of the
+// branches' input gradients, added in branch order into a zeroed tensor (:22-33; the reference forgets to
+// re-zero a reused gradInput, SURVEY B-9 -- zeroed here).  grad_outputs: n_branches x len, branch-major.
+int b200rec_duplicate_table_update_grad_input(int device, int n_branches, int64_t len,
+                                              const float* grad_outputs, float* grad_input) {
+  B200_GUARD_BEGIN
+  B200_REQUIRE(n_branches >= 0 && len >= 0, B200REC_ERR_ARG, "bad sizes");
+  B200_REQUIRE((grad_outputs && grad_input) || len == 0 || n_branches == 0, B200REC_ERR_ARG, "NULL argument");
+  B200_TRY(use_device(device));
+  if (len == 0) return B200REC_OK;
+  OpCtx c;
+  B200_TRY(c.init());
+  ScopedBuf d_g, d_o;
+  B200_TRY(upload(d_g, grad_outputs, (size_t)n_branches * len * sizeof(float), c.st));
+  B200_TRY(d_o.reserve((size_t)len * sizeof(float)));
+  B200_CUDA(cudaMemsetAsync(d_o.p, 0, (size_t)len * sizeof(float), c.st));
+  for (int i = 0; i < n_branches; ++i) B200_TRY(axpy(len, d_g.as<float>() + (size_t)i * len, d_o.as<float>(), c.st));
+  B200_TRY(download(grad_input, d_o.p, (size_t)len * sizeof(float), c.st));
+  return c.finish(0);
+  B200_GUARD_END
+}
 
 int b200rec_scatter_update_output(int device, int batch_size, int n_output, int64_t n,
                                   const float* input, const int* index, float* output) {

@@ -76,6 +76,16 @@ struct SegSum {
   float* gw = nullptr;            // [n]   out
   int* n_unique = nullptr;        // device int out
   bool drop_pad = false;          // keys equal to -1 (exchange padding) form no segment
+  // fused gradient producer (segsum.cu): rows are computed from the step's saved tensors instead of
+  // being read from dE / dw:  dE[p] = (dlogit_b / K)(S_b - X[p]) + dX[p], dw[p] = dlogit_b, b = p / F
+  bool fused = false;
+  const float* fX = nullptr;      // [n,K] gathered rows        (needed when fS is given)
+  const float* fdX = nullptr;     // [n,K] dense-branch input gradient, or nullptr
+  const float* fS = nullptr;      // [B,K] sum over fields, or nullptr (no second-order term)
+  const float* fdlogit = nullptr; // [B]
+  int fF = 0;                     // non-zeros per sample
+  float* keep_dE = nullptr;       // optional: also write the per-nnz gradients
+  float* keep_dw = nullptr;
 };
 // sort half (depends only on feats: can run on a side stream while the dense math runs)
 int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st);

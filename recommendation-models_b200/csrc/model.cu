@@ -144,7 +144,7 @@ void b200rec_model_s::destroy() {
   DevBuf* bufs[] = {&p_bias, &p_mats, &gmats, &scal, &d_feats, &d_targets, &d_index, &X, &wnz, &S,
                     &first, &second, &branch, &preds, &dlogit, &dXd, &dw, &gA, &gB, &scratch,
                     &uniq, &G, &gwU, &wpack, &wpack_mlp, &s1m, &s2m, &p2p_ctr, &x0, &gx0, &gy, &gnA, &gnB, &pooled, &gpooled, &xL, &s_cross,
-                    &g_xL, &ip, &gip, &pre, &hbuf, &stage_a, &stage_b};
+                    &g_xL, &ip, &gip, &pre, &hbuf, &stage_a, &stage_b, &enc_go, &enc_o, &enc_dx};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : acts) b.release();
   for (auto& b : xl) b.release();
@@ -305,7 +305,8 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   tl_prepack = nullptr;
   const int B = a.B;
   const long long nnz = a.nnz;
-  const bool train = a.targets != nullptr;
+  const bool enc = a.encoder_only;
+  const bool train = enc ? a.enc_grad != nullptr : a.targets != nullptr;
   const bool has_emb = kind != B200REC_LR;
   if (has_emb) B200_REQUIRE(nnz == (long long)B * F, B200REC_ERR_SHAPE,
                             "nnz %lld != batchSize %d * nFields %d (Reshape to [B,F,K] would fail)", nnz, B, F);
@@ -321,7 +322,9 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   auto phase = [](const char* name) { tl_tag = name; };
   phase("gather_fm_fwd");
   const float* Xp = a.emb;
-  if (a.table_emb) {
+  if (enc) {
+    // encoder-only: nothing sparse to do
+  } else if (a.table_emb) {
     SparseFwd s;
     s.B = B; s.F = F; s.K = has_emb ? K : 0; s.rows = a.table_rows; s.feats = a.feats;
     s.table = a.table_emb; s.wtable = a.table_w;
@@ -422,21 +425,31 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
     B200_TRY(linear_fwd(B, O, D, Xp, wz, nullptr, false, pre.as<float>(), st, gemm_mode));
     B200_TRY(pnn_ip_fwd(B, F, K, Xp, ip.as<float>(), st));
     B200_TRY(pnn_lp_fwd(B, P, O, ip.as<float>(), wp, pre.as<float>(), c0, hbuf.as<float>(), st, gemm_mode));
-    B200_TRY(mlp_forward(B, hbuf.as<float>(), mats, &last, br, st));
-    h.br[h.n_br++] = br;
+    if (!enc) {   // (the ProductEncoder alone ends here; PNN.scala:77-79 stacks a HigherOrderEncoder on it)
+      B200_TRY(mlp_forward(B, hbuf.as<float>(), mats, &last, br, st));
+      h.br[h.n_br++] = br;
+    }
+  }
+  if (enc) {
+    const size_t n_out = kind == B200REC_PNN ? (size_t)B * fc[0] : (size_t)B;
+    const float* src = kind == B200REC_PNN ? hbuf.as<float>() : br;
+    if (a.enc_out) B200_CUDA(cudaMemcpyAsync(a.enc_out, src, n_out * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (!train) return aux_join(st);
   }
 
   // ---- head ---------------------------------------------------------------------------------------
-  phase("head");
-  h.bias = a.bias;
-  h.targets = a.targets;
-  h.preds = a.preds ? a.preds : preds.as<float>();
-  h.dlogit = dlogit.as<float>();
-  h.loss = a.loss_out;
-  h.dbias = a.dbias_out;
-  if (a.gmats_out == gmats.as<float>()) h.dbias2 = gmats.as<float>() + mats_len;  // [mats grad | bias grad]
-  B200_TRY(head_run(h, scratch, st));
-  if (!train) return aux_join(st);
+  if (!enc) {
+    phase("head");
+    h.bias = a.bias;
+    h.targets = a.targets;
+    h.preds = a.preds ? a.preds : preds.as<float>();
+    h.dlogit = dlogit.as<float>();
+    h.loss = a.loss_out;
+    h.dbias = a.dbias_out;
+    if (a.gmats_out == gmats.as<float>()) h.dbias2 = gmats.as<float>() + mats_len;  // [mats grad | bias grad]
+    B200_TRY(head_run(h, scratch, st));
+    if (!train) return aux_join(st);
+  }
 
   // ---- dense branch backward ----------------------------------------------------------------------
   phase("dense_bwd");
@@ -444,7 +457,7 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
     B200_CUDA(cudaStreamWaitEvent(st, ev_aux_pack, 0));
     aux_pack_pending = false;
   }
-  const float* dlg = dlogit.as<float>();
+  const float* dlg = enc ? a.enc_grad : dlogit.as<float>();   // an encoder's gradOutput is [B,1]
   float* gm = a.gmats_out;
   float* dxd = nullptr;  // dense-branch gradient w.r.t. the embedding input
   if (kind == B200REC_DEEPFM) {
@@ -497,11 +510,15 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
     const float* wp = mats + (long long)D * O;
     dxd = dXd.as<float>();
     float* gh = pre.as<float>();  // reuse: gradient w.r.t. the product layer pre-activation
-    B200_TRY(mlp_head_backward(B, hbuf.as<float>(), mats, gm, dlg, gh, st));
-    if (mlp.dims.empty()) {
-      B200_TRY(relu_mask((long long)B * O, gh, hbuf.as<float>(), gh, st));
+    if (enc) {   // ProductEncoder.backward alone: gradOutput is [B, O], masked by the layer's own ReLU
+      B200_TRY(relu_mask((long long)B * O, a.enc_grad, hbuf.as<float>(), gh, st));
     } else {
-      B200_TRY(mlp_backward(B, hbuf.as<float>(), mats, gm, gh, hbuf.as<float>(), st));
+      B200_TRY(mlp_head_backward(B, hbuf.as<float>(), mats, gm, dlg, gh, st));
+      if (mlp.dims.empty()) {
+        B200_TRY(relu_mask((long long)B * O, gh, hbuf.as<float>(), gh, st));
+      } else {
+        B200_TRY(mlp_backward(B, hbuf.as<float>(), mats, gm, gh, hbuf.as<float>(), st));
+      }
     }
     // ProductEncoder.backward :43-70
     B200_TRY(reduce_sum((long long)B * O, gh, 1.0f, gm + (long long)D * O + (long long)P * O, scratch, st));
@@ -513,8 +530,20 @@ int b200rec_model_s::run(const RunArgs& a, cudaStream_t st) {
   }
 
   B200_TRY(aux_join(st));
+  if (enc) {
+    if (a.enc_dx && dxd)
+      B200_CUDA(cudaMemcpyAsync(a.enc_dx, dxd, (size_t)B * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return B200REC_OK;
+  }
 
   // ---- per-nnz gradients (GradUtil.scala:7-42) ------------------------------------------------------
+  deferred.valid = false;
+  if (a.defer_sparse_bwd && has_emb && canonical && !a.out_slot) {
+    // the resident step's scatter-add computes them on the fly (segsum.cu: fused gradient producer)
+    deferred.X = Xp; deferred.S = second_order ? S.as<float>() : nullptr; deferred.dX = dxd;
+    deferred.dlogit = dlg; deferred.valid = true;
+    return B200REC_OK;
+  }
   phase("emb_grad");
   SparseBwd sb;
   sb.B = B; sb.F = has_emb ? F : (int)(B ? nnz / B : 0); sb.K = has_emb ? K : 0;

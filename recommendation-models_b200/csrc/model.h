@@ -39,6 +39,23 @@ struct RunArgs {
   float* gmats_out = nullptr;  // [mats_len]
   float* loss_out = nullptr;   // [1]
   const int* out_slot = nullptr;  // sharded path: per-nnz gradients are written to these slots
+  // resident step: leave the per-nnz gradient producer (GradUtil.scala:7-42) to the fused segment
+  // reduce (segsum.cu); run() then only records where its inputs are (Model::deferred)
+  bool defer_sparse_bwd = false;
+  // encoder-only call (the reference's HigherOrderEncoder / CINEncoder / CrossEncoder / ProductEncoder
+  // .forward / .backward): `emb` is the encoder input [B, F*K], no sparse terms, no head
+  bool encoder_only = false;
+  float* enc_out = nullptr;         // [B]   ([B, fc[0]] for the PNN product encoder)
+  const float* enc_grad = nullptr;  // gradOutput, same shape; nullptr => forward only
+  float* enc_dx = nullptr;          // gradInput [B, F*K] out
+};
+
+struct DeferredGrad {       // inputs of the per-nnz gradient the fused scatter-add computes on the fly
+  const float* X = nullptr;      // gathered rows [nnz,K]
+  const float* S = nullptr;      // [B,K] or nullptr
+  const float* dX = nullptr;     // [nnz,K] or nullptr
+  const float* dlogit = nullptr; // [B]
+  bool valid = false;
 };
 
 }  // namespace b200rec
@@ -86,7 +103,10 @@ struct b200rec_model_s {
   long long graph_epoch = -1, graph_warm_epoch = -1;   // g_alloc_epoch at capture / at the eager warm-up
   const void* graph_table = nullptr;
   bool graph_enabled = true;
-  int gemm_mode = 0;  // 0 fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32 tcgen05
+  int gemm_mode = 0;  // 0 fp32 SIMT, 1 split-precision tcgen05 (TF32 + bf16 corrections), 2 1xTF32 tcgen05
+  b200rec::DeferredGrad deferred;
+  bool fused_scatter = false;    // resident step: per-nnz gradient computed inside the segment reduce (measured slower: off)
+  bool keep_nnz_grads = false;   // resident step: also materialise the per-nnz gradients (b200rec_step_nnz_grad_ptrs)
   int last_B = 0;
   long long last_nnz = 0;
   using DevBuf = b200rec::DevBuf;
@@ -96,6 +116,7 @@ struct b200rec_model_s {
   DevBuf uniq, G, gwU, wpack, wpack_mlp;
   b200rec::PrePack prepack;
   DevBuf s1m, s2m;  // optimizer slots of [mats | bias]
+  DevBuf enc_go, enc_o, enc_dx;   // encoder-level calls: gradOutput in, output / gradInput out
   DevBuf p2p_ctr;   // [0] block-completion counter of the peer-exchange kernels, [1] device step counter
   bool join_pending[3] = {false, false, false};   // a side-stream sort was forked and not joined yet
   bool capturing = false;                        // b200rec_capture_begin .. _end

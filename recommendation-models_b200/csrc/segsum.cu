@@ -9,11 +9,21 @@
 // order.  Loads are issued in parallel, only the fp32 adds are sequential, so the result is
 // bit-identical to the reference's hash-map accumulation regardless of grid size -- there are
 // no float atomics anywhere.
-//   * short segments (<= LONG_T rows): LPR = K/4 lanes per segment, 128-bit loads
-//   * long segments  (hot ids of the power law): one warp per segment; 32/LPR rows are loaded
-//     per instruction, then folded into the accumulator in order through shuffles.
+//   * short segments (<= LONG_T = 4 rows, the bulk of a power-law batch): LPR = K/4 lanes per segment;
+//     its (up to) 4 positions and then its 4 rows are loaded as two batches of independent 128-bit
+//     loads -- straight-line code, no per-segment loop to diverge on
+//   * longer segments (the hot ids): one warp per segment; 32/LPR rows are loaded per instruction, 64
+//     rows per batch with the next batch's positions prefetched, then folded into the accumulator in
+//     order through shuffles.  Their list is built in the sort half.
 // The sort half depends only on the ids, so the driver runs it on a side stream while the
 // dense math runs (model.cu).
+//
+// FUSED gradient producer (resident step): instead of reading a per-nnz gradient dE[N,K] that an
+// elementwise kernel wrote a moment earlier, the reduce can compute each row on the fly,
+//     dE[p,:] = (dlogit_b / K) (S_b - X[p,:]) + dX[p,:],   dw[p] = dlogit_b,   b = p / F
+// (SecondOrderEncoder backward + GradUtil.embeddingGrad / weightsGrad, rec/util/GradUtil.scala:7-42), with
+// the same arithmetic as emb_grad_kernel (sparse.cu), so the sums are bit-identical to the two-kernel
+// path while the 2 x N x K x 4 bytes of the dE round trip never touch HBM.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -21,7 +31,10 @@
 
 namespace b200rec {
 
-static constexpr int LONG_T = 32;   // (8 was measured slower: 3 000 one-warp segments instead of 700)
+static constexpr int LONG_T = 4;    // segments longer than this take the warp-per-segment role
+static constexpr int BIG_T = 64;    // ... and beyond this the block-per-segment role (shared-memory staging)
+static constexpr int BIG_CH = 448;  // rows of a big segment staged per round (448 x 68 B = 30 KB of shared memory)
+static constexpr int BIG_MAX_K = 16; // widest row the staging buffer is sized for
 
 int SegSumWorkspace::reserve(long long n) {
   if (n <= cap_n) return B200REC_OK;
@@ -30,7 +43,8 @@ int SegSumWorkspace::reserve(long long n) {
   B200_TRY(vals_a.reserve(ni * 4));
   B200_TRY(vals_b.reserve(ni * 4));
   B200_TRY(seg_start.reserve(ni * 4));
-  B200_TRY(long_list.reserve(ni / LONG_T * 4 + 64));
+  // [0, ni/LONG_T): segments of LONG_T+1 .. BIG_T rows; [ni/LONG_T, ...): segments of more than BIG_T rows
+  B200_TRY(long_list.reserve((ni / LONG_T + ni / BIG_T) * 4 + 128));
   B200_TRY(counters.reserve(64));
   size_t sort_bytes = 0, scan_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
@@ -75,12 +89,17 @@ __global__ void seg_heads_kernel(long long n, const unsigned* keys, const int* s
   }
 }
 
-// hot ids (segments longer than LONG_T) -> long_list, still in the sort half (off the critical path)
-__global__ void seg_long_kernel(const int* n_unique, const int* seg_start, int* long_list, int* long_count) {
+// hot ids -> two lists by length class, still in the sort half (off the critical path).  The order
+// inside a list is whatever the atomics give: it only decides which warp / block sums which segment.
+__global__ void seg_long_kernel(const int* n_unique, const int* seg_start, int* long_list, int* big_list,
+                                int* counts, int big_t) {
   const int U = *n_unique;
   for (long long seg = blockIdx.x * (long long)blockDim.x + threadIdx.x; seg < U;
-       seg += (long long)gridDim.x * blockDim.x)
-    if (seg_start[seg + 1] - seg_start[seg] > LONG_T) long_list[atomicAdd(long_count, 1)] = (int)seg;
+       seg += (long long)gridDim.x * blockDim.x) {
+    const int len = seg_start[seg + 1] - seg_start[seg];
+    if (len > big_t) big_list[atomicAdd(counts + 1, 1)] = (int)seg;
+    else if (len > LONG_T) long_list[atomicAdd(counts, 1)] = (int)seg;
+  }
 }
 
 int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
@@ -117,7 +136,8 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
     int grid = cdiv(n, 256);
     if (grid > 148 * 8) grid = 148 * 8;
     B200_LAUNCH(seg_long_kernel, grid, 256, 0, st, a.n_unique, ws.seg_start.as<int>(), ws.long_list.as<int>(),
-                counters);
+                ws.long_list.as<int>() + (ws.cap_n + 8) / LONG_T, counters,
+                a.K <= BIG_MAX_K ? BIG_T : 0x7fffffff);   // wider rows than the staging buffer: warp role only
   }
   B200_CHECK_LAUNCH();
   return B200REC_OK;
@@ -135,84 +155,98 @@ int segsum_inverse(SegSumWorkspace& ws, long long n, int* inv, cudaStream_t st) 
   return B200REC_OK;
 }
 
+// ---- where a row of the per-nnz gradient comes from ---------------------------------------------
+struct RowSrc {
+  const float* dE = nullptr;      // plain: [n,K]
+  const float* dw = nullptr;      // plain: [n]
+  // fused (X or dX given): computed per row, see the header
+  const float* X = nullptr;
+  const float* dX = nullptr;
+  const float* S = nullptr;
+  const float* dlogit = nullptr;
+  int F = 1;
+  float* dE_keep = nullptr;       // fused: also materialise the per-nnz gradients (tests / callers that ask)
+  float* dw_keep = nullptr;
+  bool has_e = false, has_w = false, fused = false;
+};
+
+template <int K>
+__device__ __forceinline__ void load_row(const RowSrc& s, long long p, int sub, float4& v, float& w) {
+  if (!s.fused) {
+    if (s.has_e) v = ldg_f4(s.dE + p * K + sub * 4);
+    if (s.has_w && sub == 0) w = __ldg(s.dw + p);
+    return;
+  }
+  const int b = (int)(p / s.F);
+  const float g0 = __ldg(s.dlogit + b);
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s.dX) g = ld_stream_f4(s.dX + p * K + sub * 4);
+  if (s.S) {   // exactly emb_grad_kernel's arithmetic
+    const float c = g0 / (float)K;
+    const float4 sv = ldg_f4(s.S + (long long)b * K + sub * 4);
+    const float4 x = ld_stream_f4(s.X + p * K + sub * 4);
+    g.x = fmaf(c, sv.x - x.x, g.x); g.y = fmaf(c, sv.y - x.y, g.y);
+    g.z = fmaf(c, sv.z - x.z, g.z); g.w = fmaf(c, sv.w - x.w, g.w);
+  }
+  v = g;
+  if (sub == 0) w = g0;
+  if (s.dE_keep) st_f4(s.dE_keep + p * K + sub * 4, g);
+  if (s.dw_keep && sub == 0) s.dw_keep[p] = g0;
+}
+
 // ---- in-order segment sums --------------------------------------------------------------------
 template <int LPR>
-__device__ __forceinline__ void segsum_short_role(int block, int n_blocks, const int* n_unique,
-                                                  const int* seg_start, const unsigned* perm,
-                                                  const float* dE, const float* dw, float* G, float* gw) {
+__device__ __forceinline__ void segsum_short_role(int block, int n_blocks, long long n, const int* seg_idx,
+                                                  const unsigned* perm, const RowSrc src, float* G, float* gw) {
+  // Walks SORTED POSITIONS, not segments: a lane group looks at position p, and if p is the head of a
+  // segment of at most LONG_T rows it sums that segment.  seg_idx (the 1-based segment number of every
+  // sorted position, left by the sort half) and perm are read at p-1 .. p+LONG_T: contiguous, coalesced
+  // loads, and only TWO dependent load levels (positions -> rows) instead of three through seg_start.
   constexpr int K = 4 * LPR;
-  constexpr int UNR = 4;
-  const int U = *n_unique;
   const long long tid = block * (long long)blockDim.x + threadIdx.x;
   const int sub = (int)(tid % LPR);
   const long long n_groups = ((long long)n_blocks * blockDim.x) / LPR;
-  // SB segments per iteration: their (start, length), first position and first row are loaded as
-  // three batches of independent loads (the chain start -> perm -> row is paid once per batch, and
-  // most segments have one row); the remaining rows of a segment follow in order.
-  constexpr int SB = 4;
-  for (long long seg0 = tid / LPR; seg0 < U; seg0 += n_groups * SB) {
-    int start[SB], len[SB];
+  for (long long p = tid / LPR; p < n; p += n_groups) {
+    const int s0 = seg_idx[p];
+    const int sprev = p > 0 ? seg_idx[p - 1] : 0;
+    int sn[LONG_T];
+    unsigned q[LONG_T];
 #pragma unroll
-    for (int i = 0; i < SB; ++i) {
-      const long long seg = seg0 + i * n_groups;
-      start[i] = 0; len[i] = 0;
-      if (seg < U) {
-        start[i] = seg_start[seg];
-        len[i] = seg_start[seg + 1] - start[i];
-        if (len[i] > LONG_T) len[i] = 0;   // a hot id: the long role sums it
+    for (int j = 0; j < LONG_T; ++j) {
+      sn[j] = p + 1 + j < n ? seg_idx[p + 1 + j] : 0;   // segment of position p + 1 + j (0: past the end)
+      q[j] = p + j < n ? perm[p + j] : 0u;
+    }
+    if (s0 == sprev) continue;                          // not a segment head
+    int len = 1;
+#pragma unroll
+    for (int j = 0; j < LONG_T; ++j) len += (len == j + 1 && sn[j] == s0) ? 1 : 0;
+    if (len > LONG_T) continue;                         // a longer segment: the warp / block roles sum it
+    float4 v[LONG_T];
+    float w[LONG_T];
+#pragma unroll
+    for (int j = 0; j < LONG_T; ++j) {
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w[j] = 0.f;
+      if (j < len) load_row<K>(src, (long long)q[j], sub, v[j], w[j]);
+    }
+    float4 acc = make_float4(0.f + v[0].x, 0.f + v[0].y, 0.f + v[0].z, 0.f + v[0].w);
+    float aw = 0.f + w[0];
+#pragma unroll
+    for (int j = 1; j < LONG_T; ++j) {
+      if (j < len) {
+        acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+        aw += w[j];
       }
     }
-    unsigned p0[SB];
-#pragma unroll
-    for (int i = 0; i < SB; ++i) p0[i] = len[i] > 0 ? perm[start[i]] : 0u;
-    float4 v0[SB];
-    float w0[SB];
-#pragma unroll
-    for (int i = 0; i < SB; ++i) {
-      v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      w0[i] = 0.f;
-      if (len[i] > 0) {
-        if (dE) v0[i] = ldg_f4(dE + (long long)p0[i] * K + sub * 4);
-        if (dw && sub == 0) w0[i] = __ldg(dw + p0[i]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < SB; ++i) {
-      if (len[i] <= 0) continue;
-      const long long seg = seg0 + i * n_groups;
-      float4 acc = make_float4(0.f + v0[i].x, 0.f + v0[i].y, 0.f + v0[i].z, 0.f + v0[i].w);
-      float aw = 0.f + w0[i];
-      for (int j0 = 1; j0 < len[i]; j0 += UNR) {
-        float4 v[UNR];
-        float w[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          w[u] = 0.f;
-          if (j0 + u < len[i]) {
-            const long long p = perm[start[i] + j0 + u];
-            if (dE) v[u] = ldg_f4(dE + p * K + sub * 4);
-            if (dw && sub == 0) w[u] = __ldg(dw + p);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          if (j0 + u < len[i]) {
-            acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
-            aw += w[u];
-          }
-        }
-      }
-      if (G) st_f4(G + seg * K + sub * 4, acc);
-      if (gw && sub == 0) gw[seg] = aw;
-    }
+    const long long seg = s0 - 1;
+    if (G && src.has_e) st_f4(G + seg * K + sub * 4, acc);
+    if (gw && src.has_w && sub == 0) gw[seg] = aw;
   }
 }
 
 template <int LPR>
 __device__ __forceinline__ void segsum_long_role(int block, int n_blocks, const int* seg_start,
-                                                 const unsigned* perm, const float* dE,
-                                                 const float* dw, float* G, float* gw,
+                                                 const unsigned* perm, const RowSrc src, float* G, float* gw,
                                                  const int* long_list, const int* long_count) {
   // One warp per hot id.  Rows are LOADED 32/LPR x UNR at a time (all loads of a batch in flight,
   // the positions of the next batch prefetched meanwhile) and ADDED strictly in non-zero order
@@ -245,11 +279,7 @@ __device__ __forceinline__ void segsum_long_role(int block, int n_blocks, const 
         const int j = base + u * RPW + slot;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         w[u] = 0.f;
-        if (j < len) {
-          const long long p = pnext[u];
-          if (dE) v[u] = ldg_f4(dE + p * K + sub * 4);
-          if (dw && sub == 0) w[u] = __ldg(dw + p);
-        }
+        if (j < len) load_row<K>(src, (long long)pnext[u], sub, v[u], w[u]);
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {  // positions of the next batch: their latency hides under the fold
@@ -280,17 +310,69 @@ __device__ __forceinline__ void segsum_long_role(int block, int n_blocks, const 
   }
 }
 
+// One BLOCK per very hot id (more than BIG_T rows; the hottest id of a Criteo-shaped batch of 8192 owns
+// ~430).  The only sequential part of an in-order sum is its chain of fp32 adds; everything else is made
+// parallel: all 256 threads fetch up to BIG_CH rows of the segment into shared memory in one round of
+// independent loads, then K + 1 lanes of warp 0 (one per component, one for the first-order weight) walk
+// the staged rows in non-zero order -- one LDS + one FADD per row instead of five shuffles, and no
+// load latency inside the chain.
+template <int LPR>
+__device__ __forceinline__ void segsum_big_role(int block, int n_blocks, const int* seg_start,
+                                                const unsigned* perm, const RowSrc src, float* G, float* gw,
+                                                const int* big_list, const int* big_count, float* rows_s,
+                                                float* w_s) {
+  constexpr int K = 4 * LPR;
+  const int n_big = *big_count;
+  const int tid = threadIdx.x;
+  for (int bi = block; bi < n_big; bi += n_blocks) {
+    const int seg = big_list[bi];
+    const int start = seg_start[seg];
+    const int len = seg_start[seg + 1] - start;
+    float acc = 0.f;     // lane k < K of warp 0: component k; lane K: the weight gradient
+    for (int base = 0; base < len; base += BIG_CH) {
+      const int n = min(BIG_CH, len - base);
+      for (int q = tid; q < n * LPR; q += blockDim.x) {
+        const int j = q / LPR, sub = q - j * LPR;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float w = 0.f;
+        load_row<K>(src, (long long)perm[start + base + j], sub, v, w);
+        *reinterpret_cast<float4*>(rows_s + j * K + sub * 4) = v;
+        if (sub == 0) w_s[j] = w;
+      }
+      __syncthreads();
+      if (tid <= K) {
+        const float* col = tid < K ? rows_s + tid : w_s;
+        const int stride = tid < K ? K : 1;
+#pragma unroll 8
+        for (int j = 0; j < n; ++j) acc += col[j * stride];
+      }
+      __syncthreads();
+    }
+    if (tid < K && G && src.has_e) G[(long long)seg * K + tid] = acc;
+    if (tid == K && gw && src.has_w) gw[seg] = acc;
+  }
+}
+
 // ONE launch: the first l_blocks blocks take the hot ids (one warp each: they run longest, so they
 // start first), the others the short segments.  The hot-id list comes from the sort half.
 template <int LPR>
-__global__ void __launch_bounds__(256) segsum_kernel(int l_blocks, const int* n_unique, const int* seg_start,
-                                                     const unsigned* perm, const float* dE, const float* dw,
-                                                     float* G, float* gw, const int* long_list,
-                                                     const int* long_count) {
-  if ((int)blockIdx.x < l_blocks)
-    segsum_long_role<LPR>(blockIdx.x, l_blocks, seg_start, perm, dE, dw, G, gw, long_list, long_count);
-  else
-    segsum_short_role<LPR>(blockIdx.x - l_blocks, gridDim.x - l_blocks, n_unique, seg_start, perm, dE, dw, G, gw);
+__global__ void __launch_bounds__(256, 4) segsum_kernel(int b_blocks, int l_blocks, long long n, const int* seg_idx,
+                                                     const int* seg_start, const unsigned* perm,
+                                                     const RowSrc src, float* G, float* gw,
+                                                     const int* long_list, const int* big_list,
+                                                     const int* counts) {
+  constexpr int SK = 4 * LPR <= BIG_MAX_K ? 4 * LPR : 1;   // wider rows never reach the big role (seg_long_kernel)
+  __shared__ __align__(16) float rows_s[BIG_CH * SK];
+  __shared__ float w_s[BIG_CH];
+  const int b = (int)blockIdx.x;
+  if (b < b_blocks) {
+    if (4 * LPR <= BIG_MAX_K)
+      segsum_big_role<LPR>(b, b_blocks, seg_start, perm, src, G, gw, big_list, counts + 1, rows_s, w_s);
+  } else if (b < b_blocks + l_blocks) {
+    segsum_long_role<LPR>(b - b_blocks, l_blocks, seg_start, perm, src, G, gw, long_list, counts);
+  } else {
+    segsum_short_role<LPR>(b - b_blocks - l_blocks, gridDim.x - b_blocks - l_blocks, n, seg_idx, perm, src, G, gw);
+  }
 }
 
 // any K: one thread per (segment, k), strictly sequential
@@ -323,14 +405,24 @@ static int launch_segsum(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) 
   const unsigned* perm = ws.vals_b.as<unsigned>();
   int* counters = ws.counters.as<int>();
   int* long_list = ws.long_list.as<int>();
-  long long groups = a.n;  // upper bound on the number of segments
-  int grid = cdiv(groups * LPR, 256);
+  int grid = cdiv(a.n * LPR, 256);   // one lane group per sorted position (grid-stride beyond 8 blocks per SM)
   if (grid > 148 * 8) grid = 148 * 8;
-  long long max_long = a.n / LONG_T + 1;
+  long long max_long = a.n / (LONG_T + 1) + 1;
   int lgrid = cdiv(max_long * 32, 256);
-  if (lgrid > 148) lgrid = 148;
-  B200_LAUNCH((segsum_kernel<LPR>), lgrid + grid, 256, 0, st, lgrid, a.n_unique, seg_start, perm, a.dE, a.dw,
-              a.G, a.gw, long_list, counters);
+  if (lgrid > 148 * 4) lgrid = 148 * 4;     // ~5 000 segments of a Criteo-shaped batch of 8192 exceed 4 rows: one warp each
+  RowSrc src;
+  src.dE = a.dE; src.dw = a.dw;
+  src.fused = a.fused;
+  if (a.fused) {
+    src.X = a.fX; src.dX = a.fdX; src.S = a.fS; src.dlogit = a.fdlogit; src.F = a.fF > 0 ? a.fF : 1;
+    src.dE_keep = a.keep_dE; src.dw_keep = a.keep_dw;
+  }
+  src.has_e = a.fused ? (a.G != nullptr) : (a.dE != nullptr);
+  src.has_w = a.fused ? (a.gw != nullptr) : (a.dw != nullptr);
+  const int* big_list = long_list + (ws.cap_n + 8) / LONG_T;
+  const int bgrid = 148;     // one block per very hot id; a Criteo-shaped batch of 8192 has ~270 of them
+  B200_LAUNCH((segsum_kernel<LPR>), bgrid + lgrid + grid, 256, 0, st, bgrid, lgrid, a.n, ws.vals_a.as<int>(), seg_start, perm, src,
+              a.fused || a.dE ? a.G : nullptr, a.fused || a.dw ? a.gw : nullptr, long_list, big_list, counters);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(THREADS) dz_pack_kernel(int F, int H, int C, c
       for (int e = 0; e < 4; ++e)
         if (k0 + e < C) v[e] = __ldg(W + (long long)(k0 + e) * FH + (long long)i * H + j);
     }
-    split_store(hi, lo, swz(r, c), make_float4(v[0], v[1], v[2], v[3]));
+    split_store(hi, lo, r, c, make_float4(v[0], v[1], v[2], v[3]), true);
   }
 }
 
@@ -96,7 +96,7 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     if (leader) {
-      const uint32_t idesc = make_idesc(DZ_BN);
+      const uint32_t idesc = make_idesc(DZ_BN), idesc_bf = make_idesc_bf16(DZ_BN);
       int g = 0, sb = 0, bphase = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int buf = t & 1;
@@ -114,15 +114,8 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
           char* b_hi = bbase + sb * DZ_B_STAGE;
           const uint64_t dah = make_desc(smem_u32(a_hi)), dal = make_desc(smem_u32(a_hi + A_TILE_BYTES));
           const uint64_t dbh = make_desc(smem_u32(b_hi)), dbl = make_desc(smem_u32(b_hi + DZ_BN * 128));
-          const int ksteps = (s.kvalid(kb) + UK - 1) / UK;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4);
-            mma_tf32(acc, dah + adv, dbh + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-            if (PASSES == 3) {
-              mma_tf32(acc, dal + adv, dbh + adv, idesc, 1u);
-              mma_tf32(acc, dah + adv, dbl + adv, idesc, 1u);
-            }
-          }
+          const int kvalid = s.kvalid(kb);
+          mma_block<PASSES>(acc, dah, dal, dbh, dbl, 0, idesc, idesc_bf, (kvalid + UK - 1) / UK, kvalid, kb == 0);
           mma_commit(bar_empty + 8 * st);
           if (++sb == DZ_NB) { sb = 0; bphase ^= 1; }
         }

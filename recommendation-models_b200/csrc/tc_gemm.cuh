@@ -10,11 +10,18 @@
 // directly in the canonical K-major SWIZZLE_128B layout tcgen05.mma reads through its smem
 // descriptor, and the 1x1 compression runs on the tensor cores with the accumulator in TMEM.
 //
-// Why 3xTF32: the parity bar is 1e-5 relative in fp32 (BigDL's Linear/MM are MKL sgemm).  A single
-// TF32 pass carries 10 mantissa bits (about 1e-3).  Each operand is split as x = hi + lo with
-// hi = x & 0xffffe000 (exactly what the tensor core keeps of an fp32 word) and lo = x - hi (exact),
-// and D += Ahi*Bhi + Alo*Bhi + Ahi*Blo: the dropped lo*lo term is 2^-22 relative.  The producers
-// write both parts, so the split costs two ALU ops per element and no extra memory pass.
+// Why an error-compensated split: the parity bar is 1e-5 relative in fp32 (BigDL's Linear/MM are MKL
+// sgemm).  A single TF32 pass carries 10 mantissa bits (about 1e-3).  Each operand is split as
+// x = hi + lo with hi = tf32_rn(x) (11 significant bits: exactly what the tensor core keeps of an fp32
+// word) and lo = x - hi (exact, |lo| <= 2^-12 |x|), and
+//     D += Ahi*Bhi  (kind::tf32)  +  Ahi*Blo + Alo*Bhi  (kind::f16 on bf16 copies).
+// The two correction terms are 2^-12 of the result, so their operands only need bf16's 8 bits (their
+// rounding costs 2^-9 * 2^-12 = 2^-21 relative, the level of the dropped lo*lo term): they run as ONE
+// bf16 contraction of K = 64 per 32-wide K-block -- the A correction row is [hi | lo] (32 + 32 bf16 =
+// one 128-byte swizzle row), the B correction row is [lo | hi] -- at twice the TF32 rate and half its
+// shared-memory operand traffic.  Per K-block: 4 TF32 MMAs + 4 BF16 MMAs instead of 12 TF32 MMAs
+// (round 1's 3xTF32): the tensor ceiling rises from 1/3 to 1/2 of the TF32 peak at the same accuracy
+// (measured 1.5e-6 -> see DESIGN.md).  The producers write both tiles; same shared-memory footprint.
 //
 // Structure (one CTA = one 128 x BN output tile, BN <= 256, 1 CTA / SM, warp-specialised; see
 // gemm_ws_kernel below): a 2-stage ring of {A_hi, A_lo} tiles filled by 8 producer warps
@@ -114,6 +121,35 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A * B, BF16 inputs (K = 16 per instruction), fp32 accumulate
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// All MMAs of one 32-wide K-block into the accumulator columns at `acc`: `ksteps` TF32 K-steps on the hi
+// tiles and, with PASSES == 3, as many bf16 K-steps (16 positions = 8 K values x {hi*lo, lo*hi}) on the
+// correction tiles.  boff: descriptor offset of the first B row.
+template <int PASSES>
+__device__ __forceinline__ void mma_block(uint32_t acc, uint64_t da_hi, uint64_t da_corr, uint64_t db_hi,
+                                          uint64_t db_corr, uint64_t boff, uint32_t idesc, uint32_t idesc_bf,
+                                          int ksteps, int kvalid, bool fresh) {
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4);
+    mma_tf32(acc, da_hi + adv, db_hi + adv + boff, idesc, (!fresh || ks != 0) ? 1u : 0u);
+  }
+  if (PASSES == 3) {
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint64_t adv = (uint64_t)(ks * 32 >> 4);
+      mma_bf16(acc, da_corr + adv, db_corr + adv + boff, idesc_bf, 1u);
+    }
+  }
+  (void)kvalid;
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -191,21 +227,41 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
+// the same for kind::f16 with BF16 (1) operands, fp32 accumulate
+__device__ __forceinline__ uint32_t make_idesc_bf16(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 
 // byte offset of 16-byte chunk c (0..7) of row r inside a [rows x 128 B] SWIZZLE_128B K-major tile
 __device__ __forceinline__ uint32_t swz(int r, int c) {
   return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
 }
-// x = hi + lo, hi = the 19 bits the tensor core keeps; both stored as fp32 words
-__device__ __forceinline__ void split_store(char* hi, char* lo, uint32_t off, float4 v) {
-  float4 h, l;
-  h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-  h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-  h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-  h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo_elem, float hi_elem) {   // {hi_elem, lo_elem} packed
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+// The 4 consecutive K values v of tile row r, 16-byte chunk c (K = 4c .. 4c+3 of the 32-wide block):
+//   hi tile   [rows x 32 tf32]  chunk c  <- tf32_rn(v)
+//   corr tile [rows x 64 bf16]  chunk c  <- A operand { bf16(hi) x4 | bf16(lo) x4 },  B operand { lo x4 | hi x4 }
+// The correction contraction only needs A and B to pair the same K value at the same position, so the
+// hi / lo copies of a K quad sit side by side in ONE 16-byte chunk: one conflict-free 128-bit store per
+// tile (a [hi half | lo half] row layout costs two 4-way-conflicted 64-bit stores), and bf16 K-step s
+// (16 positions = chunks 2s, 2s+1) covers exactly the K values of TF32 K-step s.
+// Both tiles are K-major SWIZZLE_128B.
+__device__ __forceinline__ void split_store(char* hi, char* corr, int r, int c, float4 v, bool is_b) {
+  float4 h;
+  h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+  const uint32_t off = swz(r, c);
   *reinterpret_cast<float4*>(hi + off) = h;
-  *reinterpret_cast<float4*>(lo + off) = l;
+  const uint32_t h0 = bf16x2_rn(h.x, h.y), h1 = bf16x2_rn(h.z, h.w);
+  const uint32_t l0 = bf16x2_rn(v.x - h.x, v.y - h.y), l1 = bf16x2_rn(v.z - h.z, v.w - h.w);
+  *reinterpret_cast<uint4*>(corr + off) = is_b ? make_uint4(l0, l1, h0, h1) : make_uint4(h0, h1, l0, l1);
 }
 
 // ---- K schedules: which 32-wide window of the contraction each stage covers ---------------------
@@ -258,6 +314,7 @@ struct RowProd {
   const float* p; long long ld; int rows_total; int tile_rows; bool vec;
   Sched s;
   int row0, tid;
+  bool is_b = false;   // B operand: the correction tile is [lo | hi] instead of [hi | lo] (split_store)
   float4 reg[MAXT];
   float4 reg2[MAXT];   // second prefetch slot (packed-B kernel: loads fly two stages ahead)
   template <int SLOT> __device__ __forceinline__ void prefetch2(int kb) {
@@ -297,7 +354,7 @@ struct RowProd {
     for (int t = 0; t < MAXT; ++t) {
       const int q = tid + t * THREADS;
       const int r = q >> 3, c = q & 7;
-      if (r < tile_rows) split_store(hi, lo, swz(r, c), src[t]);
+      if (r < tile_rows) split_store(hi, lo, r, c, src[t], is_b);
     }
   }
 };
@@ -314,6 +371,7 @@ struct ColProd {
   const float* p; long long ld; int rows_total; int tile_rows; bool vec;
   Sched s;
   int row0, tid;
+  bool is_b = false;   // B operand: the correction tile is [lo | hi] instead of [hi | lo] (split_store)
   float4 reg[MAXT];
   static constexpr int DIST = 1;
   template <int SLOT> __device__ __forceinline__ void prefetch2(int kb) { prefetch(kb); }
@@ -365,7 +423,7 @@ struct ColProd {
         const int c = q & 7, r = 4 * (q >> 3);
         if (r < tile_rows) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) split_store(hi, lo, swz(r + e, c), reg[4 * t + e]);
+          for (int e = 0; e < 4; ++e) split_store(hi, lo, r + e, c, reg[4 * t + e], is_b);
         }
       }
       return;
@@ -375,7 +433,7 @@ struct ColProd {
 #pragma unroll
     for (int t = 0; t < MAXT; ++t) {
       const int c = (tid / ROWS) + t * (THREADS / ROWS);
-      split_store(hi, lo, swz(r, c), reg[t]);
+      split_store(hi, lo, r, c, reg[t], is_b);
     }
   }
 };
@@ -440,7 +498,7 @@ struct CinZProd {
       const int q = tid + t * THREADS;
       const int r = q >> 3, c = q & 7;
       const float a = x0v[t];
-      split_store(hi, lo, swz(r, c), make_float4(a * xr[t].x, a * xr[t].y, a * xr[t].z, a * xr[t].w));
+      split_store(hi, lo, r, c, make_float4(a * xr[t].x, a * xr[t].y, a * xr[t].z, a * xr[t].w), false);
     }
   }
 };
@@ -502,11 +560,11 @@ struct CinZtProd {
     if (vec) {
       const int c = tid & 7, r = 4 * (tid >> 3);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) split_store(hi, lo, swz(r + e, c), reg[e]);
+      for (int e = 0; e < 4; ++e) split_store(hi, lo, r + e, c, reg[e], false);
       return;
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) split_store(hi, lo, swz(tid & 127, (tid >> 7) + 2 * t), reg[t]);
+    for (int t = 0; t < 4; ++t) split_store(hi, lo, tid & 127, (tid >> 7) + 2 * t, reg[t], false);
   }
 };
 
@@ -704,6 +762,7 @@ __global__ void __launch_bounds__(THREADS) pack_b_kernel(int bn, int n_stride, S
   const int nkb = sched.nkb();
   const int tile = blockIdx.x;
   bp.s = sched;
+  bp.is_b = true;
   bp.init(nullptr, tile * n_stride, threadIdx.x);
   for (int kb = blockIdx.y; kb < nkb; kb += gridDim.y) {
     char* hi = blob + ((size_t)tile * nkb + kb) * (size_t)(2 * bn * 128);
@@ -728,12 +787,14 @@ __global__ void __launch_bounds__(THREADS) pack_linear_multi_kernel(PackJobs job
     if (!TRANSPOSED) {
       RowProd<8, KPlain> bp{jb.w, jb.K, jb.N, jb.bn, (jb.K % 4 == 0) && al};
       bp.s = KPlain{0, jb.K, jb.K};
+      bp.is_b = true;
       bp.init(nullptr, tile * jb.bn, threadIdx.x);
       bp.prefetch(kb);
       bp.store(kb, hi, hi + jb.bn * 128);
     } else {
       ColProd<256, KPlain> bp{jb.w, jb.K, jb.K, jb.bn, (jb.K % 4 == 0) && al};
       bp.s = KPlain{0, jb.N, jb.N};
+      bp.is_b = true;
       bp.init(nullptr, tile * jb.bn, threadIdx.x);
       bp.prefetch(kb);
       bp.store(kb, hi, hi + jb.bn * 128);
@@ -830,6 +891,8 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     if (leader) {
       const uint32_t idesc = make_idesc(bn), idesc0 = make_idesc(h0), idesc1 = make_idesc(h1 > 0 ? h1 : 16);
+      const uint32_t idesc_bf = make_idesc_bf16(bn), idesc0_bf = make_idesc_bf16(h0),
+                     idesc1_bf = make_idesc_bf16(h1 > 0 ? h1 : 16);
       int sb = 0, bphase = 0, cpos = 0, cidx = 0;   // B ring slot / its phase, position in / index of the chunk
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb & 1;
@@ -846,46 +909,24 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         char* b_hi = bbase + sb * b_stage;
         const uint64_t dah = make_desc(smem_u32(a_hi)), dal = make_desc(smem_u32(a_hi + A_TILE_BYTES));
         const uint64_t dbh = make_desc(smem_u32(b_hi)), dbl = make_desc(smem_u32(b_hi + bn * 128));
-        const int ksteps = (s.kvalid(kb) + UK - 1) / UK;
+        const int kvalid = s.kvalid(kb);
+        const int ksteps = (kvalid + UK - 1) / UK;
+        const bool fresh = chunk_start;   // the first MMA of a chunk overwrites the accumulator
         if (opens || closes) {
           const uint64_t boff = (uint64_t)(h0 * 128 >> 4);   // B rows [h0, bn) of the stage image
           if (opens) {
             mbar_wait(bar_drained0, (cidx - 1) & 1);
             tc_fence_after();
           }
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4);
-            mma_tf32(tmem, dah + adv, dbh + adv, idesc0, (!chunk_start || ks != 0) ? 1u : 0u);
-            if (PASSES == 3) {
-              mma_tf32(tmem, dal + adv, dbh + adv, idesc0, 1u);
-              mma_tf32(tmem, dah + adv, dbl + adv, idesc0, 1u);
-            }
-          }
+          mma_block<PASSES>(tmem, dah, dal, dbh, dbl, 0, idesc0, idesc0_bf, ksteps, kvalid, fresh);
           if (closes) mma_commit(bar_half);
           if (opens) {
             mbar_wait(bar_drained, (cidx - 1) & 1);
             tc_fence_after();
           }
-          if (h1 > 0) {
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4) + boff;
-              const uint64_t ada = (uint64_t)(ks * UK * 4 >> 4);
-              mma_tf32(tmem + h0, dah + ada, dbh + adv, idesc1, (!chunk_start || ks != 0) ? 1u : 0u);
-              if (PASSES == 3) {
-                mma_tf32(tmem + h0, dal + ada, dbh + adv, idesc1, 1u);
-                mma_tf32(tmem + h0, dah + ada, dbl + adv, idesc1, 1u);
-              }
-            }
-          }
+          if (h1 > 0) mma_block<PASSES>(tmem + h0, dah, dal, dbh, dbl, boff, idesc1, idesc1_bf, ksteps, kvalid, fresh);
         } else {
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4);
-            mma_tf32(tmem, dah + adv, dbh + adv, idesc, (!chunk_start || ks != 0) ? 1u : 0u);
-            if (PASSES == 3) {
-              mma_tf32(tmem, dal + adv, dbh + adv, idesc, 1u);
-              mma_tf32(tmem, dah + adv, dbl + adv, idesc, 1u);
-            }
-          }
+          mma_block<PASSES>(tmem, dah, dal, dbh, dbl, 0, idesc, idesc_bf, ksteps, kvalid, fresh);
         }
         mma_commit(bar_empty + 8 * st);
         TC_TRACE(0, kb, 3);
@@ -901,6 +942,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
     ap.init(nullptr, m0, tid);
     if (!PACKED) {
       bp.s = s;
+      bp.is_b = true;
       bp.init(nullptr, n0, tid);
     }
     const char* myblob = bblob + ((size_t)blockIdx.x * blob_nkb + (size_t)blockIdx.z * blob_kb_per_split) * b_stage;

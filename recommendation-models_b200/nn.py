@@ -9,6 +9,8 @@ Tensors are numpy float32 arrays (the Scala shim passes Array[Float] storage the
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
 from . import _lib as L
@@ -199,3 +201,130 @@ class Linear(_Module):
         self.gradWeight[...] = 0
         if self.gradBias is not None:
             self.gradBias[...] = 0
+
+
+# ---- the encoders (dense branches), rec/model/{encoder,xdeepfm,dcn,pnn}/*Encoder.scala -------------------
+class _Encoder:
+    """forward(input) -> output, backward(input, gradOutput) -> gradInput with the parameter gradients
+    copied over `self.mats[start:...]` at the parameters' offsets -- the reference encoders' contract
+    (e.g. HigherOrderEncoder.scala:18-32).  The BigDL triple is available too."""
+    _abi = None
+    _kind = None
+
+    def __init__(self, batchSize, mats, start, handle_args, device=0):
+        from .models import make_model
+        self.batchSize, self.mats, self.start = int(batchSize), mats, int(start)
+        self._model = make_model(self._kind, *handle_args, device=device)
+        n = C.c_int64(0)
+        L.check(L.lib().b200rec_encoder_mats_len(self._model.handle, C.byref(n)))
+        self.matsLen = n.value
+        if self.start < 0 or self.start + self.matsLen > len(mats):
+            raise ValueError(f"mats has {len(mats)} elements, the encoder needs [{self.start}, {self.start + self.matsLen})")
+        self.output = self.gradInput = None
+
+    def _params(self):
+        return np.ascontiguousarray(self.mats[self.start:self.start + self.matsLen], np.float32)
+
+    def _fn(self, suffix):
+        return getattr(L.lib(), f"b200rec_{self._abi}_{suffix}")
+
+    def _in(self, input):
+        x = np.ascontiguousarray(np.asarray(input, np.float32).reshape(-1))
+        if x.size != self.batchSize * self.inputDim:
+            raise ValueError(f"input has {x.size} elements, expected {self.batchSize}*{self.inputDim}")
+        return x
+
+    def updateOutput(self, input):
+        x, p = self._in(input), self._params()
+        out = np.zeros((self.batchSize, self.outputDim), np.float32)
+        L.check(self._fn("update_output")(self._model.handle, self.batchSize, L.ptr(x), L.ptr(p), L.ptr(out)))
+        self.output = out
+        return out
+
+    forward = updateOutput
+
+    def updateGradInput(self, input, gradOutput):
+        x, p, go = self._in(input), self._params(), L.f32(np.asarray(gradOutput).reshape(-1))
+        gi = np.zeros(x.size, np.float32)
+        L.check(self._fn("update_grad_input")(self._model.handle, self.batchSize, L.ptr(x), L.ptr(p), L.ptr(go), L.ptr(gi)))
+        self.gradInput = gi
+        return gi
+
+    def accGradParameters(self, input, gradOutput, gradMats, scale=1.0):
+        """gradMats[start:...] += scale * parameter gradients (BigDL accGradParameters accumulates)."""
+        x, p, go = self._in(input), self._params(), L.f32(np.asarray(gradOutput).reshape(-1))
+        g = np.ascontiguousarray(gradMats[self.start:self.start + self.matsLen], np.float32)
+        L.check(self._fn("acc_grad_parameters")(self._model.handle, self.batchSize, L.ptr(x), L.ptr(p), L.ptr(go),
+                                                float(scale), L.ptr(g)))
+        gradMats[self.start:self.start + self.matsLen] = g
+
+    def backward(self, input, gradOutput):
+        x, p, go = self._in(input), self._params(), L.f32(np.asarray(gradOutput).reshape(-1))
+        gi = np.zeros(x.size, np.float32)
+        L.check(self._fn("backward")(self._model.handle, self.batchSize, L.ptr(x), L.ptr(p), L.ptr(go), L.ptr(gi)))
+        self.mats[self.start:self.start + self.matsLen] = p      # BackwardUtil.linearBackward: grads over mats
+        self.gradInput = gi
+        return gi
+
+    def close(self):
+        self._model.close()
+
+
+class HigherOrderEncoder(_Encoder):
+    """rec/model/encoder/HigherOrderEncoder.scala: HigherOrderEncoder(batchSize, inputDim, fcDims, mats, start)."""
+    _abi, _kind = "higher_order", "deepfm"
+
+    def __init__(self, batchSize, inputDim, fcDims, mats, start=0, reshape=True, device=0):
+        self.inputDim, self.outputDim = int(inputDim), 1
+        super().__init__(batchSize, mats, start, (int(inputDim), 1, list(fcDims)), device)
+
+
+class CINEncoder(_Encoder):
+    """rec/model/xdeepfm/CINEncoder.scala: CINEncoder(batchSize, nFields, embeddingDim, fcDims, cinDims, mats, start)."""
+    _abi, _kind = "cin", "xdeepfm"
+
+    def __init__(self, batchSize, nFields, embeddingDim, fcDims, cinDims, mats, start=0, device=0):
+        self.inputDim, self.outputDim = nFields * embeddingDim, 1
+        super().__init__(batchSize, mats, start, (nFields, embeddingDim, list(fcDims), list(cinDims)), device)
+
+
+class CrossEncoder(_Encoder):
+    """rec/model/dcn/CrossEncoder.scala: CrossEncoder(batchSize, nFields, embeddingDim, crossDepth, fcDims, mats, start)."""
+    _abi, _kind = "cross", "dcn"
+
+    def __init__(self, batchSize, nFields, embeddingDim, crossDepth, fcDims, mats, start=0, device=0):
+        self.inputDim, self.outputDim = nFields * embeddingDim, 1
+        super().__init__(batchSize, mats, start, (nFields, embeddingDim, list(fcDims), (), int(crossDepth)), device)
+
+
+class ProductEncoder(_Encoder):
+    """rec/model/pnn/ProductEncoder.scala: ProductEncoder(batchSize, nFields, embeddingDim, outputDim, mats, start)."""
+    _abi, _kind = "product", "pnn"
+
+    def __init__(self, batchSize, nFields, embeddingDim, outputDim, mats, start=0, device=0):
+        self.inputDim, self.outputDim = nFields * embeddingDim, int(outputDim)
+        super().__init__(batchSize, mats, start, (nFields, embeddingDim, [int(outputDim)]), device)
+
+
+class DuplicateTable(_Module):
+    """nn/DuplicateTable.scala: fan the input out to the member modules, sum their input gradients."""
+
+    def __init__(self, device=0):
+        super().__init__(device)
+        self.modules = []
+
+    def add(self, module):
+        self.modules.append(module)
+        return self
+
+    def updateOutput(self, input):
+        self.output = [m.forward(input) for m in self.modules]
+        return self.output
+
+    def updateGradInput(self, input, gradOutput):
+        gs = [np.asarray(m.updateGradInput(input, g), np.float32).reshape(-1) for m, g in zip(self.modules, gradOutput)]
+        stack = np.ascontiguousarray(np.stack(gs)) if gs else np.zeros((0, 0), np.float32)
+        out = np.zeros(stack.shape[1] if gs else 0, np.float32)
+        L.check(L.lib().b200rec_duplicate_table_update_grad_input(self.device, len(gs), out.size, L.ptr(stack), L.ptr(out)))
+        self.gradInput = out.reshape(np.asarray(input).shape)
+        return self.gradInput

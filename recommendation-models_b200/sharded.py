@@ -179,6 +179,10 @@ class GpuOps:
         self.stream.synchronize()
         if int(self.overflow.item()):
             self.overflow.zero_()
+            # the ids that found no slot were read as zero rows and flagged as bad ids too: consume those
+            # words, the overflow is the error to report
+            self.lib.b200rec_table_status(self.table.handle, 1, self.stream_ptr)
+            self.lib.b200rec_model_sync(self.model.handle)
             raise RuntimeError(
                 f"exchange bucket overflow: one (source, owner) bucket received more than cap={self.cap} distinct ids; "
                 "that step's rows / gradients are incomplete.  Build the sharded model with a larger cap "

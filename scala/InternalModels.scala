@@ -37,6 +37,29 @@ abstract class B200InternalModel(kind: Int, nFields: Int, embeddingDim: Int, fcD
   def close(): Unit = check(lib.b200rec_model_destroy(handle))
 }
 
+/** rec/model/lr/LR.scala:42-90 -- InternalLRModel has no constructor arguments and its forward / backward
+  * take no embedding / mats (RecModelType.BIAS_WEIGHT): the same C calls with NULL for both. */
+class InternalLRModel extends B200InternalModel(Kind.LR, 0, 0, Array.empty, Array.empty, 0) {
+  def forward(batchSize: Int, index: Array[Int], weights: Array[Float], bias: Array[Float]): Array[Float] =
+    forward(batchSize, index, weights, bias, null, null)
+  def backward(batchSize: Int, index: Array[Int], weights: Array[Float], bias: Array[Float],
+               targets: Array[Float]): Float =
+    backward(batchSize, index, weights, bias, null, null, targets)
+}
+
+/** FM (BASELINE configs[0]): the reference has the BIAS_WEIGHT_EMBEDDING plumbing
+  * (rec/model/ParRecModel.scala:401-437, rec/model/RecModel.scala:27-35,74-84) but no model class
+  * (SURVEY B-1); this is DeepFM minus the HigherOrderEncoder: first order + SecondOrderEncoder + bias. */
+class InternalFMModel(nFields: Int, embeddingDim: Int)
+  extends B200InternalModel(Kind.FM, nFields, embeddingDim, Array.empty, Array.empty, 0) {
+  def forward(batchSize: Int, index: Array[Int], weights: Array[Float], bias: Array[Float],
+              embedding: Array[Float]): Array[Float] =
+    forward(batchSize, index, weights, bias, embedding, null)
+  def backward(batchSize: Int, index: Array[Int], weights: Array[Float], bias: Array[Float],
+               embedding: Array[Float], targets: Array[Float]): Float =
+    backward(batchSize, index, weights, bias, embedding, null, targets)
+}
+
 class InternalDeepFMModel(nFields: Int, embeddingDim: Int, fcDims: Array[Int])
   extends B200InternalModel(Kind.DeepFM, nFields, embeddingDim, fcDims, Array.empty, 0)
 
@@ -48,6 +71,61 @@ class InternalDCNModel(nFields: Int, embeddingDim: Int, crossDepth: Int, fcDims:
 
 class InternalPNNModel(nFields: Int, embeddingDim: Int, fcDims: Array[Int])
   extends B200InternalModel(Kind.PNN, nFields, embeddingDim, fcDims, Array.empty, 0)
+
+/** The encoders with the reference's own constructor arguments and forward / backward signatures
+  * (rec/model/encoder/HigherOrderEncoder.scala:18-32, xdeepfm/CINEncoder.scala:36,60,
+  * dcn/CrossEncoder.scala:40,57, pnn/ProductEncoder.scala:34,43): Tensor storage in, Tensor out, the
+  * parameter gradients copied over mats(start ...) by backward like BackwardUtil.linearBackward. */
+abstract class B200Encoder(kind: Int, batchSize: Int, nFields: Int, embeddingDim: Int, fcDims: Array[Int],
+                           cinDims: Array[Int], crossDepth: Int, mats: Array[Float], start: Int,
+                           outputDim: Int) {
+  import com.intel.analytics.bigdl.tensor.Tensor
+  protected val handle: Pointer = {
+    val out = new PointerByReference()
+    check(lib.b200rec_model_create(kind, nFields, embeddingDim, fcDims, fcDims.length, cinDims, cinDims.length,
+      crossDepth, 0, out))
+    out.getValue
+  }
+  private val matsLen: Int = { val n = new com.sun.jna.ptr.LongByReference(); check(lib.b200rec_encoder_mats_len(handle, n)); n.getValue.toInt }
+  protected def fwd(in: Array[Float], p: Array[Float], out: Array[Float]): Int
+  protected def bwd(in: Array[Float], p: Array[Float], go: Array[Float], gi: Array[Float]): Int
+
+  def forward(input: Tensor[Float]): Tensor[Float] = {
+    val out = new Array[Float](batchSize * outputDim)
+    check(fwd(input.contiguous().storage().array(), java.util.Arrays.copyOfRange(mats, start, start + matsLen), out))
+    Tensor(out, Array(batchSize, outputDim))
+  }
+  def backward(input: Tensor[Float], gradOutput: Tensor[Float]): Tensor[Float] = {
+    val p = java.util.Arrays.copyOfRange(mats, start, start + matsLen)
+    val gi = new Array[Float](batchSize * nFields * embeddingDim)
+    check(bwd(input.contiguous().storage().array(), p, gradOutput.contiguous().storage().array(), gi))
+    System.arraycopy(p, 0, mats, start, matsLen)          // BackwardUtil.linearBackward: grads over mats
+    Tensor(gi, Array(batchSize, nFields * embeddingDim))
+  }
+}
+class HigherOrderEncoder(batchSize: Int, inputDim: Int, fcDims: Array[Int], mats: Array[Float], start: Int = 0)
+  extends B200Encoder(Kind.DeepFM, batchSize, inputDim, 1, fcDims, Array.empty, 0, mats, start, 1) {
+  protected def fwd(in: Array[Float], p: Array[Float], out: Array[Float]): Int = lib.b200rec_higher_order_update_output(handle, batchSize, in, p, out)
+  protected def bwd(in: Array[Float], p: Array[Float], go: Array[Float], gi: Array[Float]): Int = lib.b200rec_higher_order_backward(handle, batchSize, in, p, go, gi)
+}
+class CINEncoder(batchSize: Int, nFields: Int, embeddingDim: Int, fcDims: Array[Int], cinDims: Array[Int],
+                 mats: Array[Float], start: Int = 0)
+  extends B200Encoder(Kind.XDeepFM, batchSize, nFields, embeddingDim, fcDims, cinDims, 0, mats, start, 1) {
+  protected def fwd(in: Array[Float], p: Array[Float], out: Array[Float]): Int = lib.b200rec_cin_update_output(handle, batchSize, in, p, out)
+  protected def bwd(in: Array[Float], p: Array[Float], go: Array[Float], gi: Array[Float]): Int = lib.b200rec_cin_backward(handle, batchSize, in, p, go, gi)
+}
+class CrossEncoder(batchSize: Int, nFields: Int, embeddingDim: Int, crossDepth: Int, fcDims: Array[Int],
+                   mats: Array[Float], start: Int = 0)
+  extends B200Encoder(Kind.DCN, batchSize, nFields, embeddingDim, fcDims, Array.empty, crossDepth, mats, start, 1) {
+  protected def fwd(in: Array[Float], p: Array[Float], out: Array[Float]): Int = lib.b200rec_cross_update_output(handle, batchSize, in, p, out)
+  protected def bwd(in: Array[Float], p: Array[Float], go: Array[Float], gi: Array[Float]): Int = lib.b200rec_cross_backward(handle, batchSize, in, p, go, gi)
+}
+class ProductEncoder(batchSize: Int, nFields: Int, embeddingDim: Int, outputDim: Int, mats: Array[Float],
+                     start: Int = 0)
+  extends B200Encoder(Kind.PNN, batchSize, nFields, embeddingDim, Array(outputDim), Array.empty, 0, mats, start, outputDim) {
+  protected def fwd(in: Array[Float], p: Array[Float], out: Array[Float]): Int = lib.b200rec_product_update_output(handle, batchSize, in, p, out)
+  protected def bwd(in: Array[Float], p: Array[Float], go: Array[Float], gi: Array[Float]): Int = lib.b200rec_product_backward(handle, batchSize, in, p, go, gi)
+}
 
 /** The resident replacement of ParRecModel's pull / optimize / push cycle
   * (rec/model/ParRecModel.scala:439-478): table and dense params live on the GPU, a step is one call.

@@ -116,3 +116,31 @@ def test_step_graph_replay(gpu_pkg, name):
         if om is not None:
             assert_close(res["mats_grad"], om, what=f"mats_grad step {step}", rtol=2e-5)
     model.close(); table.close()
+
+
+@pytest.mark.parametrize("name", ["fm", "deepfm", "xdeepfm"])
+def test_fused_scatter_is_bit_identical(gpu_pkg, name):
+    """b200rec_model_set_fused_scatter: the per-nnz gradient computed inside the segment reduce must give
+    the same bits as the two-kernel path (same arithmetic, same non-zero order), with and without the
+    per-nnz gradients kept."""
+    synth = gpu_pkg.synth
+    cfg = CONFIGS[name]
+    F, K, rows, B = 39, 16, 39 * 40, 700          # small vocabulary: hot ids far beyond 64 rows, many 5..64
+    res = []
+    for fused, keep in ((0, 0), (1, 0), (1, 1)):
+        model = gpu_pkg.make_model(name, F, K, cfg.get("fc_dims", ()), cfg.get("cin_dims", ()))
+        gpu_pkg._lib.check(gpu_pkg.lib().b200rec_model_set_fused_scatter(model.handle, fused, keep))
+        table = gpu_pkg.EmbeddingTable(rows, K)
+        table.init_uniform(42, -0.3, 0.3)
+        ps = gpu_pkg.ParRecModel(model, table)
+        ps.setParams(np.array([0.1], np.float32), synth.init_mats(7, model.getMatsSize()))
+        _, feats = synth.make_feats(5, 1, B, F, rows)
+        targets = synth.make_targets(5, feats, B, F)
+        for _ in range(3):                        # eager, captured, replayed
+            ps.optimize(feats, targets)
+        res.append(ps.stepResults())
+        model.close(); table.close()
+    for r in res[1:]:
+        assert np.array_equal(r["unique"], res[0]["unique"])
+        assert np.array_equal(r["emb_grad"], res[0]["emb_grad"])
+        assert np.array_equal(r["w_grad"], res[0]["w_grad"])
