@@ -46,10 +46,11 @@ def _compile(src, force, hdr_m):
     return obj, True
 
 
-def build_trace():
-    """Debug variant with the in-kernel pipeline timeline (tc_gemm.cuh: B200_TC_TRACE)."""
-    out = os.path.join(HERE, "libb200rec_trace.so")
-    cmd = [NVCC, *FLAGS, "-DB200_TC_TRACE", "-shared", "-o", out, *_sources()]
+def build_trace(define="-DB200_TC_TRACE", name="libb200rec_trace.so"):
+    """Debug variant with the in-kernel pipeline timeline (tc_gemm.cuh: B200_TC_TRACE); `--variant
+    -DNAME out.so` builds any other one-define variant for an A/B measurement."""
+    out = os.path.join(HERE, name)
+    cmd = [NVCC, *FLAGS, define, "-shared", "-o", out, *_sources()]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(r.stderr)
@@ -76,7 +77,10 @@ def build(force=False, verbose=True):
 
 
 if __name__ == "__main__":
-    if "--trace" in sys.argv:
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_trace(sys.argv[i + 1], sys.argv[i + 2]))
+    elif "--trace" in sys.argv:
         print(build_trace())
     else:
         build(force="--force" in sys.argv)

@@ -65,11 +65,12 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
   float* xs0 = reinterpret_cast<float*>(bbase + DZ_NB * DZ_B_STAGE);      // [BM][DZ_XS]
   uint64_t* bars = reinterpret_cast<uint64_t*>(xs0 + BM * DZ_XS);
   const uint32_t bar_full = smem_u32(&bars[0]);        // +8*st : A stage filled (THREADS arrivals)
-  const uint32_t bar_empty = smem_u32(&bars[2]);       // +8*st : its MMAs done (commit)
-  const uint32_t bar_bfull = smem_u32(&bars[4]);       // +8*sb : B stage landed (tx bytes)
-  const uint32_t bar_accfull = smem_u32(&bars[7]);     // +8*buf: a tile's MMAs done (commit)
-  const uint32_t bar_accempty = smem_u32(&bars[9]);    // +8*buf: the tile's epilogue read it (THREADS)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  const uint32_t bar_bfull = smem_u32(&bars[2]);       // +8*sb : B stage landed (tx bytes)
+  const uint32_t bar_accfull = smem_u32(&bars[5]);     // +8*buf: a tile's MMAs done (commit)
+  const uint32_t bar_accempty = smem_u32(&bars[7]);    // +8*buf: the tile's epilogue read it (THREADS)
+  const uint32_t bar_done = smem_u32(&bars[9]);        // +8*(g % 6): the MMAs of stage g are done (one commit per
+                                                       // stage frees A slot g % 2 and B slot g % 3, see gemm_ws_kernel)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM;
   const KPlain s{0, C, C};
@@ -79,10 +80,10 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
 
   if (threadIdx.x == 0) {
     mbar_init(bar_full, THREADS); mbar_init(bar_full + 8, THREADS);
-    mbar_init(bar_empty, 1); mbar_init(bar_empty + 8, 1);
     mbar_init(bar_bfull, 1); mbar_init(bar_bfull + 8, 1); mbar_init(bar_bfull + 16, 1);
     mbar_init(bar_accfull, 1); mbar_init(bar_accfull + 8, 1);
     mbar_init(bar_accempty, THREADS); mbar_init(bar_accempty + 8, THREADS);
+    for (int i = 0; i < 6; ++i) mbar_init(bar_done + 8 * i, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -116,16 +117,30 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
           const uint64_t dbh = make_desc(smem_u32(b_hi)), dbl = make_desc(smem_u32(b_hi + DZ_BN * 128));
           const int kvalid = s.kvalid(kb);
           mma_block<PASSES>(acc, dah, dal, dbh, dbl, 0, idesc, idesc_bf, (kvalid + UK - 1) / UK, kvalid, kb == 0);
-          mma_commit(bar_empty + 8 * st);
+          mma_commit(bar_done + 8 * (g % 6));
           if (++sb == DZ_NB) { sb = 0; bphase ^= 1; }
         }
         mma_commit(bar_accfull + 8 * buf);
       }
     }
+  } else if (warp == 1) {
+    // ===================================== B loader (see gemm_ws_kernel) =====================================
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    if (leader) {
+      int sb = 0, round = 0;
+      for (int g = 0; g < G; ++g) {
+        if (g >= DZ_NB) mbar_wait(bar_done + 8 * ((g - DZ_NB) % 6), ((g - DZ_NB) / 6) & 1);
+        mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)DZ_B_STAGE);
+        bulk_g2s(smem_u32(bbase + sb * DZ_B_STAGE), blob + (size_t)g * DZ_B_STAGE, (uint32_t)DZ_B_STAGE,
+                 bar_bfull + 8 * sb);
+        if (++sb == DZ_NB) { sb = 0; ++round; }
+      }
+    }
   } else {
     // ============================ producers / epilogue warps ============================
-    const int tid = threadIdx.x - 32;
-    const int pw = warp - 1;                          // 0..7
+    const int tid = threadIdx.x - WS_PROD0;
+    const int pw = warp - 2;                          // 0..7
     const int set = pw >> 2;                          // which half of a tile's columns (2 values of j)
     const int rl = (warp & 3) * 32 + lane;            // accumulator row = TMEM lane
     const int row = m0 + rl;
@@ -138,14 +153,6 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
       xs0[r * DZ_XS + i] = (m0 + r < R && i < F) ? __ldg(x0 + (long long)(m0 + r) * F + i) : 0.f;
     }
     asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
-    auto issue_b = [&](int g) {
-      const int sb = g % DZ_NB;
-      mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)DZ_B_STAGE);
-      bulk_g2s(smem_u32(bbase + sb * DZ_B_STAGE), blob + (size_t)g * DZ_B_STAGE, (uint32_t)DZ_B_STAGE,
-               bar_bfull + 8 * sb);
-    };
-    if (tid == 0)
-      for (int g = 0; g < DZ_NB && g < G; ++g) issue_b(g);
     if (G > 0) ap.template prefetch2<0>(0);
     if (G > 1) ap.template prefetch2<1>(1 % nkb);
 
@@ -212,19 +219,16 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
     auto stage = [&](auto slot_tag, int g) {
       constexpr int P = decltype(slot_tag)::value;
       char* a_hi = base + P * 2 * A_TILE_BYTES;
-      if (g >= STAGES) {
-        mbar_wait(bar_empty + 8 * P, ((g >> 1) - 1) & 1);     // MMA(g-2) drained: stage P is free
-        if (tid == 0 && g - 2 + DZ_NB < G) issue_b(g - 2 + DZ_NB);
-      }
+      if (g >= STAGES) mbar_wait(bar_done + 8 * ((g - 2) % 6), ((g - 2) / 6) & 1);   // MMA(g-2) done: stage P is free
       ap.template store2<P>(kb, a_hi, a_hi + A_TILE_BYTES);
-      if (g + 2 < G) {
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * P);
+      if (g + 2 < G) {     // after the hand-off: the stage's MMAs must not wait for these loads to be issued
         int kb2 = kb + 2;
         if (kb2 >= nkb) kb2 -= nkb;
         if (kb2 >= nkb) kb2 -= nkb;   // nkb == 1
         ap.template prefetch2<P>(kb2);
       }
-      fence_proxy_async();
-      mbar_arrive(bar_full + 8 * P);
       // the previous tile's epilogue, one piece per stage from its second stage on (stage (t, 1) could
       // only be produced after the last MMA of tile t - 1 completed), the rest at the tile's last stage
       if (t > 0) {

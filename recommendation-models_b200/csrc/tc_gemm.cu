@@ -11,8 +11,18 @@
 namespace b200rec {
 namespace tc {
 
-// K-blocks per TMEM accumulation chunk in the parity-grade mode (4 x 32 = 128 of K)
-static constexpr int KC_PRECISE = 4;
+// K-blocks per TMEM accumulation chunk in the parity-grade mode, and the longest contraction (in
+// K-blocks) that stays in ONE accumulation.  tcgen05.mma accumulates with truncation, so a long
+// accumulation drifts linearly with the number of accumulating instructions; every chunk is therefore
+// added into a running sum with round-to-nearest by the CUDA cores (the "drain": 2 x 106 KB of TMEM reads
+// per boundary at 64 B/clk -- about as long as the MMAs of 4 K-blocks, which is why the chunk is as long
+// as the error budget allows).  B200REC_KC / B200REC_KC_SHORT override them (measurement only).
+static int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e && *e ? std::atoi(e) : dflt;
+}
+static int kc_precise() { static const int v = env_int("B200REC_KC", 16); return v < 1 ? 1 : (v > 255 ? 255 : v); }
+static int kc_short() { static const int v = env_int("B200REC_KC_SHORT", 20); return v < 0 ? 0 : v; }
 static int round16(int n) { return (n + 15) / 16 * 16; }
 // widest tile <= 256 that splits N evenly
 static int pick_bn(int N) {
@@ -25,7 +35,7 @@ template <class AP, class BP, class Sched, class Ep, bool PACKED>
 static int launch_ws(const char* name, dim3 grid, int smem, int M, int N, int bn, int n_stride, int n_valid,
                      Sched sched, AP ap, BP bp, const char* blob, int blob_nkb, int blob_kb_per_split, Ep ep,
                      int passes, cudaStream_t st) {
-  const int kc = passes == 3 ? KC_PRECISE : 0;
+  const int kc = passes == 3 ? (kc_precise() | (kc_short() << 8)) : 0;
   const int smem_max = ws_smem_bytes(PACKED, PACKED ? 208 : 256);
   if (passes == 3) {
     auto k = gemm_ws_kernel<AP, BP, Sched, Ep, 3, PACKED>;

@@ -255,12 +255,26 @@ __device__ __forceinline__ uint32_t bf16x2_rn(float lo_elem, float hi_elem) {   
 // (16 positions = chunks 2s, 2s+1) covers exactly the K values of TF32 K-step s.
 // Both tiles are K-major SWIZZLE_128B.
 __device__ __forceinline__ void split_store(char* hi, char* corr, int r, int c, float4 v, bool is_b) {
+  const uint32_t off = swz(r, c);
+#ifdef B200_SPLIT_CVT
   float4 h;
   h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
-  const uint32_t off = swz(r, c);
   *reinterpret_cast<float4*>(hi + off) = h;
   const uint32_t h0 = bf16x2_rn(h.x, h.y), h1 = bf16x2_rn(h.z, h.w);
   const uint32_t l0 = bf16x2_rn(v.x - h.x, v.y - h.y), l1 = bf16x2_rn(v.z - h.z, v.w - h.w);
+#else
+  // The same split with integer ALU ops only (the conversion pipe is narrow and the producers are on the
+  // critical path of the two-deep A ring): tf32 = round the 13 low mantissa bits away (add half an ulp,
+  // mask), bf16 = add half an ulp to the fp32 word and keep its upper 16 bits (PRMT packs two).
+  const uint32_t bx = (__float_as_uint(v.x) + 0x1000u) & 0xffffe000u, by = (__float_as_uint(v.y) + 0x1000u) & 0xffffe000u;
+  const uint32_t bz = (__float_as_uint(v.z) + 0x1000u) & 0xffffe000u, bw = (__float_as_uint(v.w) + 0x1000u) & 0xffffe000u;
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(bx, by, bz, bw);
+  const float lx = v.x - __uint_as_float(bx), ly = v.y - __uint_as_float(by);
+  const float lz = v.z - __uint_as_float(bz), lw = v.w - __uint_as_float(bw);
+  const uint32_t h0 = __byte_perm(bx + 0x8000u, by + 0x8000u, 0x7632), h1 = __byte_perm(bz + 0x8000u, bw + 0x8000u, 0x7632);
+  const uint32_t l0 = __byte_perm(__float_as_uint(lx) + 0x8000u, __float_as_uint(ly) + 0x8000u, 0x7632);
+  const uint32_t l1 = __byte_perm(__float_as_uint(lz) + 0x8000u, __float_as_uint(lw) + 0x8000u, 0x7632);
+#endif
   *reinterpret_cast<uint4*>(corr + off) = is_b ? make_uint4(l0, l1, h0, h1) : make_uint4(h0, h1, l0, l1);
 }
 
@@ -803,18 +817,24 @@ __global__ void __launch_bounds__(THREADS) pack_linear_multi_kernel(PackJobs job
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Warp-specialised kernel (the one the launchers use).  9 warps:
-//   warp 0      : one thread issues tcgen05.mma (<= 4 K-steps x 3 passes per stage) and commits the
-//                 stage's "empty" mbarrier; it never touches operand data
-//   warps 1..8  : 256 producer threads fill the A stage (and the B stage when B is not packed),
+// Warp-specialised kernel (the one the launchers use).  10 warps:
+//   warp 0      : one thread issues tcgen05.mma (4 TF32 + 4 bf16 K-steps per stage) and commits the
+//                 stage's "empty" mbarriers; it never touches operand data
+//   warp 1      : one thread issues the cp.async.bulk copies of packed B stages into their ring, paced by
+//                 the ring's own "bempty" mbarriers.  (Round 1 had producer thread 0 issue them inside its
+//                 stage routine: the in-kernel timeline showed ~550 cycles per stage between that
+//                 thread's wait and its first store -- the bulk-copy issue -- and the stage's "full"
+//                 barrier needs every producer, so every stage's MMAs started that much later.)
+//   warps 2..9  : 256 producer threads fill the A stage (and the B stage when B is not packed),
 //                 arrive on the stage's "full" mbarrier, and run up to STAGES ahead of the tensor
-//                 core -- there is no __syncthreads in the main loop.  Producer thread 0 also issues
-//                 the cp.async.bulk copies of packed B stages.  At every accumulation-chunk boundary
+//                 core -- there is no __syncthreads in the main loop.  At every accumulation-chunk boundary
 //                 the producers add the TMEM chunk accumulator P into the running sum S (RN) and
 //                 release the MMA warp through the "drained" mbarrier.  They are the epilogue warps.
-// barriers: full[0..1] (256 arrivals), empty[0..1] (tcgen05.commit), bfull[0..2] (tx bytes), drained.
+// barriers: full[0..1] (256 arrivals), empty[0..1] (tcgen05.commit), bfull[0..2] (tx bytes), bempty[0..2]
+// (tcgen05.commit), drained.
 // ----------------------------------------------------------------------------------------------------
-constexpr int WS_THREADS = 32 + THREADS;
+constexpr int WS_THREADS = 64 + THREADS;   // MMA warp + B-loader warp + 8 producer / epilogue warps
+constexpr int WS_PROD0 = 64;               // first producer thread
 constexpr int KC_SHORT = 8;
 #ifdef B200_TC_TRACE
 // debug timeline of CTA (0,0,0): [role][kb][slot] clock64 stamps (built only into libb200rec_trace.so)
@@ -848,12 +868,16 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
   char* bbase = base + TCB_A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bbase + NB * b_stage);
   const uint32_t bar_full = smem_u32(&bars[0]);    // +8*st
-  const uint32_t bar_empty = smem_u32(&bars[2]);   // +8*st
-  const uint32_t bar_bfull = smem_u32(&bars[4]);   // +8*sb
-  const uint32_t bar_drained = smem_u32(&bars[7]);    // second column half of a chunk drained into S
-  const uint32_t bar_half = smem_u32(&bars[8]);       // first column half of a chunk's last stage computed
-  const uint32_t bar_drained0 = smem_u32(&bars[9]);   // first column half drained into S
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const uint32_t bar_bfull = smem_u32(&bars[2]);   // +8*sb
+  const uint32_t bar_drained = smem_u32(&bars[5]);    // second column half of a chunk drained into S
+  const uint32_t bar_half = smem_u32(&bars[6]);       // first column half of a chunk's last stage computed
+  const uint32_t bar_drained0 = smem_u32(&bars[7]);   // first column half drained into S
+  // ONE tcgen05.commit per stage, on done[kb % 6]: it frees A slot kb % 2 (the producers of stage kb + 2
+  // wait for it) and B slot kb % 3 (the loader of stage kb + 3 does).  6 = lcm of the two ring depths, so a
+  // barrier completes once per 6 stages and nobody can fall a whole phase behind: the MMAs of stage kb + 6
+  // need the A stage and the B stage that are produced only after these waits.
+  const uint32_t bar_done = smem_u32(&bars[8]);       // +8*(kb % 6)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   // Accumulation-chunk boundaries are pipelined by column halves [0, h0) / [h0, bn): the chunk's last
   // stage and the next chunk's first stage issue their MMAs half by half, so that the drain of one
   // half (P -> S, CUDA cores) runs under the tensor work of the other instead of idling the pipe.
@@ -866,15 +890,20 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
   // A contraction of at most KC_SHORT K-blocks (K <= 256) stays in ONE accumulation: the truncation
   // drift is linear in K (5.7e-5 at K = 8192 -> 1.8e-6 at 256, the level of the 3xTF32 split itself),
   // so the P -> S drain would buy nothing (CIN dx0 runs 7-stage CTAs).
-  if (nkb <= KC_SHORT) kc = 0;
+  // (the host passes the threshold in the high bits of kc: kc = chunk | short_threshold << 8)
+  {
+    const int kc_short = kc >> 8;
+    kc &= 255;
+    if (nkb <= kc_short) kc = 0;
+  }
 
   if (threadIdx.x == 0) {
     mbar_init(bar_full, THREADS); mbar_init(bar_full + 8, THREADS);
-    mbar_init(bar_empty, 1); mbar_init(bar_empty + 8, 1);
     mbar_init(bar_bfull, 1); mbar_init(bar_bfull + 8, 1); mbar_init(bar_bfull + 16, 1);
     mbar_init(bar_drained, THREADS);
     mbar_init(bar_half, 1);
     mbar_init(bar_drained0, THREADS);
+    for (int i = 0; i < 6; ++i) mbar_init(bar_done + 8 * i, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -893,7 +922,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
       const uint32_t idesc = make_idesc(bn), idesc0 = make_idesc(h0), idesc1 = make_idesc(h1 > 0 ? h1 : 16);
       const uint32_t idesc_bf = make_idesc_bf16(bn), idesc0_bf = make_idesc_bf16(h0),
                      idesc1_bf = make_idesc_bf16(h1 > 0 ? h1 : 16);
-      int sb = 0, bphase = 0, cpos = 0, cidx = 0;   // B ring slot / its phase, position in / index of the chunk
+      int sb = 0, bphase = 0, cpos = 0, cidx = 0, d6 = 0;   // B ring slot / its phase, position in / index of the chunk, kb % 6
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb & 1;
         const bool chunk_start = kc > 0 ? (cpos == 0) : (kb == 0);
@@ -928,16 +957,34 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         } else {
           mma_block<PASSES>(tmem, dah, dal, dbh, dbl, 0, idesc, idesc_bf, ksteps, kvalid, fresh);
         }
-        mma_commit(bar_empty + 8 * st);
+        mma_commit(bar_done + 8 * d6);
         TC_TRACE(0, kb, 3);
+        if (++d6 == 6) d6 = 0;
         if (++sb == NB) { sb = 0; bphase ^= 1; }
         if (kc > 0 && ++cpos == kc) { cpos = 0; ++cidx; }
       }
     }
+  } else if (warp == 1) {
+    // ===================================== B loader =====================================
+    if (PACKED) {
+      uint32_t leader;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+      if (leader) {
+        const char* myblob = bblob + ((size_t)blockIdx.x * blob_nkb + (size_t)blockIdx.z * blob_kb_per_split) * b_stage;
+        int sb = 0, round = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (kb >= NB) mbar_wait(bar_done + 8 * ((kb - NB) % 6), ((kb - NB) / 6) & 1);   // the MMAs of stage kb - NB are done
+          mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)b_stage);
+          bulk_g2s(smem_u32(bbase + sb * b_stage), myblob + (size_t)kb * b_stage, (uint32_t)b_stage,
+                   bar_bfull + 8 * sb);
+          if (++sb == NB) { sb = 0; ++round; }
+        }
+      }
+    }
   } else {
     // ===================================== producers =====================================
-    const int tid = threadIdx.x - 32;
-    const int pw = warp - 1;               // 0..7
+    const int tid = threadIdx.x - WS_PROD0;
+    const int pw = warp - 2;               // 0..7
     ap.s = s;
     ap.init(nullptr, m0, tid);
     if (!PACKED) {
@@ -945,15 +992,6 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
       bp.is_b = true;
       bp.init(nullptr, n0, tid);
     }
-    const char* myblob = bblob + ((size_t)blockIdx.x * blob_nkb + (size_t)blockIdx.z * blob_kb_per_split) * b_stage;
-    auto issue_b = [&](int kb) {
-      const int sb = kb % NB;
-      mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)b_stage);
-      bulk_g2s(smem_u32(bbase + sb * b_stage), myblob + (size_t)kb * b_stage, (uint32_t)b_stage,
-               bar_bfull + 8 * sb);
-    };
-    if (PACKED && tid == 0)
-      for (int kb = 0; kb < NB && kb < nkb; ++kb) issue_b(kb);
     if (nkb > 0) {
       ap.template prefetch2<0>(0);
       if (!PACKED) bp.prefetch(0);
@@ -966,22 +1004,22 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
       constexpr int P = decltype(slot_tag)::value;
       char* a_hi = base + P * 2 * A_TILE_BYTES;
       if (tid == 0) TC_TRACE(1, kb, 0);
-      if (kb >= STAGES) {
-        mbar_wait(bar_empty + 8 * P, ((kb >> 1) - 1) & 1);     // MMA(kb-2) drained: stage P is free
-        if (PACKED && tid == 0 && kb - 2 + NB < nkb) issue_b(kb - 2 + NB);
-      }
+      if (kb >= STAGES) mbar_wait(bar_done + 8 * ((kb - 2) % 6), ((kb - 2) / 6) & 1);   // MMA(kb-2) done: stage P is free
       if (tid == 0) TC_TRACE(1, kb, 1);
       ap.template store2<P>(kb, a_hi, a_hi + A_TILE_BYTES);
       if (tid == 0) TC_TRACE(1, kb, 2);
       if (!PACKED) {
         char* b_hi = bbase + P * b_stage;
         bp.store(kb, b_hi, b_hi + bn * 128);
-        if (kb + 1 < nkb) bp.prefetch(kb + 1);
       }
-      if (kb + AP::DIST < nkb) ap.template prefetch2<(AP::DIST == 2 ? P : 1 - P)>(kb + AP::DIST);
+      // hand the stage to the MMA warp FIRST, then start the loads of a later stage: the prefetch (address
+      // math + 4..8 global loads per thread) used to sit between the stores and the arrive and delayed every
+      // stage's MMAs by a few hundred cycles
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * P);
       if (tid == 0) TC_TRACE(1, kb, 3);
+      if (!PACKED && kb + 1 < nkb) bp.prefetch(kb + 1);
+      if (kb + AP::DIST < nkb) ap.template prefetch2<(AP::DIST == 2 ? P : 1 - P)>(kb + AP::DIST);
       if (kc > 0 && kb > 0 && pcpos == 0) {
         // Stage kb (just produced, so the MMA warp can start it the moment it is released) opens a new
         // accumulation chunk; the previous one ended with stage kb-1, whose MMAs ran as two column
@@ -995,7 +1033,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {   // one copy of the drain code for both halves
           if (half == 0) mbar_wait(bar_half, bpar);
-          else mbar_wait(bar_empty + 8 * (P ^ 1), ((kb - 1) >> 1) & 1);
+          else mbar_wait(bar_done + 8 * ((kb - 1) % 6), ((kb - 1) / 6) & 1);
           tc_fence_after();
           const int c_lo = half ? h0 / 16 : 0, c_hi = half ? bn / 16 : h0 / 16;
           const int first = c_lo + ((c_lo & 1) != ch0 ? 1 : 0);   // this thread's parity of 16-column pieces
@@ -1049,7 +1087,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         if (row < M && (pw >> 2) * 16 < ncols)
           ep.load_aux(row, n0 + (pw >> 2) * 16, min(16, ncols - (pw >> 2) * 16), aux);
       }
-      mbar_wait(bar_empty + 8 * ((nkb - 1) & 1), ((nkb - 1) >> 1) & 1);
+      mbar_wait(bar_done + 8 * ((nkb - 1) % 6), ((nkb - 1) / 6) & 1);
       if (tid == 0) TC_TRACE(2, 511, 1);
       tc_fence_after();
       const bool add_s = kc > 0 && nkb > kc;   // result = S + P (the last chunk is still in P)
@@ -1117,7 +1155,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
       }
     }
   }
-  if (threadIdx.x == 32) TC_TRACE(2, 511, 2);
+  if (threadIdx.x == WS_PROD0) TC_TRACE(2, 511, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out; rm -f gpurun_out/parity_report.jsonl
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r02k_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02k_pytest.log
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/r02k_bench_int.json 2> gpurun_out/r02k_bench_int.err; echo "bench rc=$?"
+B200REC_LIB=$PWD/recommendation-models_b200/libb200rec_cvt.so timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/r02k_bench_cvt.json 2> gpurun_out/r02k_bench_cvt.err; echo "bench rc=$?"
+tail -4 gpurun_out/r02k_pytest.log

@@ -38,7 +38,7 @@ dump("linear dW (split-K)", 8)
 # CIN forward through a tiny xdeepfm forward
 F, K = 39, 16
 m = pkg.make_model("xdeepfm", F, K, [16], [200, 200])
-Bm = 64
+Bm = int(os.environ.get('TRACE_CIN_BATCH', '64'))
 n = Bm * F
 from oracle import refport
 mats = pkg.synth.init_mats(1, refport.mats_size("xdeepfm", F, K, [16], [200, 200]))
