@@ -27,9 +27,9 @@ constexpr int DZ_CHUNKS = DZ_HALF / 16;       // 5 tcgen05.ld of 16 columns per 
 constexpr int DZ_NB = 3;                      // B ring depth
 constexpr int DZ_B_STAGE = 2 * DZ_BN * 128;   // hi | lo image of one K-block
 constexpr int DZ_XS = DZ_FP + 1;              // row stride of the x0 tile in shared memory (conflict free)
-constexpr int DZ_TMEM_BUF = 256;              // column offset of the second accumulator
+constexpr int DZ_G = 3;                       // N tiles (accumulators) that share an A stage: 3 x 160 TMEM columns
 __host__ __device__ inline int dz_smem_bytes() {
-  return 1024 + TCB_A_BYTES + DZ_NB * DZ_B_STAGE + BM * DZ_XS * 4 + 256;
+  return 1024 + TCB_A_BYTES + DZ_NB * DZ_B_STAGE + BM * DZ_XS * 4 + 256;   // 256: 16 mbarriers + the TMEM slot
 }
 
 // weight image: blob[tile * nkb + kb] = {hi, lo}, row n = jl * FP + i  <->  W[c, i*H + tile*JT + jl],
@@ -59,6 +59,12 @@ template <int PASSES>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const float* __restrict__ x_in,
               RowProd<4, KPlain> ap, const char* __restrict__ blob, float* gx_in, bool gx_acc, float* gx0) {
+  // N tiles are swept in GROUPS of DZ_G = 3 that share every A stage: the gy tile of a K-block is split and
+  // stored once per group and feeds the MMAs of three accumulators (TMEM columns 0 / 160 / 320), so the
+  // producers do a third of round 1's work per MMA and the full / done hand-shakes happen once per 24 MMAs.
+  // The epilogue of group g - 1 (15 pieces of 16 columns) runs on the producer warps right after they have
+  // put the first two A stages of group g in flight; the MMA warp re-uses accumulator t as soon as its tile
+  // has been read (accempty[t]).
   extern __shared__ char smem_raw[];
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   char* bbase = base + TCB_A_BYTES;
@@ -66,24 +72,28 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
   uint64_t* bars = reinterpret_cast<uint64_t*>(xs0 + BM * DZ_XS);
   const uint32_t bar_full = smem_u32(&bars[0]);        // +8*st : A stage filled (THREADS arrivals)
   const uint32_t bar_bfull = smem_u32(&bars[2]);       // +8*sb : B stage landed (tx bytes)
-  const uint32_t bar_accfull = smem_u32(&bars[5]);     // +8*buf: a tile's MMAs done (commit)
-  const uint32_t bar_accempty = smem_u32(&bars[7]);    // +8*buf: the tile's epilogue read it (THREADS)
-  const uint32_t bar_done = smem_u32(&bars[9]);        // +8*(g % 6): the MMAs of stage g are done (one commit per
-                                                       // stage frees A slot g % 2 and B slot g % 3, see gemm_ws_kernel)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  const uint32_t bar_accfull = smem_u32(&bars[5]);     // +8*(grp & 1): a group's MMAs done (commit)
+  const uint32_t bar_accempty = smem_u32(&bars[7]);    // +8*t  : the epilogue has read accumulator t (THREADS)
+  const uint32_t bar_bdone = smem_u32(&bars[10]);      // +8*(bs % 6): the MMAs of B stage bs are done (commit); frees
+                                                       // B slot bs % 3 and, for a group's last tile, the A slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM;
   const KPlain s{0, C, C};
   const int nkb = s.nkb();
   const int n_tiles = (H + DZ_JT - 1) / DZ_JT;
-  const int G = n_tiles * nkb;   // stages of the whole sweep; stage g = (tile g / nkb, K-block g % nkb)
+  const int n_groups = (n_tiles + DZ_G - 1) / DZ_G;
+  const int AS = n_groups * nkb;                 // A stages of the whole sweep: as = grp * nkb + kb
+  auto tiles_in = [&](int grp) { return min(DZ_G, n_tiles - grp * DZ_G); };
+  // B stages issued before A stage `as` (every group before the last is full)
+  auto b_before = [&](int as) { const int grp = as / nkb, kb = as - grp * nkb; return grp * DZ_G * nkb + kb * tiles_in(grp); };
 
   if (threadIdx.x == 0) {
     mbar_init(bar_full, THREADS); mbar_init(bar_full + 8, THREADS);
     mbar_init(bar_bfull, 1); mbar_init(bar_bfull + 8, 1); mbar_init(bar_bfull + 16, 1);
     mbar_init(bar_accfull, 1); mbar_init(bar_accfull + 8, 1);
-    mbar_init(bar_accempty, THREADS); mbar_init(bar_accempty + 8, THREADS);
-    for (int i = 0; i < 6; ++i) mbar_init(bar_done + 8 * i, 1);
+    for (int i = 0; i < DZ_G; ++i) mbar_init(bar_accempty + 8 * i, THREADS);
+    for (int i = 0; i < 6; ++i) mbar_init(bar_bdone + 8 * i, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -98,29 +108,32 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     if (leader) {
       const uint32_t idesc = make_idesc(DZ_BN), idesc_bf = make_idesc_bf16(DZ_BN);
-      int g = 0, sb = 0, bphase = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        const int buf = t & 1;
-        if (t >= 2) {   // the epilogue of tile t - 2 must have read this accumulator
-          mbar_wait(bar_accempty + 8 * buf, ((t >> 1) - 1) & 1);
-          tc_fence_after();
-        }
-        const uint32_t acc = tmem + buf * DZ_TMEM_BUF;
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int st = g & 1;
-          mbar_wait(bar_full + 8 * st, (g >> 1) & 1);
-          mbar_wait(bar_bfull + 8 * sb, bphase);
+      int bs = 0, as = 0;
+      for (int grp = 0; grp < n_groups; ++grp) {
+        const int nt = tiles_in(grp);
+        for (int kb = 0; kb < nkb; ++kb, ++as) {
+          const int st = as & 1;
+          mbar_wait(bar_full + 8 * st, (as >> 1) & 1);
           tc_fence_after();
           char* a_hi = base + st * 2 * A_TILE_BYTES;
-          char* b_hi = bbase + sb * DZ_B_STAGE;
           const uint64_t dah = make_desc(smem_u32(a_hi)), dal = make_desc(smem_u32(a_hi + A_TILE_BYTES));
-          const uint64_t dbh = make_desc(smem_u32(b_hi)), dbl = make_desc(smem_u32(b_hi + DZ_BN * 128));
           const int kvalid = s.kvalid(kb);
-          mma_block<PASSES>(acc, dah, dal, dbh, dbl, 0, idesc, idesc_bf, (kvalid + UK - 1) / UK, kvalid, kb == 0);
-          mma_commit(bar_done + 8 * (g % 6));
-          if (++sb == DZ_NB) { sb = 0; bphase ^= 1; }
+          for (int t = 0; t < nt; ++t, ++bs) {
+            if (kb == 0 && grp > 0) {   // the epilogue of group grp - 1 must have read this accumulator
+              mbar_wait(bar_accempty + 8 * t, (grp - 1) & 1);
+              tc_fence_after();
+            }
+            const int sb = bs % DZ_NB;
+            mbar_wait(bar_bfull + 8 * sb, (bs / DZ_NB) & 1);
+            tc_fence_after();
+            char* b_hi = bbase + sb * DZ_B_STAGE;
+            const uint64_t dbh = make_desc(smem_u32(b_hi)), dbl = make_desc(smem_u32(b_hi + DZ_BN * 128));
+            mma_block<PASSES>(tmem + t * DZ_BN, dah, dal, dbh, dbl, 0, idesc, idesc_bf, (kvalid + UK - 1) / UK, kvalid,
+                              kb == 0);
+            mma_commit(bar_bdone + 8 * (bs % 6));
+          }
         }
-        mma_commit(bar_accfull + 8 * buf);
+        mma_commit(bar_accfull + 8 * (grp & 1));
       }
     }
   } else if (warp == 1) {
@@ -128,13 +141,18 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     if (leader) {
-      int sb = 0, round = 0;
-      for (int g = 0; g < G; ++g) {
-        if (g >= DZ_NB) mbar_wait(bar_done + 8 * ((g - DZ_NB) % 6), ((g - DZ_NB) / 6) & 1);
-        mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)DZ_B_STAGE);
-        bulk_g2s(smem_u32(bbase + sb * DZ_B_STAGE), blob + (size_t)g * DZ_B_STAGE, (uint32_t)DZ_B_STAGE,
-                 bar_bfull + 8 * sb);
-        if (++sb == DZ_NB) { sb = 0; ++round; }
+      int bs = 0;
+      for (int grp = 0; grp < n_groups; ++grp) {
+        const int nt = tiles_in(grp);
+        for (int kb = 0; kb < nkb; ++kb)
+          for (int t = 0; t < nt; ++t, ++bs) {
+            const int sb = bs % DZ_NB;
+            if (bs >= DZ_NB) mbar_wait(bar_bdone + 8 * ((bs - DZ_NB) % 6), ((bs - DZ_NB) / 6) & 1);
+            mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)DZ_B_STAGE);
+            bulk_g2s(smem_u32(bbase + sb * DZ_B_STAGE),
+                     blob + ((size_t)(grp * DZ_G + t) * nkb + kb) * DZ_B_STAGE, (uint32_t)DZ_B_STAGE,
+                     bar_bfull + 8 * sb);
+          }
       }
     }
   } else {
@@ -153,8 +171,8 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
       xs0[r * DZ_XS + i] = (m0 + r < R && i < F) ? __ldg(x0 + (long long)(m0 + r) * F + i) : 0.f;
     }
     asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
-    if (G > 0) ap.template prefetch2<0>(0);
-    if (G > 1) ap.template prefetch2<1>(1 % nkb);
+    if (AS > 0) ap.template prefetch2<0>(0);
+    if (AS > 1) ap.template prefetch2<1>(1 % nkb);
 
     float dx0acc[DZ_FP];
 #pragma unroll
@@ -191,15 +209,15 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
       }
     };
     auto epi_chunk = [&](int tile, int c) {
-      const int buf = tile & 1;
+      const int grp = tile / DZ_G, t = tile - grp * DZ_G;
       if (c == 0) {
-        mbar_wait(bar_accfull + 8 * buf, (tile >> 1) & 1);
+        mbar_wait(bar_accfull + 8 * (grp & 1), (grp >> 1) & 1);   // (complete already for the group's later tiles)
         tc_fence_after();
         xj[0] = xj_next[0]; xj[1] = xj_next[1];
         dxacc[0] = 0.f; dxacc[1] = 0.f;
       }
       float v[16];
-      tmem_ld16(tmem + lane_addr + buf * DZ_TMEM_BUF + set * DZ_HALF + c * 16, v);
+      tmem_ld16(tmem + lane_addr + t * DZ_BN + set * DZ_HALF + c * 16, v);
       switch (c) {
         case 0: epi_body(std::integral_constant<int, 0>{}, v); break;
         case 1: epi_body(std::integral_constant<int, 1>{}, v); break;
@@ -210,39 +228,43 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
           store_dx(tile, 1);
           load_xj(tile + 1, xj_next);       // next tile's x values: in flight for a whole tile
           tc_fence_before();
-          mbar_arrive(bar_accempty + 8 * buf);
+          mbar_arrive(bar_accempty + 8 * t);
           break;
       }
     };
+    auto epilogue_group = [&](int grp) {
+      const int t0 = grp * DZ_G, t1 = min(n_tiles, t0 + DZ_G);
+      for (int tile = t0; tile < t1; ++tile)
+        for (int c = 0; c < DZ_CHUNKS; ++c) epi_chunk(tile, c);
+    };
 
-    int t = 0, kb = 0, epi_done = 0;   // stage g = (t, kb); pieces of tile t - 1 already drained
-    auto stage = [&](auto slot_tag, int g) {
+    int grp = 0, kb = 0;
+    auto stage = [&](auto slot_tag, int as) {
       constexpr int P = decltype(slot_tag)::value;
       char* a_hi = base + P * 2 * A_TILE_BYTES;
-      if (g >= STAGES) mbar_wait(bar_done + 8 * ((g - 2) % 6), ((g - 2) / 6) & 1);   // MMA(g-2) done: stage P is free
+      if (as >= STAGES) {   // the MMAs of A stage as - 2 are done when its LAST B stage is
+        const int bl = b_before(as - 2) + tiles_in((as - 2) / nkb) - 1;
+        mbar_wait(bar_bdone + 8 * (bl % 6), (bl / 6) & 1);
+      }
       ap.template store2<P>(kb, a_hi, a_hi + A_TILE_BYTES);
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * P);
-      if (g + 2 < G) {     // after the hand-off: the stage's MMAs must not wait for these loads to be issued
+      if (as + 2 < AS) {     // after the hand-off: the stage's MMAs must not wait for these loads to be issued
         int kb2 = kb + 2;
         if (kb2 >= nkb) kb2 -= nkb;
         if (kb2 >= nkb) kb2 -= nkb;   // nkb == 1
         ap.template prefetch2<P>(kb2);
       }
-      // the previous tile's epilogue, one piece per stage from its second stage on (stage (t, 1) could
-      // only be produced after the last MMA of tile t - 1 completed), the rest at the tile's last stage
-      if (t > 0) {
-        const int want = kb == nkb - 1 ? DZ_CHUNKS : (kb < DZ_CHUNKS ? kb : DZ_CHUNKS);
-        while (epi_done < want) epi_chunk(t - 1, epi_done++);
-      }
-      if (++kb == nkb) { kb = 0; ++t; epi_done = 0; }
+      // the previous group's epilogue, once the first two A stages of this group are in flight (one when the
+      // contraction has a single K-block)
+      if (grp > 0 && kb == (nkb > 1 ? 1 : 0)) epilogue_group(grp - 1);
+      if (++kb == nkb) { kb = 0; ++grp; }
     };
-    for (int g0 = 0; g0 < G; g0 += 2) {
-      stage(std::integral_constant<int, 0>{}, g0);
-      if (g0 + 1 < G) stage(std::integral_constant<int, 1>{}, g0 + 1);
+    for (int a0 = 0; a0 < AS; a0 += 2) {
+      stage(std::integral_constant<int, 0>{}, a0);
+      if (a0 + 1 < AS) stage(std::integral_constant<int, 1>{}, a0 + 1);
     }
-    if (n_tiles > 0)
-      for (int c = 0; c < DZ_CHUNKS; ++c) epi_chunk(n_tiles - 1, c);
+    if (n_groups > 0) epilogue_group(n_groups - 1);
 
     // gx0[row, :] += the two column halves' sums (the x0 tile is no longer read: reuse it)
     asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");

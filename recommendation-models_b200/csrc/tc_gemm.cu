@@ -16,13 +16,16 @@ namespace tc {
 // accumulation drifts linearly with the number of accumulating instructions; every chunk is therefore
 // added into a running sum with round-to-nearest by the CUDA cores (the "drain": 2 x 106 KB of TMEM reads
 // per boundary at 64 B/clk -- about as long as the MMAs of 4 K-blocks, which is why the chunk is as long
-// as the error budget allows).  B200REC_KC / B200REC_KC_SHORT override them (measurement only).
+// as the error budget allows).  Measured on B200 (profiles/r02h_kc_sweep.txt): chunks of 8 K-blocks keep a
+// K = 512 contraction at < 3e-6 of the output's largest magnitude (16-block single accumulations reach
+// 3.3e-6, a third of the whole 1e-5 budget in one layer) and cost ~5 % of CIN-forward time against 16.
+// B200REC_KC / B200REC_KC_SHORT override them (measurement only).
 static int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   return e && *e ? std::atoi(e) : dflt;
 }
-static int kc_precise() { static const int v = env_int("B200REC_KC", 16); return v < 1 ? 1 : (v > 255 ? 255 : v); }
-static int kc_short() { static const int v = env_int("B200REC_KC_SHORT", 20); return v < 0 ? 0 : v; }
+static int kc_precise() { static const int v = env_int("B200REC_KC", 8); return v < 1 ? 1 : (v > 255 ? 255 : v); }
+static int kc_short() { static const int v = env_int("B200REC_KC_SHORT", 8); return v < 0 ? 0 : v; }
 static int round16(int n) { return (n + 15) / 16 * 16; }
 // widest tile <= 256 that splits N evenly
 static int pick_bn(int N) {

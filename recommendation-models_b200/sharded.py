@@ -68,6 +68,18 @@ class ShardSpec:
         return base + (rank - base // self.period) % self.world
 
 
+def default_cap(n_nonzeros, world):
+    """Slots of one (source rank, owner rank) exchange bucket.  A bucket holds the distinct ids a rank
+    requests from one owner: never more than its non-zeros owned by that rank, which under the rotated-mod
+    owner map is a Binomial(N, 1/G) count -- mean N/G, standard deviation < sqrt(N/G).  N/G + 8 sigma (+64,
+    rounded up to 16) is therefore never reached by a batch whose ids are spread by the owner map, whatever
+    its duplicate rate; it is derived from the sizes alone, not from any batch.  The contiguous-range
+    partition (ShardSpec mode="range") has no such balance: pass cap explicitly there (cap = N never
+    overflows)."""
+    m = n_nonzeros / max(1, world)
+    return (int(m + 8.0 * m ** 0.5) + 64 + 15) // 16 * 16
+
+
 class GpuOps:
     """The device half of one rank: C-ABI calls on torch-owned device buffers."""
 
@@ -233,8 +245,8 @@ class ShardedParRecModel(_OptimizerMixin):
         self.ops, self.dist, self.spec, self.group = ops, dist, spec, group
         self.B, self.F, self.K = batch, n_fields, dim
         N, G = batch * n_fields, spec.world
-        # capacity of one (source, owner) bucket: the mean N/G plus 25 % + 1024 slack; overflow is flagged
-        self.cap = cap or int(N / G * 1.25) + 1024
+        # capacity of one (source, owner) bucket, see default_cap(); overflow is flagged and check() raises
+        self.cap = cap or default_cap(N, G)
         n = G * self.cap
         e = ops.empty
         self.send_ids, self.recv_ids, self.dst = e(n, ops.int32), e(n, ops.int32), e(N, ops.int32)
@@ -291,7 +303,7 @@ class P2PShardedParRecModel(_OptimizerMixin):
         self.B, self.F, self.K = batch, n_fields, dim
         N, G = batch * n_fields, spec.world
         assert G <= 8, "peer exchange supports up to 8 GPUs (one NVLink box)"
-        self.cap = cap or int(N / G * 1.25) + 1024
+        self.cap = cap or default_cap(N, G)
         ops.cap = self.cap
         n = G * self.cap
         dev = ops.device
@@ -592,8 +604,8 @@ def _bench_model(args, pkg, name, torch, dist, dev):
     batches = [synth.make_feats(B.SEED_DATA, s * world + rank, batch, F, rows)[1] for s in range(nb)]
     # bucket capacity: NOT read off the benchmark's batches.  A bucket holds the distinct ids one source
     # sends one owner: at most its non-zeros, N/G on average under the rotated-mod owner map, so
-    # N/G * 1.25 + 1024 (the class default) is > 25 sigma of a hash-uniform split; an overflow is
-    # flagged on the device and raised by check() below
+    # N/G + 8 sigma (default_cap) is out of reach of a hash-uniform split; an overflow is flagged on the
+    # device and raised by check() below
     sh = None
     if use_p2p:
         # every rank must take the same path: agree on whether symmetric memory came up everywhere
@@ -726,7 +738,7 @@ def _bench_model(args, pkg, name, torch, dist, dev):
                        f"dense dp{world} ({'allreduce over NVLink peer memory' if use_p2p else 'NCCL allreduce'})",
                        "table_bytes_per_gpu": int(spec.rows_local) * (K + 1) * 4,
                        "exchange": "p2p" if use_p2p else "nccl", "cuda_graph": bool(graphed), "bucket_capacity": sh.cap,
-                       "bucket_capacity_rule": "N/G * 1.25 + 1024 (not derived from the timed batches); overflow raises",
+                       "bucket_capacity_rule": "N/G + 8 sqrt(N/G) + 64 (from the sizes, not from the timed batches); overflow raises",
                        "bucket_overflow": int(ovf.item()),
                        "l2": "table shard > L2; new ids every step; no explicit flush", "gemm_mode": args.gemm_mode},
             "clocks": clk,
