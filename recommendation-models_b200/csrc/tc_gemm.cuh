@@ -461,6 +461,7 @@ struct CinZProd {
   KCin s;
   int row0, tid;
   float* x0s;
+  const float* x0row[4];   // the thread's four x0 rows (nullptr beyond R): hoisted out of the per-stage loads
   float4 xr[4];
   float x0v[4];
   static constexpr int DIST = 1;
@@ -468,6 +469,11 @@ struct CinZProd {
   template <int SLOT> __device__ __forceinline__ void store2(int kb, char* hi, char* lo) { store(kb, hi, lo); }
   __device__ __forceinline__ void init(char* extra, int r0, int t) {
     row0 = r0; tid = t;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = (t >> 3) + 32 * q;
+      x0row[q] = row0 + r < R ? x0 + (long long)(row0 + r) * s.F : nullptr;
+    }
     x0s = reinterpret_cast<float*>(extra);
     if (x0_in_smem)
     for (int idx = tid; idx < BM * s.F; idx += THREADS) {
@@ -502,8 +508,7 @@ struct CinZProd {
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int r = (tid >> 3) + 32 * t;
-      x0v[t] = x0_in_smem ? x0s[r * s.F + i]
-                          : (row0 + r < R ? __ldg(x0 + (long long)(row0 + r) * s.F + i) : 0.f);
+      x0v[t] = x0_in_smem ? x0s[r * s.F + i] : (x0row[t] ? __ldg(x0row[t] + i) : 0.f);
     }
   }
   __device__ __forceinline__ void store(int, char* hi, char* lo) {

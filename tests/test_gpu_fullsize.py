@@ -52,9 +52,12 @@ def _kink_aware(name, B, per_sample, near, extra_of, mats_got, mats_want, mats64
         err = np.abs(got - want).max(axis=1)
         bad |= err > tol
         ok = err <= tol
+        sc = np.abs(want).max()
         _report(dict(what=f"{name} {what}: samples over the 1e-5 bar", n=int((~ok).sum()), of=int(B),
-                     max_err_over_scale_rest=float(err[ok].max() / np.abs(want).max()) if ok.any() else 0.0,
-                     max_err_over_scale_all=float(err.max() / np.abs(want).max())))
+                     per_sample_err_over_scale_p50=float(np.percentile(err, 50) / sc),
+                     per_sample_err_over_scale_p99=float(np.percentile(err, 99) / sc),
+                     max_err_over_scale_rest=float(err[ok].max() / sc) if ok.any() else 0.0,
+                     max_err_over_scale_all=float(err.max() / sc)))
     ids = np.nonzero(bad)[0]
     _report(dict(what=f"{name}: samples whose closest pre-activation is within 1e-6 / 1e-5 / 1e-4 of a kink",
                  n=[int((near < m).sum()) for m in (1e-6, 1e-5, 1e-4)], violating=int(ids.size)))

@@ -54,6 +54,33 @@ def test_oracle_matches_golden(path):
     assert abs(loss - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
 
 
+REF_DUMPS = sorted(d for d in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "reference", "*"))
+                   if os.path.exists(os.path.join(d, "out_loss.bin")))
+
+
+@pytest.mark.skipif(not REF_DUMPS, reason="no fixtures dumped from the real reference yet (tests/golden/README.md): "
+                                          "parity stays UNPINNED by the reference")
+@pytest.mark.parametrize("d", REF_DUMPS or [None], ids=[os.path.basename(d) for d in REF_DUMPS] or ["none"])
+def test_oracle_matches_reference_dump(d):
+    """The oracle (fp32) against outputs of yaochitc/recommendation-models itself, dumped on a JVM by
+    scala/DumpFixtures.scala: forward preds, loss and the four in/out-aliased gradient buffers."""
+    name, B, F, K = os.path.basename(d).split("_")
+    B, F, K = int(B[1:]), int(F[1:]), int(K[1:])
+    rd = lambda n, dt="<f4": np.fromfile(os.path.join(d, n), dt) if os.path.exists(os.path.join(d, n)) else None
+    index = rd("in_index.bin", "<i4")
+    w, b, e, m, t = (rd(f"in_{k}.bin") for k in ("weights", "bias", "embedding", "mats", "targets"))
+    o = oracle_model(name, F, K)
+    close = lambda got, want, what: np.testing.assert_array_less(
+        np.abs(np.asarray(got, np.float64) - want).max(), 1e-5 * np.abs(want).max() + 1e-12, err_msg=what)
+    close(o.forward(B, index, w.copy(), b.copy(), None if e is None else e.copy(), None if m is None else m.copy()),
+          rd("out_pred.bin"), "pred")
+    loss = o.backward(B, index, w, b, e, m, t)
+    assert abs(loss - float(rd("out_loss.bin")[0])) <= 1e-5 * abs(loss)
+    for got, n in ((w, "weights"), (b, "bias"), (e, "embedding"), (m, "mats")):
+        if got is not None:
+            close(got, rd(f"out_{n}.bin"), n)
+
+
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_oracle_matches_independent_live(name):
     B, F, K = 9, 7, 6
