@@ -359,6 +359,16 @@ int b200rec_p2p_push_grads_dev(b200rec_model_t m, int64_t nnz, const int* n_dev,
                                const float* w_grad,
                                void* const* peer_grad_in, void* const* peer_gw_in,
                                void* const* peer_flags, void* stream);
+/* The two calls a rank makes between its backward and the push -- b200rec_segsum_reduce_dev (local in-order
+ * pre-reduce per distinct id) and b200rec_p2p_push_grads_dev -- as ONE kernel: the per-id sums are stored
+ * straight into the owners' grad_in / gw_in slots (dst_unique[u] = slot of distinct id u, from
+ * b200rec_p2p_dispatch_ids_dev) and the kernel raises the phase-2 flags.  Same sums, same slots; one kernel
+ * and one pass over the gradients less on the step's critical path. */
+int b200rec_p2p_reduce_push_dev(b200rec_model_t m, int ws, int64_t nnz, int key_bits, const int* feats,
+                                const float* emb_grad, const float* w_grad, int* unique, int* n_unique_dev,
+                                int world, int rank, int cap, int step, const int* dst_unique,
+                                void* const* peer_grad_in, void* const* peer_gw_in, void* const* peer_flags,
+                                void* stream);
 /* Plain SGD on the touched rows: E[id] -= lr * G[id], w[id] -= lr * gw[id] (rec/optim/
  * AsyncSGD.scala:10-31 applies the pushed gradient on the PS; textbook form, parity unpinned). */
 int b200rec_table_apply_sgd_dev(b200rec_table_t t, int64_t n_unique_cap, const int* n_unique,

@@ -96,6 +96,8 @@ SIGNATURES = {
     "b200rec_p2p_wait_dev": [vp, vp, C.c_int, C.c_int, C.c_int, vp],
     "b200rec_p2p_gather_dev": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp],
     "b200rec_p2p_push_grads_dev": [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp],
+    "b200rec_p2p_reduce_push_dev": [vp, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    vp, vp, vp, vp, vp],
     "b200rec_table_apply_sgd_dev": [vp, C.c_int64, vp, vp, vp, vp, C.c_float, vp],
     "b200rec_table_apply_optimizer_dev": [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_int64, vp, vp, vp,
                                           vp, vp],

@@ -1399,6 +1399,37 @@ int b200rec_p2p_push_grads_dev(b200rec_model_t m, int64_t nnz, const int* n_dev,
   B200_GUARD_END
 }
 
+// local in-order pre-reduce per distinct id FUSED with the gradient push: the sums are stored straight into
+// the owners' grad_in / gw_in slots and the kernel raises the phase-2 flags (csrc/segsum.cu, SegPush)
+int b200rec_p2p_reduce_push_dev(b200rec_model_t m, int ws, int64_t nnz, int key_bits, const int* feats,
+                                const float* emb_grad, const float* w_grad, int* unique, int* n_unique_dev,
+                                int world, int rank, int cap, int step, const int* dst_unique,
+                                void* const* peer_grad_in, void* const* peer_gw_in, void* const* peer_flags,
+                                void* stream) {
+  B200_GUARD_BEGIN
+  SegPush sp;
+  B200_TRY(fill_p2p(m, world, rank, step, peer_flags, sp.c));
+  B200_REQUIRE(dst_unique && w_grad && peer_grad_in && peer_gw_in && cap > 0, B200REC_ERR_ARG, "bad argument");
+  B200_REQUIRE(ws >= 0 && ws <= 2, B200REC_ERR_ARG, "workspace must be 0, 1 or 2");
+  const int K = m->kind == B200REC_LR ? 4 : m->K;
+  B200_REQUIRE(K == 4 || K == 8 || K == 16 || K == 32 || K == 64, B200REC_ERR_ARG,
+               "p2p exchange supports embeddingDim in {4,8,16,32,64}, got %d", K);
+  SegSum a;
+  B200_TRY(fill_segsum(m, K, nnz, key_bits, 0, feats, m->kind == B200REC_LR ? nullptr : emb_grad, w_grad, unique,
+                       nullptr, nullptr, n_unique_dev, a));
+  B200_TRY(use_device(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+  for (int p = 0; p < world; ++p) { sp.grad_in.p[p] = (float*)peer_grad_in[p]; sp.gw_in.p[p] = (float*)peer_gw_in[p]; }
+  sp.dst = dst_unique;
+  sp.cap = cap;
+  a.push = &sp;
+  if (m->join_pending[ws]) B200_CUDA(cudaStreamWaitEvent(st, m->join_of(ws), 0));
+  m->join_pending[ws] = false;
+  ProfTag tag("p2p_push_grads");
+  return segsum_reduce(m->ws_of(ws), a, st);
+  B200_GUARD_END
+}
+
 int b200rec_table_apply_sgd_dev(b200rec_table_t t, int64_t n_unique_cap, const int* n_unique,
                                 const int* unique, const float* emb_grad, const float* w_grad,
                                 float lr, void* stream) {

@@ -86,6 +86,7 @@ struct SegSum {
   int fF = 0;                     // non-zeros per sample
   float* keep_dE = nullptr;       // optional: also write the per-nnz gradients
   float* keep_dw = nullptr;
+  const struct SegPush* push = nullptr;   // fused gradient push: sums go to the owners' buffers, not to G / gw
 };
 // sort half (depends only on feats: can run on a side stream while the dense math runs)
 int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st);
@@ -132,6 +133,15 @@ struct P2P {
                              // carry no host step; -1 = the step after the current one, for prefetches)
   unsigned* block_counter;   // local, zero-initialised; wraps back to 0 through atomicInc
   int* flags[P2P_MAX];       // every rank's flags[3][world]
+};
+// Fused local pre-reduce + gradient push (segsum.cu): the in-order per-id sums of a rank's batch are stored
+// straight into the owners' grad_in / gw_in slots (dst[seg] = owner * cap + slot, < 0: no slot) instead of
+// a local array that a second kernel would copy out; the kernel ends with the phase-2 signal.
+struct SegPush {
+  P2P c;
+  PeerF grad_in, gw_in;
+  const int* dst = nullptr;   // [U] slot of every distinct id
+  int cap = 0;
 };
 // status (may be NULL): sticky device word; DEV_PEER_TIMEOUT is set when a peer's flag does not arrive in time
 int p2p_wait(const int* flags, int phase, int world, int step, const int* step_ptr, int* status, cudaStream_t st);

@@ -28,6 +28,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "kernels.h"
+#include "p2p_dev.cuh"
 
 namespace b200rec {
 
@@ -194,10 +195,40 @@ __device__ __forceinline__ void load_row(const RowSrc& s, long long p, int sub, 
   if (s.dw_keep && sub == 0) s.dw_keep[p] = g0;
 }
 
+// ---- where a summed row goes ---------------------------------------------------------------------
+struct RowSink {
+  float* G = nullptr;
+  float* gw = nullptr;
+  bool push = false;            // store into the owners' peer buffers instead (SegPush)
+  SegPush p;
+};
+template <int K>
+__device__ __forceinline__ void sink_row(const RowSink& o, long long seg, int sub, const float4& acc) {
+  if (!o.push) {
+    if (o.G) st_f4(o.G + seg * K + sub * 4, acc);
+    return;
+  }
+  const int s = o.p.dst[seg];
+  if (s < 0) return;            // no slot (full exchange bucket, already flagged): the gradient is dropped
+  const int ow = s / o.p.cap;
+  const long long slot = (long long)o.p.c.rank * o.p.cap + (s - ow * o.p.cap);
+  st_f4(peer_sel(o.p.grad_in.p, ow) + slot * K + sub * 4, acc);
+}
+__device__ __forceinline__ void sink_w(const RowSink& o, long long seg, float aw) {
+  if (!o.push) {
+    if (o.gw) o.gw[seg] = aw;
+    return;
+  }
+  const int s = o.p.dst[seg];
+  if (s < 0) return;
+  const int ow = s / o.p.cap;
+  peer_sel(o.p.gw_in.p, ow)[(long long)o.p.c.rank * o.p.cap + (s - ow * o.p.cap)] = aw;
+}
+
 // ---- in-order segment sums --------------------------------------------------------------------
 template <int LPR>
 __device__ __forceinline__ void segsum_short_role(int block, int n_blocks, long long n, const int* seg_idx,
-                                                  const unsigned* perm, const RowSrc src, float* G, float* gw) {
+                                                  const unsigned* perm, const RowSrc& src, const RowSink& out) {
   // Walks SORTED POSITIONS, not segments: a lane group looks at position p, and if p is the head of a
   // segment of at most LONG_T rows it sums that segment.  seg_idx (the 1-based segment number of every
   // sorted position, left by the sort half) and perm are read at p-1 .. p+LONG_T: contiguous, coalesced
@@ -239,14 +270,14 @@ __device__ __forceinline__ void segsum_short_role(int block, int n_blocks, long 
       }
     }
     const long long seg = s0 - 1;
-    if (G && src.has_e) st_f4(G + seg * K + sub * 4, acc);
-    if (gw && src.has_w && sub == 0) gw[seg] = aw;
+    if (src.has_e) sink_row<K>(out, seg, sub, acc);
+    if (src.has_w && sub == 0) sink_w(out, seg, aw);
   }
 }
 
 template <int LPR>
 __device__ __forceinline__ void segsum_long_role(int block, int n_blocks, const int* seg_start,
-                                                 const unsigned* perm, const RowSrc src, float* G, float* gw,
+                                                 const unsigned* perm, const RowSrc& src, const RowSink& out,
                                                  const int* long_list, const int* long_count) {
   // One warp per hot id.  Rows are LOADED 32/LPR x UNR at a time (all loads of a batch in flight,
   // the positions of the next batch prefetched meanwhile) and ADDED strictly in non-zero order
@@ -305,8 +336,8 @@ __device__ __forceinline__ void segsum_long_role(int block, int n_blocks, const 
         }
       }
     }
-    if (G && slot == 0) st_f4(G + (long long)seg * K + sub * 4, acc);
-    if (gw && lane == 0) gw[seg] = aw;
+    if (src.has_e && slot == 0) sink_row<K>(out, seg, sub, acc);
+    if (src.has_w && lane == 0) sink_w(out, seg, aw);
   }
 }
 
@@ -318,7 +349,7 @@ __device__ __forceinline__ void segsum_long_role(int block, int n_blocks, const 
 // load latency inside the chain.
 template <int LPR>
 __device__ __forceinline__ void segsum_big_role(int block, int n_blocks, const int* seg_start,
-                                                const unsigned* perm, const RowSrc src, float* G, float* gw,
+                                                const unsigned* perm, const RowSrc& src, const RowSink& out,
                                                 const int* big_list, const int* big_count, float* rows_s,
                                                 float* w_s) {
   constexpr int K = 4 * LPR;
@@ -348,8 +379,12 @@ __device__ __forceinline__ void segsum_big_role(int block, int n_blocks, const i
       }
       __syncthreads();
     }
-    if (tid < K && G && src.has_e) G[(long long)seg * K + tid] = acc;
-    if (tid == K && gw && src.has_w) gw[seg] = acc;
+    if (src.has_e) {   // lanes 0 .. K-1 hold one component each: regroup to the 128-bit stores of the sink
+      const float a1 = __shfl_down_sync(0xffffffffu, acc, 1), a2 = __shfl_down_sync(0xffffffffu, acc, 2),
+                  a3 = __shfl_down_sync(0xffffffffu, acc, 3);
+      if (tid < K && (tid & 3) == 0) sink_row<K>(out, seg, tid >> 2, make_float4(acc, a1, a2, a3));
+    }
+    if (tid == K && src.has_w) sink_w(out, seg, acc);
   }
 }
 
@@ -358,7 +393,7 @@ __device__ __forceinline__ void segsum_big_role(int block, int n_blocks, const i
 template <int LPR>
 __global__ void __launch_bounds__(256, 4) segsum_kernel(int b_blocks, int l_blocks, long long n, const int* seg_idx,
                                                      const int* seg_start, const unsigned* perm,
-                                                     const RowSrc src, float* G, float* gw,
+                                                     const RowSrc src, const RowSink out,
                                                      const int* long_list, const int* big_list,
                                                      const int* counts) {
   constexpr int SK = 4 * LPR <= BIG_MAX_K ? 4 * LPR : 1;   // wider rows never reach the big role (seg_long_kernel)
@@ -367,12 +402,13 @@ __global__ void __launch_bounds__(256, 4) segsum_kernel(int b_blocks, int l_bloc
   const int b = (int)blockIdx.x;
   if (b < b_blocks) {
     if (4 * LPR <= BIG_MAX_K)
-      segsum_big_role<LPR>(b, b_blocks, seg_start, perm, src, G, gw, big_list, counts + 1, rows_s, w_s);
+      segsum_big_role<LPR>(b, b_blocks, seg_start, perm, src, out, big_list, counts + 1, rows_s, w_s);
   } else if (b < b_blocks + l_blocks) {
-    segsum_long_role<LPR>(b - b_blocks, l_blocks, seg_start, perm, src, G, gw, long_list, counts);
+    segsum_long_role<LPR>(b - b_blocks, l_blocks, seg_start, perm, src, out, long_list, counts);
   } else {
-    segsum_short_role<LPR>(b - b_blocks - l_blocks, gridDim.x - b_blocks - l_blocks, n, seg_idx, perm, src, G, gw);
+    segsum_short_role<LPR>(b - b_blocks - l_blocks, gridDim.x - b_blocks - l_blocks, n, seg_idx, perm, src, out);
   }
+  if (out.push) p2p_signal(out.p.c, 2);   // every thread of every block arrives here: phase-2 flag to all owners
 }
 
 // any K: one thread per (segment, k), strictly sequential
@@ -421,8 +457,12 @@ static int launch_segsum(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) 
   src.has_w = a.fused ? (a.gw != nullptr) : (a.dw != nullptr);
   const int* big_list = long_list + (ws.cap_n + 8) / LONG_T;
   const int bgrid = 148;     // one block per very hot id; a Criteo-shaped batch of 8192 has ~270 of them
+  RowSink out;
+  out.G = a.fused || a.dE ? a.G : nullptr;
+  out.gw = a.fused || a.dw ? a.gw : nullptr;
+  if (a.push) { out.push = true; out.p = *a.push; }
   B200_LAUNCH((segsum_kernel<LPR>), bgrid + lgrid + grid, 256, 0, st, bgrid, lgrid, a.n, ws.vals_a.as<int>(), seg_start, perm, src,
-              a.fused || a.dE ? a.G : nullptr, a.fused || a.dw ? a.gw : nullptr, long_list, big_list, counters);
+              out, long_list, big_list, counters);
   B200_CHECK_LAUNCH();
   return B200REC_OK;
 }

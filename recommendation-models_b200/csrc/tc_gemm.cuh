@@ -592,9 +592,33 @@ struct CinZtProd {
 template <class T, class = void> struct has_aux : std::false_type {};
 template <class T>
 struct has_aux<T, std::void_t<decltype(&T::load_aux)>> : std::true_type {};
+template <class T, class = void> struct has_bias_stage : std::false_type {};
+template <class T>
+struct has_bias_stage<T, std::void_t<decltype(&T::apply_staged)>> : std::true_type {};
 struct EpBiasAct {  // y = act(acc + bias[n])
   float* y; long long ld; const float* bias; bool relu;
   static constexpr bool kRowReduce = false;
+  // staged form: the kernel copies the tile's bias segment to shared memory once (its global load is issued
+  // before the wait for the last MMA), so the per-chunk epilogue has no global load on its critical path
+  // (round 1: four 128-bit bias loads per 16-column chunk, ~7 dependent round trips per thread)
+  __device__ __forceinline__ float bias_at(int n, int n_end) const { return (bias && n < n_end) ? __ldg(bias + n) : 0.f; }
+  __device__ __forceinline__ void apply_staged(int m, int n0, float* v, int nv, const float* bias_s) const {
+    float* dst = y + (long long)m * ld + n0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      v[i] += bias_s[i];                      // zero beyond the tile / when there is no bias
+      if (relu) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nv) dst[i] = v[i];
+    }
+  }
   __device__ __forceinline__ void operator()(int m, int n0, float* v, int nv, int) const {
     float* dst = y + (long long)m * ld + n0;
     if (bias && nv == 16 && ((reinterpret_cast<uintptr_t>(bias + n0) & 15) == 0)) {
@@ -1092,9 +1116,16 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         if (row < M && (pw >> 2) * 16 < ncols)
           ep.load_aux(row, n0 + (pw >> 2) * 16, min(16, ncols - (pw >> 2) * 16), aux);
       }
+      [[maybe_unused]] float bias_reg = 0.f;
+      if constexpr (has_bias_stage<Ep>::value) bias_reg = ep.bias_at(n0 + tid, n0 + ncols);   // in flight under the wait
       mbar_wait(bar_done + 8 * ((nkb - 1) % 6), ((nkb - 1) / 6) & 1);
       if (tid == 0) TC_TRACE(2, 511, 1);
       tc_fence_after();
+      [[maybe_unused]] float* bias_s = reinterpret_cast<float*>(base);   // A stage 0 is free: every MMA has completed
+      if constexpr (has_bias_stage<Ep>::value) {
+        bias_s[tid] = bias_reg;                                           // THREADS = 256 >= MAX_BN columns
+        asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
+      }
       const bool add_s = kc > 0 && nkb > kc;   // result = S + P (the last chunk is still in P)
       float v[16];
       if constexpr (Ep::kRowReduce) {
@@ -1141,11 +1172,20 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
             for (int q = 0; q < 4; ++q) aux[q] = aux_next[q];
           }
         } else {
-        for (int ch = pw >> 2; ch * 16 < ncols; ch += 2) {
-          uint32_t pr[16], sr[16];
-          tmem_ld16_nowait(tmem + lane_addr + ch * 16, pr);          // P and S in one TMEM round trip
+        // two 16-column chunks per round: their TMEM loads (P and, when there is a running sum, S) are all in
+        // flight before the first wait -- half as many TMEM round trips on the epilogue's critical path
+        for (int ch = pw >> 2; ch * 16 < ncols; ch += 4) {
+          const int ch2 = ch + 2;
+          const bool two = ch2 * 16 < ncols;
+          uint32_t pr[16], sr[16], pr2[16], sr2[16];
+          float v2[16];
+          tmem_ld16_nowait(tmem + lane_addr + ch * 16, pr);
+          if (add_s) tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, sr);
+          if (two) {
+            tmem_ld16_nowait(tmem + lane_addr + ch2 * 16, pr2);
+            if (add_s) tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch2 * 16, sr2);
+          }
           if (add_s) {
-            tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, sr);
             tmem_wait_ld2(pr, sr);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(pr[i]) + __uint_as_float(sr[i]);
@@ -1154,7 +1194,24 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(pr[i]);
           }
-          if (row < M) ep(row, n0 + ch * 16, v, min(16, ncols - ch * 16), blockIdx.z);
+          if (two) {
+            if (add_s) {
+              tmem_wait_ld2(pr2, sr2);      // (already complete: wait::ld covers every earlier load; this ties the registers)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v2[i] = __uint_as_float(pr2[i]) + __uint_as_float(sr2[i]);
+            } else {
+              tmem_wait_ld1(pr2);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v2[i] = __uint_as_float(pr2[i]);
+            }
+          }
+          if constexpr (has_bias_stage<Ep>::value) {
+            if (row < M) ep.apply_staged(row, n0 + ch * 16, v, min(16, ncols - ch * 16), bias_s + ch * 16);
+            if (two && row < M) ep.apply_staged(row, n0 + ch2 * 16, v2, min(16, ncols - ch2 * 16), bias_s + ch2 * 16);
+          } else {
+            if (row < M) ep(row, n0 + ch * 16, v, min(16, ncols - ch * 16), blockIdx.z);
+            if (two && row < M) ep(row, n0 + ch2 * 16, v2, min(16, ncols - ch2 * 16), blockIdx.z);
+          }
         }
         }
       }

@@ -355,6 +355,10 @@ class P2PShardedParRecModel(_OptimizerMixin):
         self.s_feats = [torch.zeros(N, dtype=torch.int32, device=dev) for _ in range(2)]
         self.s_targets = [torch.zeros(batch, dtype=torch.float32, device=dev) for _ in range(2)]
         self.loaded = [False, False]
+        # local pre-reduce + gradient push as ONE kernel (b200rec_p2p_reduce_push_dev).  Measured on 2 GPUs
+        # (profiles/r02r_bench_2gpu_fused_push_ab.txt): 0.501 ms / step against 0.487 for the two kernels -- the
+        # scattered peer stores slow the in-order reduce more than the saved launch and pass win -- so it is off
+        self.fused_push = os.environ.get("B200REC_FUSED_PUSH", "0") == "1"
         self.graphs = {}
         self.graph_epoch = -1
         self.use_graph = True      # False: step() launches call by call (per-kernel profiling)
@@ -428,16 +432,26 @@ class P2PShardedParRecModel(_OptimizerMixin):
         L.check(lib.b200rec_p2p_allreduce_dev(m, self.n_dense, G, r, 0, o._mats_grad_ptr, self.dense_in[2],
                                               self.dense_out[2] if self.two_shot else None, flags_p,
                                               flags_t.data_ptr(), self.side[ws]))
-        # local pre-reduce per distinct id (in non-zero order), then one push per distinct id
-        L.check(lib.b200rec_segsum_reduce_dev(m, ws, self.K, N, self.gbits, 0, feats.data_ptr(),
-                                              self.grad_rows.data_ptr(), self.grad_w.data_ptr(),
-                                              loc["uniq"].data_ptr(), self.G_loc.data_ptr(),
-                                              self.gw_loc.data_ptr(), loc["n"].data_ptr(), st))
-        L.check(lib.b200rec_side_rejoin_dev(m, ws))   # after the call above: it must not wait for the allreduce
-        L.check(lib.b200rec_p2p_push_grads_dev(m, N, loc["n"].data_ptr(), G, r, cap, 0,
-                                               self.dst_u[p].data_ptr(), self.G_loc.data_ptr(),
-                                               self.gw_loc.data_ptr(), self.grad_in[2], self.gw_in[2],
-                                               flags_p, st))
+        if self.fused_push:
+            # local pre-reduce per distinct id (in non-zero order) with the sums stored straight into the
+            # owners' buffers: one kernel instead of reduce + push
+            L.check(lib.b200rec_p2p_reduce_push_dev(m, ws, N, self.gbits, feats.data_ptr(),
+                                                    self.grad_rows.data_ptr(), self.grad_w.data_ptr(),
+                                                    loc["uniq"].data_ptr(), loc["n"].data_ptr(), G, r, cap, 0,
+                                                    self.dst_u[p].data_ptr(), self.grad_in[2], self.gw_in[2],
+                                                    flags_p, st))
+            L.check(lib.b200rec_side_rejoin_dev(m, ws))   # after the call above: it must not wait for the allreduce
+        else:
+            # local pre-reduce per distinct id (in non-zero order), then one push per distinct id
+            L.check(lib.b200rec_segsum_reduce_dev(m, ws, self.K, N, self.gbits, 0, feats.data_ptr(),
+                                                  self.grad_rows.data_ptr(), self.grad_w.data_ptr(),
+                                                  loc["uniq"].data_ptr(), self.G_loc.data_ptr(),
+                                                  self.gw_loc.data_ptr(), loc["n"].data_ptr(), st))
+            L.check(lib.b200rec_side_rejoin_dev(m, ws))   # after the call above: it must not wait for the allreduce
+            L.check(lib.b200rec_p2p_push_grads_dev(m, N, loc["n"].data_ptr(), G, r, cap, 0,
+                                                   self.dst_u[p].data_ptr(), self.G_loc.data_ptr(),
+                                                   self.gw_loc.data_ptr(), self.grad_in[2], self.gw_in[2],
+                                                   flags_p, st))
         L.check(lib.b200rec_p2p_wait_dev(m, flags_t.data_ptr(), 2, G, 0, st))
         o.segsum(cur[0], self.grad_in[0], self.gw_in[0], self.unique, self.G, self.gw)   # joins side stream 1
         L.check(lib.b200rec_segsum_join_dev(m, ws, st))           # the dense allreduce
