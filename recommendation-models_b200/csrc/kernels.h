@@ -223,6 +223,8 @@ struct CinDims {
   int n_layers;
   int H[9];  // H[0]=F, H[l]=cin_dims[l-1]
 };
+// out[cols, rows] = in[rows, cols]^T
+int transpose2d(long long rows, int cols, const float* in, float* out, cudaStream_t st);
 // x0[(b,k),f] = X[b,f,k]
 int cin_transpose_in(int B, int F, int K, const float* X, float* x0, cudaStream_t st);
 // ge[b,f,k] (+)= gx0[(b,k),f]

@@ -260,6 +260,11 @@ int tc_cin_layer_fwd(int R, int F, int H, int C, const float* x0, const float* x
 
 // Both CIN input gradients from one persistent short-K GEMM per row tile (tc_cin_fused.cuh) whenever the
 // layer fits it (F <= 40 fields, C <= 256); B200REC_CIN_FUSED=0 keeps the two-GEMM path below.
+// CIN dW from transposed copies of the factors (CinZtProdT); B200REC_CIN_DW_T=0 keeps round 1's producer
+static bool cin_dw_transposed_enabled() {
+  static const bool on = [] { const char* e = std::getenv("B200REC_CIN_DW_T"); return !(e && e[0] == '0'); }();
+  return on;
+}
 static bool cin_fused_enabled() {
   static const bool on = [] { const char* e = std::getenv("B200REC_CIN_FUSED"); return !(e && e[0] == '0'); }();
   return on;
@@ -306,13 +311,35 @@ int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x
     int k_chunk = ((cdiv(R, splits) + BK - 1) / BK) * BK;
     splits = cdiv(R, k_chunk);
     const long long MN = (long long)C * FH;
-    B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)COLSUM_CHUNKS * C) * sizeof(float)));
+    // + transposed copies of the two factors (x0T [F x R], xT [H x R]) for the generated Z^T operand
+    const bool transposed = R % 4 == 0 && cin_dw_transposed_enabled();
+    const size_t n_part = ((size_t)splits * MN + (size_t)COLSUM_CHUNKS * C + 3) / 4 * 4;
+    B200_TRY(scratch.reserve((n_part + (transposed ? (size_t)R * (F + H) : 0)) * sizeof(float)));
     float* ws = scratch.as<float>();
     KPlain s{0, R, k_chunk};
-    CinZtProd ap{x0, x_in, F, H, (H % 4 == 0) && aligned16(x_in)};
     ColProd<256, KPlain> bp{gy, C, C, bn, colvec(gy, C, C)};   // B(c, r) = gy[r*C + c]: packed once (all splits)
-    B200_TRY(launch_packed("tc_cin_dW", FH, C, bn, bn, bn, cdiv(C, bn), cdiv(R, BK), s, ap, bp,
-                           tc::EpPartialT{ws, MN, FH}, passes, st, nullptr, splits, k_chunk));
+    if (transposed) {
+      float* x0T = ws + n_part;
+      float* xT = x0T + (size_t)R * F;
+      B200_TRY(transpose2d(R, F, x0, x0T, st));
+      if (x_in == x0 && H == F) xT = x0T;                 // first layer: the second factor is x0 itself
+      else B200_TRY(transpose2d(R, H, x_in, xT, st));
+      CinZtProdT ap{x0T, xT, F, H, (long long)R};
+      B200_TRY(launch_packed("tc_cin_dW", FH, C, bn, bn, bn, cdiv(C, bn), cdiv(R, BK), s, ap, bp,
+                             tc::EpPartialT{ws, MN, FH}, passes, st, nullptr, splits, k_chunk));
+    } else {
+      CinZtProd ap{x0, x_in, F, H, (H % 4 == 0) && aligned16(x_in)};
+      B200_TRY(launch_packed("tc_cin_dW", FH, C, bn, bn, bn, cdiv(C, bn), cdiv(R, BK), s, ap, bp,
+                             tc::EpPartialT{ws, MN, FH}, passes, st, nullptr, splits, k_chunk));
+    }
+#ifdef B200_TC_TRACE
+    if (H != F) {   // keep the timeline of a deep layer's dW launch (later launches overwrite g_tc_trace)
+      void *src = nullptr, *dst = nullptr;
+      cudaGetSymbolAddress(&src, tc::g_tc_trace);
+      cudaGetSymbolAddress(&dst, tc::g_tc_trace_dw);
+      cudaMemcpyAsync(dst, src, sizeof(long long) * 3 * 512 * 4, cudaMemcpyDeviceToDevice, st);
+    }
+#endif
     B200_TRY(splitk_reduce(ws, splits, MN, 1.0f, false, gW, st));
     B200_TRY(colsum(R, C, gy, 1.0f, false, gb, ws + (size_t)splits * MN, st));
   }
@@ -343,5 +370,8 @@ int tc_cin_layer_bwd(int R, int F, int H, int C, const float* x0, const float* x
 #ifdef B200_TC_TRACE
 extern "C" int b200rec_debug_tc_trace(long long* out, int n) {
   return (int)cudaMemcpyFromSymbol(out, b200rec::tc::g_tc_trace, sizeof(long long) * (size_t)n);
+}
+extern "C" int b200rec_debug_tc_trace_dw(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, b200rec::tc::g_tc_trace_dw, sizeof(long long) * (size_t)n);
 }
 #endif

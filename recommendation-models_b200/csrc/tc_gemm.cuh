@@ -134,20 +134,26 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
 // All MMAs of one 32-wide K-block into the accumulator columns at `acc`: `ksteps` TF32 K-steps on the hi
 // tiles and, with PASSES == 3, as many bf16 K-steps (16 positions = 8 K values x {hi*lo, lo*hi}) on the
 // correction tiles.  boff: descriptor offset of the first B row.
-template <int PASSES>
-__device__ __forceinline__ void mma_block(uint32_t acc, uint64_t da_hi, uint64_t da_corr, uint64_t db_hi,
-                                          uint64_t db_corr, uint64_t boff, uint32_t idesc, uint32_t idesc_bf,
-                                          int ksteps, int kvalid, bool fresh) {
+__device__ __forceinline__ void mma_block_tf32(uint32_t acc, uint64_t da_hi, uint64_t db_hi, uint64_t boff,
+                                               uint32_t idesc, int ksteps, bool fresh) {
   for (int ks = 0; ks < ksteps; ++ks) {
     const uint64_t adv = (uint64_t)(ks * UK * 4 >> 4);
     mma_tf32(acc, da_hi + adv, db_hi + adv + boff, idesc, (!fresh || ks != 0) ? 1u : 0u);
   }
-  if (PASSES == 3) {
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const uint64_t adv = (uint64_t)(ks * 32 >> 4);
-      mma_bf16(acc, da_corr + adv, db_corr + adv + boff, idesc_bf, 1u);
-    }
+}
+__device__ __forceinline__ void mma_block_bf16(uint32_t acc, uint64_t da_corr, uint64_t db_corr, uint64_t boff,
+                                               uint32_t idesc_bf, int ksteps) {
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint64_t adv = (uint64_t)(ks * 32 >> 4);
+    mma_bf16(acc, da_corr + adv, db_corr + adv + boff, idesc_bf, 1u);
   }
+}
+template <int PASSES>
+__device__ __forceinline__ void mma_block(uint32_t acc, uint64_t da_hi, uint64_t da_corr, uint64_t db_hi,
+                                          uint64_t db_corr, uint64_t boff, uint32_t idesc, uint32_t idesc_bf,
+                                          int ksteps, int kvalid, bool fresh) {
+  mma_block_tf32(acc, da_hi, db_hi, boff, idesc, ksteps, fresh);
+  if (PASSES == 3) mma_block_bf16(acc, da_corr, db_corr, boff, idesc_bf, ksteps);
   (void)kvalid;
 }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
@@ -587,6 +593,57 @@ struct CinZtProd {
   }
 };
 
+// The same operand from TRANSPOSED copies of the factors (x0T [F x R], xT [H x R], made once per layer by a
+// tiled transpose): A(m = (i, j), k = r) = x0T[i, r] * xT[j, r].  The contraction index r is now contiguous in
+// memory, so a thread fetches its 4 K values of a tile row with two 128-bit loads and multiplies them
+// component-wise -- no scalar x0 loads, no 4x4 register transposes, and the first layer (H = F = 39, rows of x
+// not 16-byte aligned) takes the same vector path as the others.
+struct CinZtProdT {
+  const float* x0T; const float* xT; int F, H; long long ldr;   // ldr = R: row stride of the transposed copies
+  KPlain s;
+  int tid;
+  const float* p0[4];   // x0T row of the (i) of this thread's four tile rows, nullptr beyond F*H
+  const float* p1[4];   // xT row of their (j)
+  // Two register sets of RAW factors: prefetch only issues loads (nothing in it depends on a loaded value, so it
+  // never stalls), the products are formed when the stage is stored two stages later.  With the multiply in the
+  // prefetch the L2 latency under load (1500-2000 cycles) was exposed once per stage (profiles/r02s_trace.txt).
+  float4 ra[2][4], rb[2][4];
+  static constexpr int DIST = 2;
+  __device__ __forceinline__ void init(char*, int r0, int t) {
+    tid = t;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int m = r0 + (t >> 3) + 32 * q;
+      const bool valid = m < F * H;
+      const int im = valid ? m / H : 0;
+      const int jm = valid ? m - im * H : 0;
+      p0[q] = valid ? x0T + (long long)im * ldr : nullptr;
+      p1[q] = valid ? xT + (long long)jm * ldr : nullptr;
+    }
+  }
+  template <int SLOT> __device__ __forceinline__ void prefetch2(int kb) {
+    const int k = s.k0(kb) + 4 * (tid & 7);          // R % 4 == 0 (host check): a quad is inside [0, k_end) or outside
+    const bool in = k < s.k_end;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (in && p0[q]) {
+        a = __ldg(reinterpret_cast<const float4*>(p0[q] + k));
+        b = __ldg(reinterpret_cast<const float4*>(p1[q] + k));
+      }
+      ra[SLOT][q] = a;
+      rb[SLOT][q] = b;
+    }
+  }
+  template <int SLOT> __device__ __forceinline__ void store2(int, char* hi, char* lo) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = ra[SLOT][q], b = rb[SLOT][q];
+      split_store(hi, lo, (tid >> 3) + 32 * q, tid & 7, make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w), false);
+    }
+  }
+};
+
 // ---- epilogues: ep(m, n0, v[16], nv, z) for one accumulator row chunk ------------------------------
 // An epilogue with load_aux / apply has its global inputs fetched one chunk ahead by the kernel.
 template <class T, class = void> struct has_aux : std::false_type {};
@@ -868,6 +925,7 @@ constexpr int KC_SHORT = 8;
 #ifdef B200_TC_TRACE
 // debug timeline of CTA (0,0,0): [role][kb][slot] clock64 stamps (built only into libb200rec_trace.so)
 __device__ long long g_tc_trace[3 * 512 * 4];
+__device__ long long g_tc_trace_dw[3 * 512 * 4];   // copy taken after a deep CIN layer's dW launch
 #define TC_TRACE(role, kb, slot)                                                          \
   do {                                                                                    \
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (kb) < 512)              \
@@ -910,7 +968,11 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
   // Accumulation-chunk boundaries are pipelined by column halves [0, h0) / [h0, bn): the chunk's last
   // stage and the next chunk's first stage issue their MMAs half by half, so that the drain of one
   // half (P -> S, CUDA cores) runs under the tensor work of the other instead of idling the pipe.
+#ifdef B200_NO_HALVES
+  const int h0 = bn, h1 = 0;
+#else
   const int h0 = ((bn / 16 + 1) / 2) * 16, h1 = bn - h0;
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM;
   const int n0 = blockIdx.x * n_stride;
@@ -972,6 +1034,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         const bool fresh = chunk_start;   // the first MMA of a chunk overwrites the accumulator
         if (opens || closes) {
           const uint64_t boff = (uint64_t)(h0 * 128 >> 4);   // B rows [h0, bn) of the stage image
+#ifdef B200_BOUNDARY_OLD
           if (opens) {
             mbar_wait(bar_drained0, (cidx - 1) & 1);
             tc_fence_after();
@@ -983,6 +1046,28 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
             tc_fence_after();
           }
           if (h1 > 0) mma_block<PASSES>(tmem + h0, dah, dal, dbh, dbl, boff, idesc1, idesc1_bf, ksteps, kvalid, fresh);
+#else
+          // Only the TF32 MMAs are split by column halves: a bf16 MMA costs the same 132 cycles at any N
+          // (profiles/r02f_mma_rate_ubench.txt), so the corrections run once at full width -- before the halves in
+          // a stage that closes a chunk, after them in a stage that opens one.
+          const bool corr_first = !opens && !fresh;   // (a fresh stage's first TF32 MMA overwrites the accumulator)
+          if (PASSES == 3 && corr_first) mma_block_bf16(tmem, dal, dbl, 0, idesc_bf, ksteps);
+          if (opens) {
+            mbar_wait(bar_drained0, (cidx - 1) & 1);
+            tc_fence_after();
+          }
+          mma_block_tf32(tmem, dah, dbh, 0, idesc0, ksteps, fresh);
+          if (closes && corr_first) mma_commit(bar_half);
+          if (opens) {
+            mbar_wait(bar_drained, (cidx - 1) & 1);
+            tc_fence_after();
+          }
+          if (h1 > 0) mma_block_tf32(tmem + h0, dah, dbh, boff, idesc1, ksteps, fresh);
+          if (!corr_first) {
+            if (PASSES == 3) mma_block_bf16(tmem, dal, dbl, 0, idesc_bf, ksteps);
+            if (closes) mma_commit(bar_half);
+          }
+#endif
         } else {
           mma_block<PASSES>(tmem, dah, dal, dbh, dbl, 0, idesc, idesc_bf, ksteps, kvalid, fresh);
         }
@@ -1003,9 +1088,15 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         int sb = 0, round = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           if (kb >= NB) mbar_wait(bar_done + 8 * ((kb - NB) % 6), ((kb - NB) / 6) & 1);   // the MMAs of stage kb - NB are done
+#ifdef B200_EXPERIMENT_HALF_B   // timing experiment only (wrong results): is the stage period set by the L2 -> SM bytes?
+          mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)b_stage / 2);
+          bulk_g2s(smem_u32(bbase + sb * b_stage), myblob + (size_t)kb * b_stage, (uint32_t)b_stage / 2,
+                   bar_bfull + 8 * sb);
+#else
           mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)b_stage);
           bulk_g2s(smem_u32(bbase + sb * b_stage), myblob + (size_t)kb * b_stage, (uint32_t)b_stage,
                    bar_bfull + 8 * sb);
+#endif
           if (++sb == NB) { sb = 0; ++round; }
         }
       }
@@ -1035,7 +1126,9 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
       if (tid == 0) TC_TRACE(1, kb, 0);
       if (kb >= STAGES) mbar_wait(bar_done + 8 * ((kb - 2) % 6), ((kb - 2) / 6) & 1);   // MMA(kb-2) done: stage P is free
       if (tid == 0) TC_TRACE(1, kb, 1);
+#ifndef B200_EXPERIMENT_NO_ASTORE   // timing experiment only (wrong results): the pipeline without producer work
       ap.template store2<P>(kb, a_hi, a_hi + A_TILE_BYTES);
+#endif
       if (tid == 0) TC_TRACE(1, kb, 2);
       if (!PACKED) {
         char* b_hi = bbase + P * b_stage;
@@ -1058,7 +1151,10 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         const bool have_s = kb > kc;
         const int ch0 = pw >> 2;
         const int bpar = (kb / kc - 1) & 1;        // boundary number: each barrier completes once per boundary
-        constexpr int DG = 1;   // pieces per TMEM round trip (the drain now hides under the other half: registers matter more)
+#ifndef B200_DRAIN_DG
+#define B200_DRAIN_DG 1
+#endif
+        constexpr int DG = B200_DRAIN_DG;   // pieces per TMEM round trip (the drain now hides under the other half: registers matter more)
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {   // one copy of the drain code for both halves
           if (half == 0) mbar_wait(bar_half, bpar);

@@ -7,14 +7,14 @@ pkg = g.load_package()
 lib = pkg.lib()
 rng = np.random.default_rng(0)
 
-def dump(title, nkb):
+def dump(title, nkb, fn="b200rec_debug_tc_trace", first=0):
     buf = (C.c_longlong * (3 * 512 * 4))()
-    lib.b200rec_debug_tc_trace(buf, 3 * 512 * 4)
+    getattr(lib, fn)(buf, 3 * 512 * 4)
     a = np.array(buf, dtype=np.int64).reshape(3, 512, 4)
     t0 = a[0, 0, 0]
     print("==", title, "nkb", nkb)
     print(" kb | MMA: start  full  bfull  issued | PROD: start  waited  stored  arrived | drained0 drained")
-    for kb in range(min(nkb, 24)):
+    for kb in range(first, min(nkb, first + 24)):
         m, p = a[0, kb] - t0, a[1, kb] - t0
         d = a[2, kb, 0] - t0 if a[2, kb, 0] else 0
         d0 = a[2, kb, 1] - t0 if a[2, kb, 1] else 0
@@ -45,3 +45,11 @@ mats = pkg.synth.init_mats(1, refport.mats_size("xdeepfm", F, K, [16], [200, 200
 m.forward(Bm, np.repeat(np.arange(Bm, dtype=np.int32), F), rng.standard_normal(n).astype(np.float32),
           np.zeros(1, np.float32), rng.standard_normal(n * K).astype(np.float32), mats)
 dump("cin fwd layer 2 (H=200)", 39 * 7)
+
+if os.environ.get('TRACE_CIN_BWD'):
+    y = m.forward(Bm, np.repeat(np.arange(Bm, dtype=np.int32), F), rng.standard_normal(n).astype(np.float32),
+                  np.zeros(1, np.float32), rng.standard_normal(n * K).astype(np.float32), mats)
+    m.backward(Bm, np.repeat(np.arange(Bm, dtype=np.int32), F), rng.standard_normal(n).astype(np.float32),
+               np.zeros(1, np.float32), rng.standard_normal(n * K).astype(np.float32), mats.copy(),
+               (rng.random(Bm) < 0.5).astype(np.float32))
+    dump("cin dW layer 1 (H=200), one split", 342, "b200rec_debug_tc_trace_dw", first=40)
