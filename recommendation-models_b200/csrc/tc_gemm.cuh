@@ -88,6 +88,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// 1-D bulk async copy shared -> global (TMA engine); completion tracked by the thread's bulk group
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {   // the shared-memory source may be reused / released afterwards
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -649,12 +657,34 @@ struct CinZtProdT {
 template <class T, class = void> struct has_aux : std::false_type {};
 template <class T>
 struct has_aux<T, std::void_t<decltype(&T::load_aux)>> : std::true_type {};
+// Staged epilogues (round 2, late).  With thread = accumulator row, a warp's 128-bit store touches 32 different
+// 128-byte lines (one 16-byte piece of 32 rows): 32 LSU wavefronts per instruction, and the epilogue of a 128 x 208
+// tile took ~9000 cycles -- 20-29 % of a short-K CTA's life (profiles/r02j, r02z timelines).  A staged epilogue
+// first parks the tile in the (now idle) operand rings, row-major with a 4-float pad (conflict-free 128-bit
+// stores: consecutive rows are 4 banks apart modulo 32), then writes it out ROW-wise:
+//   kStaged == 1: a row of the tile is one cp.async.bulk shared -> global copy, issued by one thread per row;
+//   kStaged == 2: warps walk rows, lanes walk 16-byte column groups: coalesced mask / accumulate / store.
+template <class T, class = void> struct staged_kind : std::integral_constant<int, 0> {};
+template <class T>
+struct staged_kind<T, std::void_t<decltype(T::kStaged)>> : std::integral_constant<int, T::kStaged> {};
 template <class T, class = void> struct has_bias_stage : std::false_type {};
 template <class T>
 struct has_bias_stage<T, std::void_t<decltype(&T::apply_staged)>> : std::true_type {};
 struct EpBiasAct {  // y = act(acc + bias[n])
   float* y; long long ld; const float* bias; bool relu;
   static constexpr bool kRowReduce = false;
+  static constexpr int kStaged = 1;
+  __device__ __forceinline__ bool staged_ok(int m0, int n0, int ncols) const {
+    return ld % 4 == 0 && ncols % 4 == 0 && ((reinterpret_cast<uintptr_t>(y + (long long)m0 * ld + n0) & 15) == 0);
+  }
+  __device__ __forceinline__ void pre(float* v, const float* bias_s) const {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      v[i] += bias_s[i];
+      if (relu) v[i] = fmaxf(v[i], 0.f);
+    }
+  }
+  __device__ __forceinline__ float* row_ptr(int m, int n0, int) const { return y + (long long)m * ld + n0; }
   // staged form: the kernel copies the tile's bias segment to shared memory once (its global load is issued
   // before the wait for the last MMA), so the per-chunk epilogue has no global load on its critical path
   // (round 1: four 128-bit bias loads per 16-column chunk, ~7 dependent round trips per thread)
@@ -707,6 +737,27 @@ struct EpBiasAct {  // y = act(acc + bias[n])
 struct EpMaskAcc {  // g = acc * (mask > 0) (+ g)
   float* g; long long ld; const float* mask; long long ldm; bool accumulate;
   static constexpr bool kRowReduce = false;
+  static constexpr int kStaged = 2;
+  __device__ __forceinline__ bool staged_ok(int m0, int n0, int ncols) const {
+    return ld % 4 == 0 && ncols % 4 == 0 && ((reinterpret_cast<uintptr_t>(g + (long long)m0 * ld + n0) & 15) == 0) &&
+           (!mask || (ldm % 4 == 0 && ((reinterpret_cast<uintptr_t>(mask + (long long)m0 * ldm + n0) & 15) == 0)));
+  }
+  __device__ __forceinline__ void pre(float*, const float*) const {}
+  __device__ __forceinline__ float4 load_mask4(int m, int n) const {
+    return mask ? __ldg(reinterpret_cast<const float4*>(mask + (long long)m * ldm + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  __device__ __forceinline__ void store4(int m, int n, float4 o, const float4& k) const {
+    float* dst = g + (long long)m * ld + n;
+    if (!(k.x > 0.f)) o.x = 0.f;
+    if (!(k.y > 0.f)) o.y = 0.f;
+    if (!(k.z > 0.f)) o.z = 0.f;
+    if (!(k.w > 0.f)) o.w = 0.f;
+    if (accumulate) {
+      const float4 p = *reinterpret_cast<const float4*>(dst);
+      o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+    }
+    *reinterpret_cast<float4*>(dst) = o;
+  }
   // the mask chunk of a row is loaded one chunk ahead of its use (aux), so that its latency hides
   // under the TMEM load / stores of the previous chunk instead of serialising the epilogue
   __device__ __forceinline__ bool vec_ok(int m, int n0, int nv) const {
@@ -762,6 +813,12 @@ struct EpMaskAcc {  // g = acc * (mask > 0) (+ g)
 struct EpPartial {  // split-K partial: ws[z][m][n]
   float* ws; long long MN; long long ld;
   static constexpr bool kRowReduce = false;
+  static constexpr int kStaged = 1;
+  __device__ __forceinline__ bool staged_ok(int m0, int n0, int ncols) const {
+    return ld % 4 == 0 && MN % 4 == 0 && ncols % 4 == 0 && ((reinterpret_cast<uintptr_t>(ws + (long long)m0 * ld + n0) & 15) == 0);
+  }
+  __device__ __forceinline__ void pre(float*, const float*) const {}
+  __device__ __forceinline__ float* row_ptr(int m, int n0, int z) const { return ws + (long long)z * MN + (long long)m * ld + n0; }
   __device__ __forceinline__ void operator()(int m, int n0, float* v, int nv, int z) const {
     float* dst = ws + (long long)z * MN + (long long)m * ld + n0;
     if (nv == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -1207,9 +1264,15 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
       if (tid == 0) TC_TRACE(2, 511, 0);
       const int row = m0 + (warp & 3) * 32 + lane;
       const int ncols = min(n_valid, N - n0);
+      bool staged_on = false;
+      if constexpr (staged_kind<Ep>::value != 0) {
+#ifndef B200_NO_STAGED_EP
+        staged_on = ep.staged_ok(m0, n0, ncols) && ncols <= 256;   // (256 columns: two 16-byte groups per lane and row)
+#endif
+      }
       [[maybe_unused]] float4 aux[4], aux_next[4];
       if constexpr (has_aux<Ep>::value) {   // first chunk's global inputs: in flight while the last MMAs drain
-        if (row < M && (pw >> 2) * 16 < ncols)
+        if (!staged_on && row < M && (pw >> 2) * 16 < ncols)
           ep.load_aux(row, n0 + (pw >> 2) * 16, min(16, ncols - (pw >> 2) * 16), aux);
       }
       [[maybe_unused]] float bias_reg = 0.f;
@@ -1246,6 +1309,89 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
         if (pw >= 4) red[(warp & 3) * 32 + lane] = acc;
         asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
         if (pw < 4 && row < M) ep.finish(row, blockIdx.x, acc + red[(warp & 3) * 32 + lane]);
+      } else if (staged_kind<Ep>::value != 0 && staged_on) {
+        if constexpr (staged_kind<Ep>::value != 0) {
+          // ---- phase 1: TMEM -> registers (-> bias / ReLU) -> staging tile, thread = accumulator row ----
+          float* stg = reinterpret_cast<float*>(base + 1024);   // (the first KB holds the staged bias)
+          const int lds = bn + 4;
+          const int rl = (warp & 3) * 32 + lane;
+          float* srow = stg + rl * lds;
+          for (int ch = pw >> 2; ch * 16 < ncols; ch += 4) {
+            const int ch2 = ch + 2;
+            const bool two = ch2 * 16 < ncols;
+            uint32_t pr[16], sr[16], pr2[16], sr2[16];
+            float v2[16];
+            tmem_ld16_nowait(tmem + lane_addr + ch * 16, pr);
+            if (add_s) tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch * 16, sr);
+            if (two) {
+              tmem_ld16_nowait(tmem + lane_addr + ch2 * 16, pr2);
+              if (add_s) tmem_ld16_nowait(tmem + lane_addr + TMEM_S + ch2 * 16, sr2);
+            }
+            if (add_s) {
+              tmem_wait_ld2(pr, sr);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(pr[i]) + __uint_as_float(sr[i]);
+            } else {
+              tmem_wait_ld1(pr);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(pr[i]);
+            }
+            if (two) {
+              if (add_s) {
+                tmem_wait_ld2(pr2, sr2);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v2[i] = __uint_as_float(pr2[i]) + __uint_as_float(sr2[i]);
+              } else {
+                tmem_wait_ld1(pr2);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v2[i] = __uint_as_float(pr2[i]);
+              }
+            }
+            ep.pre(v, bias_s + ch * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(srow + ch * 16 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            if (two) {
+              ep.pre(v2, bias_s + ch2 * 16);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(srow + ch2 * 16 + 4 * q) = make_float4(v2[4 * q], v2[4 * q + 1], v2[4 * q + 2], v2[4 * q + 3]);
+            }
+          }
+          if constexpr (staged_kind<Ep>::value == 1) fence_proxy_async();   // the bulk copies read through the async proxy
+          asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
+          // ---- phase 2: row-wise write-out ----
+          if constexpr (staged_kind<Ep>::value == 1) {
+            if (tid < BM && m0 + tid < M) {
+              bulk_s2g(ep.row_ptr(m0 + tid, n0, blockIdx.z), smem_u32(stg + tid * lds), (uint32_t)ncols * 4u);
+              bulk_commit_wait_read();
+            }
+          } else {
+            const int nq = ncols >> 2;                    // 16-byte column groups of a row
+            for (int r0 = pw * 4; r0 < BM; r0 += 32) {    // 4 rows per warp and round: their mask loads fly together
+              float4 mk[4][2];
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) {
+                const int m = m0 + r0 + rr;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int c4 = lane + 32 * h;
+                  mk[rr][h] = (m < M && c4 < nq) ? ep.load_mask4(m, n0 + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+              }
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) {
+                const int m = m0 + r0 + rr;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int c4 = lane + 32 * h;
+                  if (m < M && c4 < nq)
+                    ep.store4(m, n0 + 4 * c4, *reinterpret_cast<const float4*>(stg + (r0 + rr) * lds + 4 * c4), mk[rr][h]);
+                }
+              }
+            }
+          }
+        }
       } else {
         if constexpr (has_aux<Ep>::value) {
           for (int ch = pw >> 2; ch * 16 < ncols; ch += 2) {
