@@ -1359,19 +1359,32 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
             }
           }
           if constexpr (staged_kind<Ep>::value == 1) fence_proxy_async();   // the bulk copies read through the async proxy
+          if (tid == 0) TC_TRACE(2, 510, 0);
           asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
+          if (tid == 0) TC_TRACE(2, 510, 1);
           // ---- phase 2: row-wise write-out ----
           if constexpr (staged_kind<Ep>::value == 1) {
+#ifndef B200_EP_STG_ROWS   // one cp.async.bulk per row; coalesced 128-bit stores by all warps measured the same or 1 % slower
             if (tid < BM && m0 + tid < M) {
               bulk_s2g(ep.row_ptr(m0 + tid, n0, blockIdx.z), smem_u32(stg + tid * lds), (uint32_t)ncols * 4u);
               bulk_commit_wait_read();
             }
+#else
+            const int nq = ncols >> 2;                    // 16-byte column groups of a row
+            for (int r = pw; r < BM && m0 + r < M; r += THREADS / 32) {
+              float* dst = ep.row_ptr(m0 + r, n0, blockIdx.z);
+              const float* src = stg + r * lds;
+              for (int c4 = lane; c4 < nq; c4 += 32)
+                *reinterpret_cast<float4*>(dst + 4 * c4) = *reinterpret_cast<const float4*>(src + 4 * c4);
+            }
+#endif
           } else {
             const int nq = ncols >> 2;                    // 16-byte column groups of a row
-            for (int r0 = pw * 4; r0 < BM; r0 += 32) {    // 4 rows per warp and round: their mask loads fly together
-              float4 mk[4][2];
+            constexpr int RR = 8;                         // rows per warp and round: their mask loads fly together
+            for (int r0 = pw * RR; r0 < BM; r0 += 8 * RR) {
+              float4 mk[RR][2];
 #pragma unroll
-              for (int rr = 0; rr < 4; ++rr) {
+              for (int rr = 0; rr < RR; ++rr) {
                 const int m = m0 + r0 + rr;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -1380,7 +1393,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
                 }
               }
 #pragma unroll
-              for (int rr = 0; rr < 4; ++rr) {
+              for (int rr = 0; rr < RR; ++rr) {
                 const int m = m0 + r0 + rr;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {

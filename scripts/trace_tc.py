@@ -19,6 +19,9 @@ def dump(title, nkb, fn="b200rec_debug_tc_trace", first=0):
         d = a[2, kb, 0] - t0 if a[2, kb, 0] else 0
         d0 = a[2, kb, 1] - t0 if a[2, kb, 1] else 0
         print(f"{kb:3d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d} | {p[0]:7d} {p[1]:7d} {p[2]:7d} {p[3]:7d} | {d0:7d} {d:7d}")
+    ph = a[2, 510] - t0
+    if a[2, 510, 0]:
+        print(f" staged epilogue: tile parked {ph[0]}, barrier passed {ph[1]}")
     e = a[2, 511] - t0
     print(f" epilogue: producers done {e[0]}, last MMA drained {e[1]}, epilogue stored {e[2]}, CTA end {e[3]}")
     m = a[0, :nkb] - t0
