@@ -32,6 +32,29 @@ int splitk_reduce(const float* ws, int splits, long long MN, float scale, bool a
   return B200REC_OK;
 }
 
+// the same for a weight-gradient GEMM that carried the bias gradient as column K of its [N x ldw] partials
+__global__ void splitk_reduce_wb_kernel(const float* ws, int splits, int N, int K, int ldw, float scale,
+                                        bool accumulate, float* gw, float* gb) {
+  const long long total = (long long)N * (K + 1), MN = (long long)N * ldw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / (K + 1)), k = (int)(i - (long long)n * (K + 1));
+    const float* p = ws + (long long)n * ldw + k;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += p[z * MN];
+    s *= scale;
+    float* out = k < K ? gw + (long long)n * K + k : gb + n;
+    *out = accumulate ? *out + s : s;
+  }
+}
+int splitk_reduce_wb(const float* ws, int splits, int N, int K, int ldw, float scale, bool accumulate,
+                     float* gw, float* gb, cudaStream_t st) {
+  B200_LAUNCH(splitk_reduce_wb_kernel, grid1d((long long)N * (K + 1)), 256, 0, st, ws, splits, N, K, ldw, scale,
+              accumulate, gw, gb);
+  B200_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
 int linear_fwd(int M, int N, int K, const float* x, const float* w, const float* b, bool relu,
                float* y, cudaStream_t st, int mode) {
   if (N > 1 && mode) return tc_linear_fwd(M, N, K, x, w, b, relu, y, mode == 1 ? 3 : 1, st);

@@ -165,6 +165,8 @@ gemm_simt_kernel(int M, int N, int K, int k_chunk, AOp aop, BOp bop, Ep ep) {
 // out (+)= scale * sum_z ws[z]   (z ascending: fixed order)            -- dense.cu
 int splitk_reduce(const float* ws, int splits, long long MN, float scale, bool accumulate,
                   float* out, cudaStream_t st);
+int splitk_reduce_wb(const float* ws, int splits, int N, int K, int ldw, float scale, bool accumulate,
+                     float* gw, float* gb, cudaStream_t st);
 // colsum / COLSUM_CHUNKS: kernels.h
 // the split count gemm_simt really uses for (K, splits)
 static inline int real_splits(int K, int splits) {

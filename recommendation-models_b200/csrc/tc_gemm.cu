@@ -224,19 +224,26 @@ int tc_linear_bwd_input(int M, int N, int K, const float* gy, const float* w, co
 int tc_linear_bwd_params(int M, int N, int K, const float* x, const float* gy, float scale,
                          bool accumulate, float* gw, float* gb, DevBuf& scratch, int passes,
                          cudaStream_t st) {
-  const int bn = pick_bn(K);
-  const int tiles = cdiv(N, BM) * cdiv(K, bn);
+  // With a bias gradient asked for, the B operand is [x | 1]: output column K is gb = colsum(gy).  The partials
+  // then have K + 4 columns (16-byte rows for the staged epilogue; columns K + 1 .. K + 3 are zero).
+  static const bool fuse_gb = [] { const char* e = std::getenv("B200REC_FUSE_BIAS_GRAD"); return !(e && e[0] == '0'); }();
+  const bool with_gb = gb != nullptr && fuse_gb;
+  const int Kc = with_gb ? K + 4 : K;
+  const int bn = pick_bn(Kc);
+  const int tiles = cdiv(N, BM) * cdiv(Kc, bn);
   int splits = pick_splits_waves(tiles, cdiv(M, BK), M / 256 > 0 ? M / 256 : 1);
   int k_chunk = ((cdiv(M, splits) + BK - 1) / BK) * BK;
   splits = cdiv(M, k_chunk);
-  const long long MN = (long long)N * K;
+  const long long MN = (long long)N * Kc;
   B200_TRY(scratch.reserve(((size_t)splits * MN + (size_t)COLSUM_CHUNKS * N) * sizeof(float)));
   float* ws = scratch.as<float>();
   KPlain s{0, M, k_chunk};
   ColProd<128, KPlain> ap{gy, N, N, BM, colvec(gy, N, N)};  // A(n, m) = gy[m*N + n]
   ColProd<256, KPlain> bp{x, K, K, bn, colvec(x, K, K)};   // B(k, m) = x[m*K + k]: packed once (all splits)
-  B200_TRY(launch_packed("tc_linear_dW", N, K, bn, bn, bn, cdiv(K, bn), cdiv(M, BK), s, ap, bp,
-                         tc::EpPartial{ws, MN, K}, passes, st, nullptr, splits, k_chunk));
+  if (with_gb) bp.ones_row = K;
+  B200_TRY(launch_packed("tc_linear_dW", N, Kc, bn, bn, bn, cdiv(Kc, bn), cdiv(M, BK), s, ap, bp,
+                         tc::EpPartial{ws, MN, Kc}, passes, st, nullptr, splits, k_chunk));
+  if (with_gb) return splitk_reduce_wb(ws, splits, N, K, Kc, scale, accumulate, gw, gb, st);
   B200_TRY(splitk_reduce(ws, splits, MN, scale, accumulate, gw, st));
   if (gb) B200_TRY(colsum(M, N, gy, scale, accumulate, gb, ws + (size_t)splits * MN, st));
   return B200REC_OK;

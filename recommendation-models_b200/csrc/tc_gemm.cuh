@@ -400,11 +400,19 @@ struct ColProd {
   Sched s;
   int row0, tid;
   bool is_b = false;   // B operand: the correction tile is [lo | hi] instead of [hi | lo] (split_store)
+  // Row `ones_row` of the operand reads as 1.0 at every valid k (and is otherwise past rows_total): the weight-
+  // gradient GEMM gy^T [x | 1] then yields the bias gradient (column sums of gy) as one more output column, and
+  // the two column-sum launches per layer disappear (BackwardUtil.linearBackward's gradBias).
+  int ones_row = -1;
   float4 reg[MAXT];
   static constexpr int DIST = 1;
   template <int SLOT> __device__ __forceinline__ void prefetch2(int kb) { prefetch(kb); }
   template <int SLOT> __device__ __forceinline__ void store2(int kb, char* hi, char* lo) { store(kb, hi, lo); }
   __device__ __forceinline__ void init(char*, int r0, int t) { row0 = r0; tid = t; }
+  __device__ __forceinline__ float4 ones4(int c, int kv) const {
+    return make_float4(4 * c + 0 < kv ? 1.f : 0.f, 4 * c + 1 < kv ? 1.f : 0.f, 4 * c + 2 < kv ? 1.f : 0.f,
+                       4 * c + 3 < kv ? 1.f : 0.f);
+  }
   __device__ __forceinline__ void prefetch(int kb) {
     const int kv = s.kvalid(kb);
     if (vec) {
@@ -424,6 +432,11 @@ struct ColProd {
         reg[4 * t + 1] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
         reg[4 * t + 2] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
         reg[4 * t + 3] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+        if (ones_row >= 0 && r < tile_rows) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (row0 + r + e == ones_row) reg[4 * t + e] = ones4(c, kv);
+        }
       }
       return;
     }
@@ -440,6 +453,7 @@ struct ColProd {
         if (4 * c + 2 < kv) v.z = __ldg(src + (long long)(4 * c + 2) * ld);
         if (4 * c + 3 < kv) v.w = __ldg(src + (long long)(4 * c + 3) * ld);
       }
+      if (ones_row >= 0 && r < tile_rows && row0 + r == ones_row) v = ones4(c, kv);
       reg[t] = v;
     }
   }
