@@ -722,6 +722,7 @@ static int step_on_device(Model* m, Table* t, int B, const int* feats, const flo
     B200_TRY(m->dw.reserve((size_t)nnz * f));
     B200_TRY(m->seg.reserve(nnz));
     sg.n = nnz; sg.K = has_emb ? m->K : 4; sg.key_bits = key_bits_for(t->rows);
+    sg.background = m->kind != B200REC_LR && m->kind != B200REC_FM;   // FM / LR: the sort IS the critical path
     sg.feats = feats;
     sg.unique = m->uniq.as<int>();
     sg.n_unique = m->scal.as<int>() + 2;

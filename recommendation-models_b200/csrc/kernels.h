@@ -58,6 +58,7 @@ int dot2_bwd(long long n, int K, const float* a, const float* b, const float* go
              float* gb, cudaStream_t st);
 
 // ---------------------------------------------------------------- segsum.cu (scatter-add) ----
+constexpr int RS_THREADS = 256, RS_TILE = 2048, RS_BINS = 256;   // radix sort: threads per tile, items per tile, 8-bit digits
 struct SegSumWorkspace {
   DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, seg_start, long_list, counters;
   long long cap_n = 0;
@@ -76,6 +77,7 @@ struct SegSum {
   float* gw = nullptr;            // [n]   out
   int* n_unique = nullptr;        // device int out
   bool drop_pad = false;          // keys equal to -1 (exchange padding) form no segment
+  bool background = false;        // the sort half runs beside dense math (side stream): few fat blocks instead of one per tile
   // fused gradient producer (segsum.cu): rows are computed from the step's saved tensors instead of
   // being read from dE / dw:  dE[p] = (dlogit_b / K)(S_b - X[p]) + dX[p], dw[p] = dlogit_b, b = p / F
   bool fused = false;

@@ -4,7 +4,9 @@
 // (makeWeightsGrad): for every non-zero i = 0..N-1 IN ORDER, grads(j).addTo(feats(i), buf(i*K+j)).
 // So the gradient of a distinct id is the fp32 sum of its rows in increasing i.
 //
-// Here: a stable LSD radix sort of (id, i) pairs groups equal ids while keeping i ascending;
+// Here: a stable LSD radix sort of (id, i) pairs groups equal ids while keeping i ascending (own kernels, below:
+// a batch is 10^5 .. 10^6 keys of 24 - 32 bits, where a library onesweep sort is bound by its tile-to-tile look-back
+// chain -- 0.10 ms for 320 k pairs -- while three short launches per 8-bit digit have no serial chain at all);
 // segment heads give the distinct ids (ascending); each segment is then summed strictly in
 // order.  Loads are issued in parallel, only the fp32 adds are sequential, so the result is
 // bit-identical to the reference's hash-map accumulation regardless of grid size -- there are
@@ -24,8 +26,7 @@
 // (SecondOrderEncoder backward + GradUtil.embeddingGrad / weightsGrad, rec/util/GradUtil.scala:7-42), with
 // the same arithmetic as emb_grad_kernel (sparse.cu), so the sums are bit-identical to the two-kernel
 // path while the 2 x N x K x 4 bytes of the dE round trip never touch HBM.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "p2p_dev.cuh"
@@ -47,11 +48,10 @@ int SegSumWorkspace::reserve(long long n) {
   // [0, ni/LONG_T): segments of LONG_T+1 .. BIG_T rows; [ni/LONG_T, ...): segments of more than BIG_T rows
   B200_TRY(long_list.reserve((ni / LONG_T + ni / BIG_T) * 4 + 128));
   B200_TRY(counters.reserve(64));
-  size_t sort_bytes = 0, scan_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
-                                  (const unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 32);
-  cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)n);
-  B200_TRY(cub_tmp.reserve((sort_bytes > scan_bytes ? sort_bytes : scan_bytes) * 2 + 1024));
+  B200_TRY(keys_a.reserve(ni * 4));
+  // radix-sort histograms [256 digits][tiles] (+ the per-tile segment-head counts of the segment scan)
+  const size_t tiles = (ni + RS_TILE - 1) / RS_TILE;
+  B200_TRY(cub_tmp.reserve((RS_BINS * tiles + RS_BINS + 2 * tiles + 64) * 4));   // SEG_TILE = RS_TILE / 2
   cap_n = n;
   return B200REC_OK;
 }
@@ -62,31 +62,235 @@ void SegSumWorkspace::release() {
   cap_n = 0;
 }
 
-__global__ void iota_kernel(long long n, unsigned* v, int* counters) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < n) v[i] = (unsigned)i;
-  if (i == 0) { counters[0] = 0; counters[1] = 0; }
-}
-
-__global__ void head_flag_kernel(long long n, const unsigned* keys, int* flags) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
-}
-
-// seg_idx[i] = 1-based segment number of sorted position i (inclusive scan of the head flags)
-__global__ void seg_heads_kernel(long long n, const unsigned* keys, const int* seg_idx,
-                                 int* seg_start, int* unique, int* n_unique, bool drop_pad) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int s = seg_idx[i];
-  if (i == 0 || keys[i] != keys[i - 1]) {
-    seg_start[s - 1] = (int)i;
-    unique[s - 1] = (int)keys[i];
+// ---- stable LSD radix sort of (key, position) pairs, 8 bits per pass, three launches per pass ------------
+//   rs_hist   : tile t (2048 consecutive items) counts its digits                    -> hist[digit][tile]
+//   rs_rowscan: one block per digit: exclusive prefix over the tiles + the digit's total (rs_scatter scans the 256 totals)
+//   rs_scatter: the tile walks its items in 8 rounds of 256 (round, thread) = index order; inside a round the rank
+//               of an item among equal digits = match.any inside the warp + per-warp digit counts scanned over the
+//               8 warps, so equal keys keep their input order (the pass is stable; nothing is atomic)
+// The first pass takes the position as the value (no iota array).
+// (every kernel of the sort half is a 256-thread block with few registers: it has to fit NEXT TO a resident GEMM
+// CTA -- 320 threads x 168 registers -- or it would wait for an SM between two GEMM launches and stall them)
+__device__ __forceinline__ int block_excl_scan_256(int v, int* warp_sums, int* total) {   // blockDim.x == 256
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
   }
-  if (i == n - 1) {
-    // exchange padding (key 0xffffffff) sorts last: its segment is not a feature id
-    *n_unique = (drop_pad && keys[i] == 0xffffffffu) ? s - 1 : s;
-    seg_start[s] = (int)n;
+  if (lane == 31) warp_sums[w] = inc;
+  __syncthreads();
+  int wbase = 0, tot = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int x = warp_sums[q];
+    wbase += q < w ? x : 0;
+    tot += x;
+  }
+  if (total) *total = tot;
+  __syncthreads();
+  return wbase + inc - v;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(int n, const unsigned* __restrict__ keys, int shift,
+                                                              int* __restrict__ hist, int tiles, int group, int* counters) {
+  __shared__ int cnt[RS_BINS];
+  if (counters && blockIdx.x == 0 && threadIdx.x < 2) counters[threadIdx.x] = 0;   // the hot-id list counters
+  // a block takes `group` consecutive tiles: one tile per block when the sort is on the critical path (FM / LR),
+  // ~20 fat blocks when it runs beside the dense math, where the GEMMs leave 20 of the 148 SMs idle and anything
+  // spread over all SMs takes issue slots from their producer warps
+  for (int tile = blockIdx.x * group; tile < min(tiles, (blockIdx.x + 1) * group); ++tile) {
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = tile * RS_TILE;
+  unsigned d[RS_TILE / RS_THREADS];
+#pragma unroll
+  for (int j = 0; j < RS_TILE / RS_THREADS; ++j) {      // all loads of the tile in flight
+    const int i = base + j * RS_THREADS + threadIdx.x;
+    d[j] = i < n ? ((keys[i] >> shift) & (RS_BINS - 1)) : 0xffffu;
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < RS_TILE / RS_THREADS; ++j) {
+    // one shared-memory atomic per distinct digit of the warp (the high digits of feature ids take few values)
+    const unsigned peers = __match_any_sync(0xffffffffu, d[j]);
+    if (d[j] != 0xffffu && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&cnt[d[j]], __popc(peers));
+  }
+  __syncthreads();
+  hist[threadIdx.x * tiles + tile] = cnt[threadIdx.x];
+  __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) rs_scan_kernel(int* __restrict__ a, int total) {   // one block: exclusive scan in place
+  __shared__ int warp_sums[8];
+  const int per = (total + 255) / 256;
+  const int b0 = threadIdx.x * per, b1 = min(total, b0 + per);
+  int s = 0;
+  for (int i = b0; i < b1; ++i) s += a[i];
+  int run = block_excl_scan_256(s, warp_sums, nullptr);
+  for (int i = b0; i < b1; ++i) {
+    const int v = a[i];
+    a[i] = run;
+    run += v;
+  }
+}
+
+// one block per digit: hist[d][0 .. tiles) becomes its own exclusive prefix, totals[d] the digit's count
+__global__ void __launch_bounds__(RS_THREADS) rs_rowscan_kernel(int* __restrict__ hist, int tiles, int* __restrict__ totals) {
+  __shared__ int wsum[RS_THREADS / 32];
+  __shared__ int carry_s;
+  int* row = hist + (size_t)blockIdx.x * tiles;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < tiles; c0 += RS_THREADS) {
+    const int i = c0 + threadIdx.x;
+    const int v = i < tiles ? row[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int wbase = 0;
+#pragma unroll
+    for (int q = 0; q < RS_THREADS / 32; ++q) wbase += q < w ? wsum[q] : 0;
+    const int carry = carry_s;
+    if (i < tiles) row[i] = carry + wbase + inc - v;
+    __syncthreads();
+    if (threadIdx.x == RS_THREADS - 1) carry_s = carry + wbase + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int n, const unsigned* __restrict__ keys_in,
+                                                                 const unsigned* __restrict__ vals_in, int shift,
+                                                                 const int* __restrict__ hist, int tiles, int group,
+                                                                 const int* __restrict__ totals,
+                                                                 unsigned* __restrict__ keys_out,
+                                                                 unsigned* __restrict__ vals_out) {
+  __shared__ int base[RS_BINS];                        // next output slot of every digit for this tile
+  __shared__ int wcnt[RS_THREADS / 32][RS_BINS];       // per-warp digit counts of the current round
+  __shared__ int wsum[RS_THREADS / 32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  for (int tile = blockIdx.x * group; tile < min(tiles, (blockIdx.x + 1) * group); ++tile) {
+  const int tile0 = tile * RS_TILE;
+  constexpr int NJ = RS_TILE / RS_THREADS;
+  unsigned keyr[NJ], valr[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {                       // the tile's loads fly together, ahead of the ranking rounds
+    const int i = tile0 + j * RS_THREADS + t;
+    keyr[j] = i < n ? keys_in[i] : 0u;
+    valr[j] = (i < n && vals_in) ? vals_in[i] : (unsigned)i;
+  }
+  {  // first slot of digit t for this tile = (digits before t) + (digit t in the tiles before this one)
+    const int tot = totals[t];
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int wbase = 0;
+#pragma unroll
+    for (int q = 0; q < RS_THREADS / 32; ++q) wbase += q < w ? wsum[q] : 0;
+    base[t] = wbase + inc - tot + hist[t * tiles + tile];
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int i = tile0 + j * RS_THREADS + t;
+    if (tile0 + j * RS_THREADS >= n) break;            // block-uniform
+    const bool valid = i < n;
+    const unsigned key = keyr[j], val = valr[j];
+    const unsigned d = valid ? ((key >> shift) & (RS_BINS - 1)) : 0xffffu;
+#pragma unroll
+    for (int q = 0; q < RS_THREADS / 32; ++q) wcnt[q][t] = 0;
+    __syncthreads();
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) wcnt[w][d] = __popc(peers);
+    __syncthreads();
+    int acc = 0;                                       // thread t scans digit t over the warps
+#pragma unroll
+    for (int q = 0; q < RS_THREADS / 32; ++q) {
+      const int c = wcnt[q][t];
+      wcnt[q][t] = acc;
+      acc += c;
+    }
+    __syncthreads();
+    if (valid) {
+      const int pos = base[d] + wcnt[w][d] + rank;
+      keys_out[pos] = key;
+      vals_out[pos] = val;
+    }
+    __syncthreads();
+    base[t] += acc;
+  }
+  __syncthreads();
+  }
+}
+
+// ---- segments of the sorted keys: three launches, no library scan ----------------------------------------
+//   seg_count : heads (key != previous key) per tile of 1024 positions
+//   rs_scan   : exclusive scan of the tile counts
+//   seg_write : seg_idx[i] = 1-based segment number of sorted position i; seg_start / unique at the heads
+constexpr int SEG_TILE = 1024, SEG_THREADS = 256, SEG_PER = SEG_TILE / SEG_THREADS;   // a thread owns 4 consecutive positions
+__global__ void __launch_bounds__(SEG_THREADS) seg_count_kernel(int n, const unsigned* __restrict__ keys, int* __restrict__ tile_heads) {
+  __shared__ int warp_sums[8];
+  const int i0 = blockIdx.x * SEG_TILE + threadIdx.x * SEG_PER;
+  int h = 0;
+  unsigned prev = i0 > 0 && i0 - 1 < n ? keys[i0 - 1] : 0u;
+#pragma unroll
+  for (int u = 0; u < SEG_PER; ++u) {
+    const int i = i0 + u;
+    const unsigned k = i < n ? keys[i] : 0u;
+    h += (i < n && (i == 0 || k != prev)) ? 1 : 0;
+    prev = k;
+  }
+  int tot;
+  block_excl_scan_256(h, warp_sums, &tot);
+  if (threadIdx.x == 0) tile_heads[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SEG_THREADS) seg_write_kernel(int n, const unsigned* __restrict__ keys,
+                                                                const int* __restrict__ tile_off, int* __restrict__ seg_idx,
+                                                                int* __restrict__ seg_start, int* __restrict__ unique,
+                                                                int* __restrict__ n_unique, bool drop_pad) {
+  __shared__ int warp_sums[8];
+  const int i0 = blockIdx.x * SEG_TILE + threadIdx.x * SEG_PER;
+  unsigned k[SEG_PER];
+  int hd[SEG_PER], h = 0;
+  unsigned prev = i0 > 0 && i0 - 1 < n ? keys[i0 - 1] : 0u;
+#pragma unroll
+  for (int u = 0; u < SEG_PER; ++u) {
+    const int i = i0 + u;
+    k[u] = i < n ? keys[i] : 0u;
+    hd[u] = (i < n && (i == 0 || k[u] != prev)) ? 1 : 0;
+    h += hd[u];
+    prev = k[u];
+  }
+  int s = tile_off[blockIdx.x] + block_excl_scan_256(h, warp_sums, nullptr);   // heads before this thread's positions
+#pragma unroll
+  for (int u = 0; u < SEG_PER; ++u) {
+    const int i = i0 + u;
+    if (i >= n) break;
+    s += hd[u];                      // inclusive: 1-based segment number of position i
+    seg_idx[i] = s;
+    if (hd[u]) {
+      seg_start[s - 1] = i;
+      unique[s - 1] = (int)k[u];
+    }
+    if (i == n - 1) {
+      // exchange padding (key 0xffffffff) sorts last: its segment is not a feature id
+      *n_unique = (drop_pad && k[u] == 0xffffffffu) ? s - 1 : s;
+      seg_start[s] = n;
+    }
   }
 }
 
@@ -112,27 +316,36 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
     return B200REC_OK;
   }
   const int n = (int)a.n;
-  unsigned* vals_in = ws.vals_a.as<unsigned>();
-  unsigned* perm = ws.vals_b.as<unsigned>();
+  unsigned* perm = ws.vals_b.as<unsigned>();          // the sorted pairs always end in (keys_b, vals_b)
   unsigned* keys_sorted = ws.keys_b.as<unsigned>();
-  B200_LAUNCH(iota_kernel, cdiv(n, 256), 256, 0, st, (long long)n, vals_in, counters);
-  size_t tmp = ws.cub_tmp.cap;
-  int bits = a.key_bits < 1 ? 1 : (a.key_bits > 32 ? 32 : a.key_bits);
-  if (tl_prof) tl_prof->begin("cub::DeviceRadixSort::SortPairs", st);
-  B200_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp.p, tmp, (const unsigned*)a.feats,
-                                            keys_sorted, vals_in, perm, n, 0, bits, st));
-  if (tl_prof) tl_prof->end(st);
-  g_launches.fetch_add(2 + (bits + 7) / 8, std::memory_order_relaxed);  // cub's own kernels
-  // head flags -> inclusive scan -> segment table.  vals_a (the iota) is free again: reuse it.
+  int* hist = ws.cub_tmp.as<int>();
+  int* totals = hist + (size_t)RS_BINS * cdiv(n, RS_TILE);
+  const int bits = a.key_bits < 1 ? 1 : (a.key_bits > 32 ? 32 : a.key_bits);
+  const int passes = (bits + 7) / 8;
+  const int tiles = cdiv(n, RS_TILE);
+  static const int bg_group = [] { const char* e = std::getenv("B200REC_SORT_GROUP"); return e && *e ? atoi(e) : 1; }();
+  const int group = a.background && bg_group > 1 ? bg_group : 1;   // (measured: 1 is best; ~20 fat blocks make the sort the critical path)
+  const int blocks = cdiv(tiles, group);
+  const unsigned* kin = (const unsigned*)a.feats;
+  const unsigned* vin = nullptr;                      // first pass: the value is the position itself
+  for (int p = 0; p < passes; ++p) {
+    const bool to_b = ((passes - 1 - p) & 1) == 0;    // ping-pong so that the last pass writes the b buffers
+    unsigned* kout = to_b ? ws.keys_b.as<unsigned>() : ws.keys_a.as<unsigned>();
+    unsigned* vout = to_b ? ws.vals_b.as<unsigned>() : ws.vals_a.as<unsigned>();
+    B200_LAUNCH(rs_hist_kernel, blocks, RS_THREADS, 0, st, n, kin, 8 * p, hist, tiles, group, p == 0 ? counters : nullptr);
+    B200_LAUNCH(rs_rowscan_kernel, RS_BINS, RS_THREADS, 0, st, hist, tiles, totals);
+    B200_LAUNCH(rs_scatter_kernel, blocks, RS_THREADS, 0, st, n, kin, vin, 8 * p, hist, tiles, group, totals, kout, vout);
+    kin = kout;
+    vin = vout;
+  }
+  // segment table.  vals_a is free again (the last pass read it at most): it becomes seg_idx.
   int* seg_idx = ws.vals_a.as<int>();
-  B200_LAUNCH(head_flag_kernel, cdiv(n, 256), 256, 0, st, (long long)n, keys_sorted, seg_idx);
-  tmp = ws.cub_tmp.cap;
-  if (tl_prof) tl_prof->begin("cub::DeviceScan::InclusiveSum", st);
-  B200_CUDA(cub::DeviceScan::InclusiveSum(ws.cub_tmp.p, tmp, seg_idx, seg_idx, n, st));
-  if (tl_prof) tl_prof->end(st);
-  g_launches.fetch_add(2, std::memory_order_relaxed);
-  B200_LAUNCH(seg_heads_kernel, cdiv(n, 256), 256, 0, st, (long long)n, keys_sorted, seg_idx,
-              ws.seg_start.as<int>(), a.unique, a.n_unique, a.drop_pad);
+  const int stiles = cdiv(n, SEG_TILE);
+  int* tile_heads = totals + RS_BINS;
+  B200_LAUNCH(seg_count_kernel, stiles, SEG_THREADS, 0, st, n, keys_sorted, tile_heads);
+  B200_LAUNCH(rs_scan_kernel, 1, 256, 0, st, tile_heads, stiles);
+  B200_LAUNCH(seg_write_kernel, stiles, SEG_THREADS, 0, st, n, keys_sorted, tile_heads, seg_idx, ws.seg_start.as<int>(),
+              a.unique, a.n_unique, a.drop_pad);
   {
     int grid = cdiv(n, 256);
     if (grid > 148 * 8) grid = 148 * 8;
