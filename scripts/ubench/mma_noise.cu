@@ -2,6 +2,7 @@
 // TF32 + bf16 K-block (4 + 4, M=128, N=208, operands in shared memory) 400 times; NW "noise" warps meanwhile run
 //   mode 0: nothing (they wait)          mode 1: integer ALU chains (the producers' split arithmetic)
 //   mode 2: ALU + 128-bit shared stores  mode 3: ALU + L1-hitting global loads      mode 4: shared stores only
+//   mode 5: four independent integer chains per thread (issue-bound)
 // placed on all four schedulers or only on schedulers 1-3 (the MMA warp is warp 0 = scheduler 0).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I recommendation-models_b200/csrc -I include \
 //        scripts/ubench/mma_noise.cu -o scripts/ubench/mma_noise && ./scripts/ubench/mma_noise
@@ -55,9 +56,13 @@ __global__ void __launch_bounds__(1024, 1) noise_kernel(int bn, int reps, int mo
     while (!stop) {
 #pragma unroll 8
       for (int i = 0; i < 32; ++i) {
-        if (mode != 4) {
+        if (mode != 4 && mode != 5) {
           x = (x + 0x1000u) & 0xffffe000u; y = __byte_perm(y + 0x8000u, x, 0x7632); z = (z + x) ^ y; w = (w + 0x8000u) & z;
           x += w; y += z;
+        }
+        if (mode == 5) {   // four INDEPENDENT chains: issue-bound noise (the modes above are latency-bound chains)
+          x = (x + 0x1000u) & 0xffffe000u; y = (y + 0x8000u) ^ 0x7632u; z = (z + 0x1001u) & 0xfffff000u; w = (w + 0x8001u) ^ 0x1234u;
+          x = (x + 0x1000u) & 0xffffe000u; y = (y + 0x8000u) ^ 0x7632u; z = (z + 0x1001u) & 0xfffff000u; w = (w + 0x8001u) ^ 0x1234u;
         }
         if (mode == 2 || mode == 4) *reinterpret_cast<uint4*>(scratch + ((threadIdx.x * 16 + i * 16384) & 32767)) = make_uint4(x, y, z, w);
         if (mode == 3) { const float4 v = __ldg(reinterpret_cast<const float4*>(gp + ((i & 7) << 12))); x ^= __float_as_uint(v.x); }
@@ -78,12 +83,12 @@ int main() {
   float* g; cudaMalloc(&g, 1 << 20); cudaMemset(g, 0, 1 << 20);
   const int smem = 2 * (16384 + 32768) + 32768 + 2048;
   cudaFuncSetAttribute(noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const char* names[] = {"idle", "ALU", "ALU + STS.128", "ALU + LDG(L1 hit)", "STS.128 only"};
+  const char* names[] = {"idle", "ALU chains", "ALU + STS.128", "ALU + LDG(L1 hit)", "STS.128 only", "ALU 4 indep. chains"};
   const int reps = 400, bn = 208;
-  for (int grid : {1, 148})
+  for (int grid : {148})
     for (int nw : {8, 16})
       for (int skip = 0; skip < 2; ++skip)
-        for (int mode = 0; mode < 5; ++mode) {
+        for (int mode = 0; mode < 6; ++mode) {
           if (mode == 0 && skip) continue;
           cudaMemset(d, 0, 16);
           noise_kernel<<<grid, 32 * (1 + nw + (skip ? nw / 3 + 1 : 0)), smem>>>(bn, reps, mode, skip, g, d, sink);
