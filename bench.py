@@ -48,6 +48,23 @@ F, K = 39, 16
 SEED_DATA, SEED_PARAMS = 1234, 42
 
 
+def gather_ceiling_us(n_rows):
+    """Measured time of a pure random-row copy of n_rows rows (scripts/ubench/gather_rate.cu), or None."""
+    path = os.path.join(ROOT, "profiles", "r02x_gather_rate_ubench.txt")
+    if not os.path.exists(path):
+        return None
+    power_law = False
+    for line in open(path):
+        if line.startswith("== ids:"):
+            power_law = "power-law" in line
+        if power_law and line.startswith("copy U=5  rows + separate weights") and f"n={n_rows:8d}" in line:
+            try:
+                return float(line.split("avg")[1].split("us")[0])
+            except (IndexError, ValueError):
+                return None
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -345,6 +362,14 @@ def measure_1gpu(args, name, pkg, torch, local):
                            frac=round(ach / pk["hbm"], 4), algorithmic_bytes=amount)
                 if ach > pk["hbm"]:
                     row["note"] = "above the HBM copy peak: part of the operands was still in L2 from the producing kernel"
+                if tag == "gather_fm_fwd":
+                    c = gather_ceiling_us(B * F)
+                    if c:
+                        row["pattern_ceiling"] = dict(
+                            us=c, frac_of_ceiling=round(min(1.0, c * 1e-3 / ms_step), 3),
+                            source="profiles/r02x_gather_rate_ubench.txt: a stand-alone kernel that only copies the same number of "
+                                   "random 64-B rows (+ 4-B weights) out of a 654 MB table, power-law ids, timed with CUDA events: "
+                                   "at one batch the gather is latency- / launch-bound, not HBM-bound (2.9-4.7 TB/s at 4 M rows)")
             else:
                 ach = amount / (ms_step * 1e-3) / 1e12
                 row.update(bound="tensor", achieved=round(ach, 2), peak=tf32_peak, unit="TFLOP/s",
