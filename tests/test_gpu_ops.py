@@ -175,3 +175,36 @@ def test_scatter_add_bit_exact(gpu_pkg, n, rows, K):
     assert np.array_equal(G, rG)
     assert np.array_equal(gw, rgw)
     assert np.array_equal(gpu_pkg.distinct(feats), refport.distinct_int_indices(feats))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pattern", ["random31", "equal", "ascending", "descending", "two_values", "powerlaw"])
+@pytest.mark.parametrize("n", [2047, 2048, 2049, 4097, 700001])
+def test_scatter_add_sort_stress(gpu_pkg, pattern, n):
+    """The sort half is the library's own radix sort (segsum.cu: rs_hist / rs_rowscan / rs_scatter, 2048-item tiles,
+    8-bit digits, ranks by warp match): tile-boundary sizes, many tiles, all 31 key bits, degenerate digit
+    distributions -- ids, sums (in non-zero order, bit-exact) and the distinct set against the oracle."""
+    rng = np.random.default_rng(n)
+    K = 4
+    if pattern == "random31":
+        feats = rng.integers(0, 2**31 - 1, n)
+    elif pattern == "equal":
+        feats = np.full(n, 123456789)
+    elif pattern == "ascending":
+        feats = np.arange(n) * 3001 % (2**31 - 1)
+        feats.sort()
+    elif pattern == "descending":
+        feats = np.sort(rng.integers(0, 2**31 - 1, n))[::-1]
+    elif pattern == "two_values":
+        feats = np.where(rng.random(n) < 0.5, 255, 256)          # a carry between the first two digits
+    else:
+        feats = np.minimum(rng.pareto(0.7, n).astype(np.int64), 10**6)
+    feats = np.ascontiguousarray(feats).astype(np.int32)
+    dE = rng.standard_normal((n, K)).astype(np.float32)
+    dw = rng.standard_normal(n).astype(np.float32)
+    ids, G, gw = gpu_pkg.scatter_add(feats, dE, dw, dim=K)
+    rids, rG = refport.make_embedding_grad(dE.reshape(-1), feats, K)
+    _, rgw = refport.make_weights_grad(dw, feats)
+    assert np.array_equal(ids, rids)
+    assert np.array_equal(G, rG)
+    assert np.array_equal(gw, rgw)
