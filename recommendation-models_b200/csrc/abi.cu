@@ -5,6 +5,7 @@
 // Error convention: the reference raises IllegalArgumentException from Scala
 // `require`s (nn/Scatter.scala:29-30,52-53; nn/DuplicateTable.scala:61-62); here every entry point
 // returns a negative status and b200rec_last_error() carries the message.  Nothing throws.
+#include <cstdlib>
 #include <algorithm>
 #include <cstdarg>
 #include <cstring>
@@ -21,6 +22,15 @@ namespace b200rec {
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_alloc_epoch{0};
+int g_pdl = -1;
+int pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = std::getenv("B200REC_PDL");
+    g_pdl = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;
+  }
+  return g_pdl;
+}
+thread_local int tl_pdl_hint = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -20,6 +20,7 @@ template <int NPL>
 __global__ void __launch_bounds__(256) cross_fwd_kernel(int B, int D, int L, const float* X,
                                                         const float* w, const float* c, float* xL,
                                                         float* s_out) {
+  B200_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += gridDim.x * wpb) {
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) cross_bwd_kernel(int B, int D, int L, con
                                                         const float* w, const float* s_in,
                                                         const float* g_xL, float* dX, float* u,
                                                         float* gs_out, float* gcs) {
+  B200_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += gridDim.x * wpb) {
@@ -111,6 +113,7 @@ constexpr int CROSS_CHUNKS = 64;
 __global__ void cross_dw_stage1(int B, int D, int L, const float* X, const float* u,
                                 const float* gs, const float* gcs, int rows_per_chunk, float* part,
                                 float* ps, float* pc) {
+  B200_PDL_ENTRY();
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   const int r0 = c * rows_per_chunk, r1 = min(B, r0 + rows_per_chunk);
@@ -139,6 +142,7 @@ __global__ void cross_dw_stage1(int B, int D, int L, const float* X, const float
 // stage 2: gw[l,d] = sum_c part + beta_l * sum_c ps ;  gc[l] = sum_c pc
 __global__ void cross_dw_stage2(int D, int L, const float* cvec, const float* part, const float* ps,
                                 const float* pc, float* gw, float* gc) {
+  B200_PDL_ENTRY();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < L * D) {
     const int l = t / D, d = t - l * D;
@@ -223,6 +227,7 @@ __device__ __forceinline__ int pair_index(int i, int j, int F) {  // i < j
 
 __global__ void __launch_bounds__(128) pnn_ip_fwd_kernel(int B, int F, int K, const float* X,
                                                          float* ip) {
+  B200_PDL_ENTRY();
   extern __shared__ float sv[];  // [F][K+1]
   const int P = F * (F - 1) / 2;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -248,6 +253,7 @@ __global__ void __launch_bounds__(128) pnn_ip_fwd_kernel(int B, int F, int K, co
 __global__ void __launch_bounds__(128) pnn_ip_bwd_kernel(int B, int F, int K, const float* X,
                                                          const float* gip, float* dX,
                                                          bool accumulate) {
+  B200_PDL_ENTRY();
   extern __shared__ float sm[];  // v [F][K+1] then g [P]
   const int P = F * (F - 1) / 2;
   float* sv = sm;

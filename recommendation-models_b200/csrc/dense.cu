@@ -10,6 +10,7 @@ namespace b200rec {
 
 __global__ void splitk_reduce_kernel(const float* ws, int splits, long long MN, float scale,
                                      bool accumulate, float* out) {
+  B200_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < MN;
        i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -35,6 +36,7 @@ int splitk_reduce(const float* ws, int splits, long long MN, float scale, bool a
 // the same for a weight-gradient GEMM that carried the bias gradient as column K of its [N x ldw] partials
 __global__ void splitk_reduce_wb_kernel(const float* ws, int splits, int N, int K, int ldw, float scale,
                                         bool accumulate, float* gw, float* gb) {
+  B200_PDL_ENTRY();
   const long long total = (long long)N * (K + 1), MN = (long long)N * ldw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -76,6 +78,7 @@ int linear_bwd_input(int M, int N, int K, const float* gy, const float* w, const
 
 // column sums of gy[M,N] in two fixed-order stages
 __global__ void colsum_stage1(int M, int N, const float* g, int rows_per_chunk, float* part) {
+  B200_PDL_ENTRY();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   if (n >= N) return;
@@ -95,6 +98,7 @@ __global__ void colsum_stage1(int M, int N, const float* g, int rows_per_chunk, 
 // one warp per column: lanes stride over the chunks, then a fixed xor tree (deterministic)
 __global__ void colsum_stage2(int N, int chunks, const float* part, float scale, bool accumulate,
                               float* out) {
+  B200_PDL_ENTRY();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -142,6 +146,7 @@ int linear_bwd_params(int M, int N, int K, const float* x, const float* gy, floa
 // out[m] (+)= x[m,:] . w + b0      one warp per row
 __global__ void gemv_rows_kernel(int M, int K, const float* x, int ldx, const float* w,
                                  const float* b0, bool accumulate, float* out) {
+  B200_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int m = blockIdx.x * wpb + (threadIdx.x >> 5); m < M; m += gridDim.x * wpb) {
@@ -166,6 +171,7 @@ int gemv_rows(int M, int K, const float* x, int ldx, const float* w, const float
 // g[m,k] = d[m] * w[k] (* (mask[m,k] > 0))
 __global__ void outer_rows_kernel(int M, int K, const float* d, const float* w, const float* mask,
                                   int ldm, float* g, int ldg) {
+  B200_PDL_ENTRY();
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)M * K;
        t += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(t / K), k = (int)(t - (long long)m * K);
@@ -186,6 +192,7 @@ int outer_rows(int M, int K, const float* d, const float* w, const float* mask, 
 // gw[k] = sum_m d[m] x[m,k]   (two fixed-order stages)
 __global__ void wcolsum_stage1(int M, int K, const float* d, const float* x, int ldx,
                                int rows_per_chunk, float* part) {
+  B200_PDL_ENTRY();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   if (k >= K) return;
@@ -216,6 +223,7 @@ int wcolsum(int M, int K, const float* d, const float* x, int ldx, float* gw, De
 __global__ void __launch_bounds__(128) head_bwd_kernel(int M, int K, const float* d, const float* a,
                                                        const float* w, bool mask, float* g,
                                                        int rows_per_chunk, float* part) {
+  B200_PDL_ENTRY();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   const int r0 = c * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
@@ -242,6 +250,7 @@ constexpr int HB_UNR = 8;
 __global__ void __launch_bounds__(128) head_bwd_vec_kernel(int M, int K, const float* d, const float* a,
                                                            const float* w, bool mask, float* g,
                                                            int rows_per_chunk, float* part) {
+  B200_PDL_ENTRY();
   const int k = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int c = blockIdx.y;
   const int r0 = c * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
@@ -311,6 +320,7 @@ int head_layer_bwd(int M, int K, const float* d, const float* a, const float* w,
 
 // deterministic sum of n floats
 __global__ void reduce_stage1(long long n, const float* x, float* part) {
+  B200_PDL_ENTRY();
   __shared__ float sh[8];
   float s = 0.f;
   const long long per = (n + gridDim.x - 1) / gridDim.x;
@@ -326,6 +336,7 @@ __global__ void reduce_stage1(long long n, const float* x, float* part) {
   }
 }
 __global__ void reduce_stage2(int nparts, const float* part, float scale, float* out) {
+  B200_PDL_ENTRY();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < nparts; ++i) t += part[i];
@@ -344,6 +355,7 @@ int reduce_sum(long long n, const float* x, float scale, float* out, DevBuf& scr
 
 // h = relu(a + c0)  (c0 optional scalar)
 __global__ void add_bias_relu_kernel(long long n, const float* a, const float* c0, float* h) {
+  B200_PDL_ENTRY();
   const float c = c0 ? __ldg(c0) : 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
@@ -356,6 +368,7 @@ int add_bias_relu(long long n, const float* a, const float* c0, float* h, cudaSt
   return B200REC_OK;
 }
 __global__ void relu_mask_kernel(long long n, const float* g, const float* h, float* out) {
+  B200_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     out[i] = h[i] > 0.f ? g[i] : 0.f;
@@ -368,6 +381,7 @@ int relu_mask(long long n, const float* g, const float* h, float* out, cudaStrea
 }
 
 __global__ void axpy_kernel(long long n, const float* x, float* y) {
+  B200_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     y[i] += x[i];

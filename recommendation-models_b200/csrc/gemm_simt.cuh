@@ -79,6 +79,7 @@ struct EpAddBiasRelu2 {  // PNN: h = relu(prev + acc + c0)
 template <class AOp, class BOp, class Ep>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(int M, int N, int K, int k_chunk, AOp aop, BOp bop, Ep ep) {
+  B200_PDL_ENTRY();
   __shared__ __align__(16) float As[2][GBK][GBM + GPAD];
   __shared__ __align__(16) float Bs[2][GBK][GBN + GPAD];
   const int tid = threadIdx.x;

@@ -10,6 +10,7 @@
 namespace b200rec {
 
 __global__ void __launch_bounds__(256) head_kernel(Head h, float* part) {
+  B200_PDL_ENTRY();
   __shared__ float sh_l[8], sh_b[8];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   float li = 0.f, gi = 0.f;
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(256) head_kernel(Head h, float* part) {
 
 __global__ void head_finish_kernel(int nparts, int B, const float* part, float* loss, float* dbias,
                                    float* dbias2) {
+  B200_PDL_ENTRY();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double a = 0.0;  // BCECriterion accumulates the two dot products in a double
     float c = 0.f;

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) opt_rows_kernel(int kind, int K, long lon
                                                        float* table, float* wtable,
                                                        float* s1e, float* s2e, float* s1w, float* s2w,
                                                        int* err) {
+  B200_PDL_ENTRY();
   device_corrections(kind, p1, p2, step_dev, c1, c2);
   const int U = *n_unique;
   const int KK = K + 1;  // column K = the first-order weight
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) opt_dense_kernel(int kind, long long n, c
                                                         float p1, float p2, float c1, float c2,
                                                         const int* step_dev, float* w,
                                                         float* s1, float* s2) {
+  B200_PDL_ENTRY();
   device_corrections(kind, p1, p2, step_dev, c1, c2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)

@@ -65,6 +65,7 @@ static unsigned long long p2p_timeout_ns() {
 
 __global__ void p2p_wait_kernel(const int* flags, int phase, int world, int step, const int* step_ptr,
                                 unsigned long long timeout_ns, int* status) {
+  B200_PDL_ENTRY();
   p2p_wait_block(flags, phase, world, step > 0 ? step : *step_ptr - step, timeout_ns, status);
 }
 
@@ -78,6 +79,7 @@ int p2p_wait(const int* flags, int phase, int world, int step, const int* step_p
 // start of a step: advance the device step counter and reset the ids buffer of the NEXT step to the
 // -1 padding (nobody writes that buffer before this rank's next phase-0 signal)
 __global__ void p2p_begin_step_kernel(int* step_ctr, int* ids_next, long long n) {
+  B200_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     ids_next[i] = -1;
@@ -101,6 +103,7 @@ constexpr int EX_UNR = 4;
 // data-parallel replicas need their SUM.  Every rank publishes its vector in symmetric memory and
 // then reads all G vectors, adding them in rank order: all replicas get bit-identical sums.
 __global__ void __launch_bounds__(EX_THREADS) p2p_publish_kernel(long long n, const float* src, float* mine, P2P c) {
+  B200_PDL_ENTRY();
   const long long n4 = n >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(src);
   float4* d4 = reinterpret_cast<float4*>(mine);
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(EX_THREADS) p2p_publish_kernel(long long n, co
 }
 
 __global__ void __launch_bounds__(256) p2p_reduce_kernel(long long n, float* dst, P2P c, PeerF bufs) {
+  B200_PDL_ENTRY();
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(long long n, float* dst
 // stores the result into every peer's `out` buffer (flag 4); then everyone copies `out` back.  NVLink
 // bytes per rank: 2 (G-1)/G n instead of (G-1) n.  n4 = float4 count of the zero-padded vectors.
 __global__ void __launch_bounds__(256) p2p_reduce_scatter_kernel(long long n4, P2P c, PeerF bufs, PeerF outs) {
+  B200_PDL_ENTRY();
   const long long lo = n4 * c.rank / c.world, hi = n4 * (c.rank + 1) / c.world;
   for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi;
        i += (long long)gridDim.x * blockDim.x) {
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_scatter_kernel(long long n4, P
 }
 
 __global__ void __launch_bounds__(256) p2p_copy_back_kernel(long long n, const float* src, float* dst) {
+  B200_PDL_ENTRY();
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x)
@@ -209,6 +215,7 @@ __global__ void __launch_bounds__(256) p2p_rank_place_kernel(long long n, const 
                                                              int cap, const int* feats,
                                                              const int* block_offsets, int* dst,
                                                              int* overflow, P2P c, PeerI ids_in) {
+  B200_PDL_ENTRY();
   __shared__ int run[PCS_MAXW];
   __shared__ int wcnt[8][PCS_MAXW];
   if (n_dev) n = min(n, (long long)*n_dev);
@@ -274,6 +281,7 @@ int p2p_plan(ShardPlanWorkspace& ws, long long n, const int* n_dev, long long pe
 // per-nnz slot = slot of the non-zero's distinct id  (dispatch over distinct ids: dedup before exchange)
 __global__ void p2p_compose_kernel(long long n, const unsigned* perm, const int* seg_idx,
                                    const int* dst_unique, int* dst) {
+  B200_PDL_ENTRY();
   // sorted position p of the batch's ids: non-zero perm[p] belongs to distinct id seg_idx[p] - 1
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (p < n) dst[perm[p]] = dst_unique[seg_idx[p] - 1];
@@ -300,6 +308,7 @@ template <int LPR>
 __global__ void __launch_bounds__(EX_THREADS) p2p_gather_kernel(long long rows, int cap, const int* ids_in,
                                                                 const float* table, const float* wtable, P2P c,
                                                                 PeerF rows_in, PeerF w_in, int* err) {
+  B200_PDL_ENTRY();
   constexpr int K = 4 * LPR;
   const long long n_vec = (long long)c.world * cap * LPR;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -365,6 +374,7 @@ __global__ void __launch_bounds__(EX_THREADS) p2p_push_grads_kernel(long long n,
                                                                     const int* dst, const float* dE,
                                                                     const float* dw, P2P c, PeerF grad_in,
                                                                     PeerF gw_in) {
+  B200_PDL_ENTRY();
   constexpr int K = 4 * LPR;
   if (n_dev) n = min(n, (long long)*n_dev);
   const long long n_vec = n * LPR;

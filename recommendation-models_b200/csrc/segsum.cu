@@ -95,6 +95,7 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* warp_sums, int* t
 
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(int n, const unsigned* __restrict__ keys, int shift,
                                                               int* __restrict__ hist, int tiles, int group, int* counters) {
+  B200_PDL_ENTRY();
   __shared__ int cnt[RS_BINS];
   if (counters && blockIdx.x == 0 && threadIdx.x < 2) counters[threadIdx.x] = 0;   // the hot-id list counters
   // a block takes `group` consecutive tiles: one tile per block when the sort is on the critical path (FM / LR),
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(int n, const unsign
   }
 }
 
-__global__ void __launch_bounds__(256) rs_scan_kernel(int* __restrict__ a, int total) {   // one block: exclusive scan in place
+__global__ void __launch_bounds__(256) rs_scan_kernel(int* __restrict__ a, int total) {
+  B200_PDL_ENTRY();   // one block: exclusive scan in place
   __shared__ int warp_sums[8];
   const int per = (total + 255) / 256;
   const int b0 = threadIdx.x * per, b1 = min(total, b0 + per);
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(256) rs_scan_kernel(int* __restrict__ a, int t
 
 // one block per digit: hist[d][0 .. tiles) becomes its own exclusive prefix, totals[d] the digit's count
 __global__ void __launch_bounds__(RS_THREADS) rs_rowscan_kernel(int* __restrict__ hist, int tiles, int* __restrict__ totals) {
+  B200_PDL_ENTRY();
   __shared__ int wsum[RS_THREADS / 32];
   __shared__ int carry_s;
   int* row = hist + (size_t)blockIdx.x * tiles;
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int n, const uns
                                                                  const int* __restrict__ totals,
                                                                  unsigned* __restrict__ keys_out,
                                                                  unsigned* __restrict__ vals_out) {
+  B200_PDL_ENTRY();
   __shared__ int base[RS_BINS];                        // next output slot of every digit for this tile
   __shared__ int wcnt[RS_THREADS / 32][RS_BINS];       // per-warp digit counts of the current round
   __shared__ int wsum[RS_THREADS / 32];
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int n, const uns
 //   seg_write : seg_idx[i] = 1-based segment number of sorted position i; seg_start / unique at the heads
 constexpr int SEG_TILE = 1024, SEG_THREADS = 256, SEG_PER = SEG_TILE / SEG_THREADS;   // a thread owns 4 consecutive positions
 __global__ void __launch_bounds__(SEG_THREADS) seg_count_kernel(int n, const unsigned* __restrict__ keys, int* __restrict__ tile_heads) {
+  B200_PDL_ENTRY();
   __shared__ int warp_sums[8];
   const int i0 = blockIdx.x * SEG_TILE + threadIdx.x * SEG_PER;
   int h = 0;
@@ -262,6 +267,7 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_write_kernel(int n, const uns
                                                                 const int* __restrict__ tile_off, int* __restrict__ seg_idx,
                                                                 int* __restrict__ seg_start, int* __restrict__ unique,
                                                                 int* __restrict__ n_unique, bool drop_pad) {
+  B200_PDL_ENTRY();
   __shared__ int warp_sums[8];
   const int i0 = blockIdx.x * SEG_TILE + threadIdx.x * SEG_PER;
   unsigned k[SEG_PER];
@@ -298,6 +304,7 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_write_kernel(int n, const uns
 // inside a list is whatever the atomics give: it only decides which warp / block sums which segment.
 __global__ void seg_long_kernel(const int* n_unique, const int* seg_start, int* long_list, int* big_list,
                                 int* counts, int big_t) {
+  B200_PDL_ENTRY();
   const int U = *n_unique;
   for (long long seg = blockIdx.x * (long long)blockDim.x + threadIdx.x; seg < U;
        seg += (long long)gridDim.x * blockDim.x) {
@@ -359,6 +366,7 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
 
 // inv[i] = index of the distinct id of non-zero i (valid after segsum_sort on the same workspace)
 __global__ void seg_inverse_kernel(long long n, const unsigned* perm, const int* seg_idx, int* inv) {
+  B200_PDL_ENTRY();
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (p < n) inv[perm[p]] = seg_idx[p] - 1;
 }
@@ -609,6 +617,7 @@ __global__ void __launch_bounds__(256, 4) segsum_kernel(int b_blocks, int l_bloc
                                                      const RowSrc src, const RowSink out,
                                                      const int* long_list, const int* big_list,
                                                      const int* counts) {
+  B200_PDL_ENTRY();
   constexpr int SK = 4 * LPR <= BIG_MAX_K ? 4 * LPR : 1;   // wider rows never reach the big role (seg_long_kernel)
   __shared__ __align__(16) float rows_s[BIG_CH * SK];
   __shared__ float w_s[BIG_CH];
@@ -628,6 +637,7 @@ __global__ void __launch_bounds__(256, 4) segsum_kernel(int b_blocks, int l_bloc
 __global__ void segsum_generic_kernel(const int* n_unique, const int* seg_start,
                                       const unsigned* perm, int K, const float* dE,
                                       const float* dw, float* G, float* gw) {
+  B200_PDL_ENTRY();
   const int U = *n_unique;
   const int KK = K + 1;  // column K = the first-order weight gradient
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)U * KK;
@@ -710,6 +720,7 @@ int segsum_reduce(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
 // is third-party, parity unpinned).  Touched rows only.
 __global__ void apply_sgd_kernel(int K, long long rows, const int* n_unique, const int* unique, const float* G,
                                  const float* gw, float lr, float* table, float* wtable, int* err) {
+  B200_PDL_ENTRY();
   const int U = *n_unique;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)U * K;
        t += (long long)gridDim.x * blockDim.x) {

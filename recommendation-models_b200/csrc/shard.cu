@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) shard_hist_kernel(long long n, const int*
                                                          long long period, const int* feats,
                                                          int* block_counts, int* send_ids,
                                                          long long n_send) {
+  B200_PDL_ENTRY();
   __shared__ int cnt[CS_MAXW];
   if (n_dev) n = min(n, (long long)*n_dev);
   if (threadIdx.x < CS_MAXW) cnt[threadIdx.x] = 0;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256) shard_hist_kernel(long long n, const int*
 // The counts are staged in shared memory in chunks (coalesced) so the serial scan runs at smem latency.
 __global__ void __launch_bounds__(256) shard_scan_kernel(int n_blocks, int world, int* block_counts,
                                                          int* offsets) {
+  B200_PDL_ENTRY();
   constexpr int CHUNK = 4096;            // ints of block_counts per pass
   __shared__ int buf[CHUNK];
   __shared__ int tot[CS_MAXW + 1];
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(256) shard_rank_kernel(long long n, const int*
                                                          long long period, const int* feats,
                                                          const int* block_offsets, const int* offsets,
                                                          unsigned* owner_sorted, unsigned* perm) {
+  B200_PDL_ENTRY();
   if (n_dev) n = min(n, (long long)*n_dev);
   __shared__ int run[CS_MAXW];            // items of each owner already ranked in this block
   __shared__ int wcnt[8][CS_MAXW];        // per-warp counts of the current pass
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(256) shard_rank_kernel(long long n, const int*
 __global__ void shard_place_kernel(long long n, int world, long long period, int cap, const int* feats,
                                    const unsigned* owner_sorted, const unsigned* perm,
                                    const int* offsets, int* send_ids, int* dst, int* overflow) {
+  B200_PDL_ENTRY();
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (p >= n) return;
   const int o = (int)owner_sorted[p];

@@ -21,6 +21,7 @@ namespace b200rec {
 // ------------------------------------------------------------------------------------------------
 template <int LPR, bool GATHER>
 __global__ void __launch_bounds__(256) fm_fwd_kernel(SparseFwd a) {
+  B200_PDL_ENTRY();
   constexpr int RPW = 32 / LPR;  // rows per warp-wide load
   constexpr int UNR = 5;         // independent row loads in flight per lane (39 fields = 5 x 8)
   const int K = 4 * LPR;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) fm_fwd_kernel(SparseFwd a) {
 // Generic K (not 4*2^n): one warp per sample, lane strides over k.  Same outputs.
 template <bool GATHER>
 __global__ void __launch_bounds__(256) fm_fwd_generic_kernel(SparseFwd a) {
+  B200_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int F = a.F, K = a.K;
@@ -191,6 +193,7 @@ int sparse_fwd(const SparseFwd& a, cudaStream_t st) {
 // Elementwise over [B*F, K]; may run in place over X.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) emb_grad_kernel(SparseBwd a, long long n_vec, int kv) {
+  B200_PDL_ENTRY();
   // one thread per float4 of the [B*F, K] grid (kv = K/4 vectors per row)
   const int F = a.F, K = a.K;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_vec;
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(256) emb_grad_kernel(SparseBwd a, long long n_
 }
 
 __global__ void __launch_bounds__(256) emb_grad_generic_kernel(SparseBwd a, long long n) {
+  B200_PDL_ENTRY();
   const int F = a.F, K = a.K;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
        t += (long long)gridDim.x * blockDim.x) {
@@ -235,6 +239,7 @@ __global__ void __launch_bounds__(256) emb_grad_generic_kernel(SparseBwd a, long
 
 __global__ void dw_only_kernel(long long n, int F, const int* index, const float* dlogit,
                                const int* out_slot, float* dw) {
+  B200_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const long long o = out_slot ? (long long)out_slot[i] : i;
@@ -274,6 +279,7 @@ __global__ void __launch_bounds__(256) lookup_kernel(long long rows, int K, long
                                                      const int* feats, const float* table,
                                                      const float* wtable, float* emb_out,
                                                      float* w_out, int* err) {
+  B200_PDL_ENTRY();
   const int kv = K / 4;  // caller guarantees K % 4 == 0 on this path
   const long long n_vec = n * kv;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_vec;
@@ -299,6 +305,7 @@ template <bool PAD>
 __global__ void lookup_generic_kernel(long long rows, int K, long long n, const int* feats,
                                       const float* table, const float* wtable, float* emb_out,
                                       float* w_out, int* err) {
+  B200_PDL_ENTRY();
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n * K;
        t += (long long)gridDim.x * blockDim.x) {
     const long long i = t / K;
@@ -354,6 +361,7 @@ int lookup_rows_padded(long long rows, int K, long long n, const int* feats, con
 // index falls back to a full in-order scan of the n inputs per output row (correct, slow, rare).
 // ------------------------------------------------------------------------------------------------
 __global__ void index_check_kernel(long long n, int B, const int* index, int* flags, int* err) {
+  B200_PDL_ENTRY();
   // flags[0] |= 1 when index is not non-decreasing
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -365,6 +373,7 @@ __global__ void index_check_kernel(long long n, int B, const int* index, int* fl
 
 __global__ void scatter_fwd_kernel(int B, int n_out, long long n, const float* in,
                                    const int* index, float* out, const int* flags) {
+  B200_PDL_ENTRY();
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)B * n_out) return;
   const int b = (int)(t / n_out), c = (int)(t % n_out);
@@ -385,6 +394,7 @@ __global__ void scatter_fwd_kernel(int B, int n_out, long long n, const float* i
 
 __global__ void scatter_bwd_kernel(int B, int n_out, long long n, const int* index,
                                    const float* gout, float* gin, int* err) {
+  B200_PDL_ENTRY();
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n * n_out;
        t += (long long)gridDim.x * blockDim.x) {
     const long long i = t / n_out;
@@ -426,6 +436,7 @@ int scatter_bwd(int B, int n_out, long long n, const int* index, const float* go
 // ------------------------------------------------------------------------------------------------
 __global__ void pair_gather_fwd_kernel(int B, int F, int P, int K, const float* in,
                                        const int* rows, const int* cols, float* ro, float* co) {
+  B200_PDL_ENTRY();
   const long long n = (long long)B * P * K;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
        t += (long long)gridDim.x * blockDim.x) {
@@ -442,6 +453,7 @@ __global__ void pair_gather_fwd_kernel(int B, int F, int P, int K, const float* 
 __global__ void pair_gather_bwd_kernel(int B, int F, int P, int K, const int* rows,
                                        const int* cols, const float* gr, const float* gc,
                                        float* gin) {
+  B200_PDL_ENTRY();
   const long long n = (long long)B * F * K;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
        t += (long long)gridDim.x * blockDim.x) {
@@ -459,6 +471,7 @@ __global__ void pair_gather_bwd_kernel(int B, int F, int P, int K, const int* ro
 }
 
 __global__ void dot2_fwd_kernel(long long n, int K, const float* a, const float* b, float* out) {
+  B200_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float acc = 0.f;
@@ -470,6 +483,7 @@ __global__ void dot2_fwd_kernel(long long n, int K, const float* a, const float*
 
 __global__ void dot2_bwd_kernel(long long n, int K, const float* a, const float* b,
                                 const float* go, float* ga, float* gb) {
+  B200_PDL_ENTRY();
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n * K;
        t += (long long)gridDim.x * blockDim.x) {
     const float g = go[t / K];

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256) table_init_kernel(float* table, float* wt
                                                          long long rows, int K, uint64_t seed,
                                                          float lo, float span, long long row_offset,
                                                          long long row_stride) {
+  B200_PDL_ENTRY();
   const long long n = rows * K;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
        t += (long long)gridDim.x * blockDim.x) {
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256) table_init_sharded_kernel(float* table, f
                                                                  long long rows, int K, uint64_t seed,
                                                                  float lo, float span, int rank,
                                                                  int world, long long period) {
+  B200_PDL_ENTRY();
   const long long n = rows * K;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
        t += (long long)gridDim.x * blockDim.x) {

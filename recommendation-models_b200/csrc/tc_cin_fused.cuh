@@ -36,6 +36,7 @@ __host__ __device__ inline int dz_smem_bytes() {
 // column = c - 32 kb; rows with i >= F or j >= H and columns with c >= C are zero
 __global__ void __launch_bounds__(THREADS) dz_pack_kernel(int F, int H, int C, const float* __restrict__ W,
                                                           char* blob) {
+  B200_PDL_ENTRY();
   const int tile = blockIdx.x, kb = blockIdx.y, nkb = gridDim.y;
   char* hi = blob + ((size_t)tile * nkb + kb) * (size_t)DZ_B_STAGE;
   char* lo = hi + DZ_BN * 128;
@@ -65,6 +66,7 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
   // The epilogue of group g - 1 (15 pieces of 16 columns) runs on the producer warps right after they have
   // put the first two A stages of group g in flight; the MMA warp re-uses accumulator t as soon as its tile
   // has been read (accempty[t]).
+  griddep_launch();   // (programmatic dependent launch: see gemm_ws_kernel)
   extern __shared__ char smem_raw[];
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   char* bbase = base + TCB_A_BYTES;
@@ -100,6 +102,7 @@ cin_dz_kernel(int R, int F, int H, int C, const float* __restrict__ x0, const fl
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();   // first global access below
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {

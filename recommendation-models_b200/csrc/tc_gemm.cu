@@ -39,6 +39,8 @@ static int launch_ws(const char* name, dim3 grid, int smem, int M, int N, int bn
                      Sched sched, AP ap, BP bp, const char* blob, int blob_nkb, int blob_kb_per_split, Ep ep,
                      int passes, cudaStream_t st) {
   const int kc = passes == 3 ? (kc_precise() | (kc_short() << 8)) : 0;
+  // programmatic dependent launch for single-wave grids (the next kernel's prologue under this one's tail)
+  PdlHint pdl_hint((long long)grid.x * grid.y * grid.z <= 148 || pdl_enabled() == 3);
   const int smem_max = ws_smem_bytes(PACKED, PACKED ? 208 : 256);
   if (passes == 3) {
     auto k = gemm_ws_kernel<AP, BP, Sched, Ep, 3, PACKED>;

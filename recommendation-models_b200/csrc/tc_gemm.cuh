@@ -930,6 +930,7 @@ __host__ __device__ inline int tcb_smem_bytes(int bn) {
 
 template <class BP, class Sched>
 __global__ void __launch_bounds__(THREADS) pack_b_kernel(int bn, int n_stride, Sched sched, BP bp, char* blob) {
+  B200_PDL_ENTRY();
   const int nkb = sched.nkb();
   const int tile = blockIdx.x;
   bp.s = sched;
@@ -949,6 +950,7 @@ struct PackJob { const float* w; int N, K, bn, nkb, n_tiles; long long off; };
 struct PackJobs { PackJob j[8]; };
 template <bool TRANSPOSED>
 __global__ void __launch_bounds__(THREADS) pack_linear_multi_kernel(PackJobs jobs, char* blob) {
+  B200_PDL_ENTRY();
   const PackJob jb = jobs.j[blockIdx.z];
   const int tile = blockIdx.x;
   if (tile >= jb.n_tiles) return;
@@ -1019,6 +1021,7 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
                const char* __restrict__ bblob, int blob_nkb, int blob_kb_per_split, Ep ep) {
   // packed B with split-K: the blob holds the stages of the WHOLE contraction ([n_tile][blob_nkb]);
   // split z starts at stage z * blob_kb_per_split
+  griddep_launch();   // the next kernel of the stream may be scheduled (it waits for this one to complete)
   extern __shared__ char smem_raw[];
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int NB = ws_nb(PACKED, bn);
@@ -1073,6 +1076,10 @@ gemm_ws_kernel(int M, int N, int bn, int n_stride, int n_valid, int kc, Sched sc
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // Programmatic dependent launch: everything above touched only shared / tensor memory, so it ran while the
+  // previous kernel of the stream was still finishing; its results are needed (and this kernel's writes allowed)
+  // from here on.
+  griddep_wait();
 
   if (warp == 0) {
     // ===================================== MMA issuer =====================================
