@@ -115,6 +115,7 @@ static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   const int mode = pdl_enabled();
+  // (also marking every grid of <= 64 blocks measured within noise, every grid of <= 1100 blocks +3 % slower)
   cfg.numAttrs = (mode == 1 || (mode >= 2 && tl_pdl_hint)) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
