@@ -11,14 +11,20 @@
 using namespace b200rec::tc;
 
 __global__ void __launch_bounds__(1024, 1) noise_kernel(int bn, int reps, int mode, int skip_sched0, const float* g, long long* out,
-                                                        unsigned* sink) {
+                                                        unsigned* sink, int commit_each = 0) {
   extern __shared__ char smem_raw[];
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
+  __shared__ uint64_t ring[6];   // commit_each: one tcgen05.commit per K-block on a ring of barriers nobody waits for
   __shared__ uint32_t tmem_slot;
   __shared__ volatile int stop;
   for (int i = threadIdx.x; i < (16384 + 32768) * 2 / 4; i += blockDim.x) reinterpret_cast<float*>(base)[i] = 0.001f * (i & 255);
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); stop = 0; }
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    for (int i = 0; i < 6; ++i) mbar_init(smem_u32(&ring[i]), 1);
+    fence_mbar_init();
+    stop = 0;
+  }
   if (threadIdx.x < 32) tmem_alloc(smem_u32(&tmem_slot), 512);
   fence_proxy_async();
   tc_fence_before();
@@ -41,6 +47,7 @@ __global__ void __launch_bounds__(1024, 1) noise_kernel(int bn, int reps, int mo
         const uint64_t adv = (uint64_t)(ks * 32 >> 4);
         mma_bf16(tmem, dac + adv, dbc + adv, id_b, 1u);
       }
+      if (commit_each) mma_commit(smem_u32(&ring[r % 6]));
     }
     mma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
@@ -98,5 +105,13 @@ int main() {
                  skip ? "(not on scheduler 0)" : "(all schedulers)", names[mode], (double)h[0] / reps, h[1],
                  e == cudaSuccess ? "" : cudaGetErrorString(e));
         }
+  // does a tcgen05.commit per K-block (what the pipeline needs to free its ring slots) cost tensor time?
+  for (int ce = 0; ce < 2; ++ce) {
+    cudaMemset(d, 0, 16);
+    noise_kernel<<<148, 32 * 9, smem>>>(bn, reps, 0, 0, g, d, sink, ce);
+    long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("commit per K-block: %d   %7.1f cycles per K-block (8 MMAs) %s\n", ce, (double)h[0] / reps, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  }
   return 0;
 }
