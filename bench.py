@@ -386,7 +386,10 @@ def measure_1gpu(args, name, pkg, torch, local):
         roofline = dict(kernel=dom["phase"], bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"],
                         unit=dom["unit"], frac=dom["frac"], traffic=traffic, peak_source=pk["src"],
                         launches_per_step=dom["launches_per_step"], ms_per_step=dom["ms_per_step"],
-                        event_overhead_us_per_launch=round(ev_us, 2))
+                        event_overhead_us_per_launch=round(ev_us, 2),
+                        note="kernel durations from a separate pass with a CUDA-event pair around every launch on one stream: "
+                             "no dependent-launch overlap, no auxiliary-stream overlap -- the phases sum to more than the "
+                             "graph-replayed step (ms_per_step of the line), which has both")
 
     out = {
         "metric": "train samples/sec (fwd+bwd)", "value": round(B * Ksteps / (ms_total * 1e-3), 1),
