@@ -100,3 +100,21 @@ def test_optimizer_oracle_textbook_forms():
     w1 = refport.optimizer_update("momentum", w, g, st, 0.1)
     w2 = refport.optimizer_update("momentum", w1, g, st, 0.1)
     assert np.allclose(w1 - w2, 0.1 * (0.9 * g + g))
+
+
+def test_bench_helpers_on_cpu():
+    """bench.py's pure-host helpers: the gather pattern ceiling is read from the committed micro-benchmark output,
+    and the algorithmic work table names the phases the per-kernel pass tags."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = bench.gather_ceiling_us(8192 * 39)
+    assert c is not None and 5.0 < c < 100.0          # microseconds for one batch of random 64-B rows
+    assert bench.gather_ceiling_us(12345) is None      # only sizes the micro-benchmark measured
+    w = bench.algorithmic_work("deepfm", [400, 400, 400], [], 0, 8192, 150000)
+    for phase in ("gather_fm_fwd", "dense_fwd", "dense_bwd", "emb_grad", "scatter_add"):
+        assert phase in w and w[phase][1] > 0
+    assert w["gather_fm_fwd"][0] == "hbm" and w["dense_bwd"][0] == "tensor"
