@@ -51,7 +51,7 @@ int SegSumWorkspace::reserve(long long n) {
   B200_TRY(keys_a.reserve(ni * 4));
   // radix-sort histograms [256 digits][tiles] (+ the per-tile segment-head counts of the segment scan)
   const size_t tiles = (ni + RS_TILE - 1) / RS_TILE;
-  B200_TRY(cub_tmp.reserve((RS_BINS * tiles + RS_BINS + 2 * tiles + 64) * 4));   // SEG_TILE = RS_TILE / 2
+  B200_TRY(cub_tmp.reserve((2 * RS_BINS * tiles + 2 * RS_BINS + 2 * tiles + 64) * 4));   // up to 512 bins; SEG_TILE = RS_TILE / 2
   cap_n = n;
   return B200REC_OK;
 }
@@ -93,23 +93,27 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* warp_sums, int* t
   return wbase + inc - v;
 }
 
+// DB = bits per digit: 8, or 9 where that saves a whole pass (17-18 and 25-27 key bits: the sharded step's 100 M-row ids)
+template <int DB>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(int n, const unsigned* __restrict__ keys, int shift,
                                                               int* __restrict__ hist, int tiles, int group, int* counters) {
   B200_PDL_ENTRY();
-  __shared__ int cnt[RS_BINS];
+  constexpr int BINS = 1 << DB, PER = BINS / RS_THREADS;   // PER consecutive digits per thread
+  __shared__ int cnt[BINS];
   if (counters && blockIdx.x == 0 && threadIdx.x < 2) counters[threadIdx.x] = 0;   // the hot-id list counters
   // a block takes `group` consecutive tiles: one tile per block when the sort is on the critical path (FM / LR),
   // ~20 fat blocks when it runs beside the dense math, where the GEMMs leave 20 of the 148 SMs idle and anything
   // spread over all SMs takes issue slots from their producer warps
   for (int tile = blockIdx.x * group; tile < min(tiles, (blockIdx.x + 1) * group); ++tile) {
-  cnt[threadIdx.x] = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) cnt[threadIdx.x * PER + j] = 0;
   __syncthreads();
   const int base = tile * RS_TILE;
   unsigned d[RS_TILE / RS_THREADS];
 #pragma unroll
   for (int j = 0; j < RS_TILE / RS_THREADS; ++j) {      // all loads of the tile in flight
     const int i = base + j * RS_THREADS + threadIdx.x;
-    d[j] = i < n ? ((keys[i] >> shift) & (RS_BINS - 1)) : 0xffffu;
+    d[j] = i < n ? ((keys[i] >> shift) & (BINS - 1)) : 0xffffu;
   }
   const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -119,7 +123,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(int n, const unsign
     if (d[j] != 0xffffu && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&cnt[d[j]], __popc(peers));
   }
   __syncthreads();
-  hist[threadIdx.x * tiles + tile] = cnt[threadIdx.x];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) hist[(threadIdx.x * PER + j) * tiles + tile] = cnt[threadIdx.x * PER + j];
   __syncthreads();
   }
 }
@@ -171,6 +176,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_rowscan_kernel(int* __restrict_
   if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
 }
 
+template <int DB>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int n, const unsigned* __restrict__ keys_in,
                                                                  const unsigned* __restrict__ vals_in, int shift,
                                                                  const int* __restrict__ hist, int tiles, int group,
@@ -178,8 +184,9 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int n, const uns
                                                                  unsigned* __restrict__ keys_out,
                                                                  unsigned* __restrict__ vals_out) {
   B200_PDL_ENTRY();
-  __shared__ int base[RS_BINS];                        // next output slot of every digit for this tile
-  __shared__ int wcnt[RS_THREADS / 32][RS_BINS];       // per-warp digit counts of the current round
+  constexpr int BINS = 1 << DB, PER = BINS / RS_THREADS;   // thread t owns the PER consecutive digits t * PER ...
+  __shared__ int base[BINS];                           // next output slot of every digit for this tile
+  __shared__ int wcnt[RS_THREADS / 32][BINS];          // per-warp digit counts of the current round
   __shared__ int wsum[RS_THREADS / 32];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   for (int tile = blockIdx.x * group; tile < min(tiles, (blockIdx.x + 1) * group); ++tile) {
@@ -192,8 +199,10 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int n, const uns
     keyr[j] = i < n ? keys_in[i] : 0u;
     valr[j] = (i < n && vals_in) ? vals_in[i] : (unsigned)i;
   }
-  {  // first slot of digit t for this tile = (digits before t) + (digit t in the tiles before this one)
-    const int tot = totals[t];
+  {  // first slot of a digit for this tile = (all smaller digits) + (the same digit in the tiles before this one)
+    int totj[PER], tot = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { totj[j] = totals[t * PER + j]; tot += totj[j]; }
     int inc = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -205,7 +214,12 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int n, const uns
     int wbase = 0;
 #pragma unroll
     for (int q = 0; q < RS_THREADS / 32; ++q) wbase += q < w ? wsum[q] : 0;
-    base[t] = wbase + inc - tot + hist[t * tiles + tile];
+    int run = wbase + inc - tot;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      base[t * PER + j] = run + hist[(t * PER + j) * tiles + tile];
+      run += totj[j];
+    }
   }
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
@@ -213,20 +227,26 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int n, const uns
     if (tile0 + j * RS_THREADS >= n) break;            // block-uniform
     const bool valid = i < n;
     const unsigned key = keyr[j], val = valr[j];
-    const unsigned d = valid ? ((key >> shift) & (RS_BINS - 1)) : 0xffffu;
+    const unsigned d = valid ? ((key >> shift) & (BINS - 1)) : 0xffffu;
 #pragma unroll
-    for (int q = 0; q < RS_THREADS / 32; ++q) wcnt[q][t] = 0;
+    for (int q = 0; q < RS_THREADS / 32; ++q)
+#pragma unroll
+      for (int jj = 0; jj < PER; ++jj) wcnt[q][t * PER + jj] = 0;
     __syncthreads();
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const int rank = __popc(peers & ((1u << lane) - 1u));
     if (valid && rank == 0) wcnt[w][d] = __popc(peers);
     __syncthreads();
-    int acc = 0;                                       // thread t scans digit t over the warps
+    int acc[PER];                                      // thread t scans its digits over the warps
 #pragma unroll
-    for (int q = 0; q < RS_THREADS / 32; ++q) {
-      const int c = wcnt[q][t];
-      wcnt[q][t] = acc;
-      acc += c;
+    for (int jj = 0; jj < PER; ++jj) {
+      acc[jj] = 0;
+#pragma unroll
+      for (int q = 0; q < RS_THREADS / 32; ++q) {
+        const int c = wcnt[q][t * PER + jj];
+        wcnt[q][t * PER + jj] = acc[jj];
+        acc[jj] += c;
+      }
     }
     __syncthreads();
     if (valid) {
@@ -235,7 +255,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(int n, const uns
       vals_out[pos] = val;
     }
     __syncthreads();
-    base[t] += acc;
+#pragma unroll
+    for (int jj = 0; jj < PER; ++jj) base[t * PER + jj] += acc[jj];
   }
   __syncthreads();
   }
@@ -326,9 +347,10 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
   unsigned* perm = ws.vals_b.as<unsigned>();          // the sorted pairs always end in (keys_b, vals_b)
   unsigned* keys_sorted = ws.keys_b.as<unsigned>();
   int* hist = ws.cub_tmp.as<int>();
-  int* totals = hist + (size_t)RS_BINS * cdiv(n, RS_TILE);
   const int bits = a.key_bits < 1 ? 1 : (a.key_bits > 32 ? 32 : a.key_bits);
-  const int passes = (bits + 7) / 8;
+  const int db = (bits + 8) / 9 < (bits + 7) / 8 ? 9 : 8;   // 9-bit digits where they save a pass
+  const int passes = (bits + db - 1) / db, bins = 1 << db;
+  int* totals = hist + (size_t)bins * cdiv(n, RS_TILE);
   const int tiles = cdiv(n, RS_TILE);
   static const int bg_group = [] { const char* e = std::getenv("B200REC_SORT_GROUP"); return e && *e ? atoi(e) : 1; }();
   const int group = a.background && bg_group > 1 ? bg_group : 1;   // (measured: 1 is best; ~20 fat blocks make the sort the critical path)
@@ -339,16 +361,22 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
     const bool to_b = ((passes - 1 - p) & 1) == 0;    // ping-pong so that the last pass writes the b buffers
     unsigned* kout = to_b ? ws.keys_b.as<unsigned>() : ws.keys_a.as<unsigned>();
     unsigned* vout = to_b ? ws.vals_b.as<unsigned>() : ws.vals_a.as<unsigned>();
-    B200_LAUNCH(rs_hist_kernel, blocks, RS_THREADS, 0, st, n, kin, 8 * p, hist, tiles, group, p == 0 ? counters : nullptr);
-    B200_LAUNCH(rs_rowscan_kernel, RS_BINS, RS_THREADS, 0, st, hist, tiles, totals);
-    B200_LAUNCH(rs_scatter_kernel, blocks, RS_THREADS, 0, st, n, kin, vin, 8 * p, hist, tiles, group, totals, kout, vout);
+    if (db == 9) {
+      B200_LAUNCH(rs_hist_kernel<9>, blocks, RS_THREADS, 0, st, n, kin, db * p, hist, tiles, group, p == 0 ? counters : nullptr);
+      B200_LAUNCH(rs_rowscan_kernel, bins, RS_THREADS, 0, st, hist, tiles, totals);
+      B200_LAUNCH(rs_scatter_kernel<9>, blocks, RS_THREADS, 0, st, n, kin, vin, db * p, hist, tiles, group, totals, kout, vout);
+    } else {
+      B200_LAUNCH(rs_hist_kernel<8>, blocks, RS_THREADS, 0, st, n, kin, db * p, hist, tiles, group, p == 0 ? counters : nullptr);
+      B200_LAUNCH(rs_rowscan_kernel, bins, RS_THREADS, 0, st, hist, tiles, totals);
+      B200_LAUNCH(rs_scatter_kernel<8>, blocks, RS_THREADS, 0, st, n, kin, vin, db * p, hist, tiles, group, totals, kout, vout);
+    }
     kin = kout;
     vin = vout;
   }
   // segment table.  vals_a is free again (the last pass read it at most): it becomes seg_idx.
   int* seg_idx = ws.vals_a.as<int>();
   const int stiles = cdiv(n, SEG_TILE);
-  int* tile_heads = totals + RS_BINS;
+  int* tile_heads = totals + bins;
   B200_LAUNCH(seg_count_kernel, stiles, SEG_THREADS, 0, st, n, keys_sorted, tile_heads);
   B200_LAUNCH(rs_scan_kernel, 1, 256, 0, st, tile_heads, stiles);
   B200_LAUNCH(seg_write_kernel, stiles, SEG_THREADS, 0, st, n, keys_sorted, tile_heads, seg_idx, ws.seg_start.as<int>(),

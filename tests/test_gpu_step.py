@@ -144,3 +144,41 @@ def test_fused_scatter_is_bit_identical(gpu_pkg, name):
         assert np.array_equal(r["unique"], res[0]["unique"])
         assert np.array_equal(r["emb_grad"], res[0]["emb_grad"])
         assert np.array_equal(r["w_grad"], res[0]["w_grad"])
+
+
+@pytest.mark.parametrize("rows", [200_000, 5_000_000, 40_000_000, 100_000_000])
+def test_resident_step_key_widths(gpu_pkg, rows):
+    """The sort half picks its digit width from the table size: 8-bit digits, or 9-bit ones where they save a pass
+    (17-18 and 25-27 key bits -- the 100 M-row tables of the sharded config).  Ids spread over the whole table so
+    that every digit varies; distinct ids exact, summed gradients against the oracle."""
+    synth = gpu_pkg.synth
+    F, K, B = 39, 4, 512
+    model = gpu_pkg.make_model("fm", F, K, (), (), 0)
+    table = gpu_pkg.EmbeddingTable(rows, K)
+    table.init_uniform(42, -0.3, 0.3)
+    rng = np.random.default_rng(rows % 9973)
+    feats = rng.integers(0, rows, B * F).astype(np.int32)
+    feats[::7] = feats[0]                       # one hot id, and ...
+    feats[1::11] = rows - 1                     # ... the largest key
+    targets = (rng.random(B) < 0.5).astype(np.float32)
+    bias = np.array([0.05], np.float32)
+    ps = gpu_pkg.ParRecModel(model, table)
+    ps.setParams(bias, np.zeros(0, np.float32))
+    ps.optimize(feats, targets)
+    res = ps.stepResults()
+    emb = synth.table_rows(42, feats, K, -0.3, 0.3).reshape(-1)
+    w = synth.wtable_rows(42, feats, -0.3, 0.3)
+    index = np.repeat(np.arange(B, dtype=np.int32), F)
+    o = refport.Model("fm", F, K, (), (), 0)
+    o64 = refport.Model("fm", F, K, (), (), 0, np.float64)
+    oe, ow, ob = emb.copy(), w.copy(), bias.copy()
+    o.backward(B, index, ow, ob, oe, None, targets)
+    de, dw, db = emb.astype(np.float64), w.astype(np.float64), bias.astype(np.float64)
+    o64.backward(B, index, dw, db, de, None, targets)
+    ids, gw = refport.make_weights_grad(ow, feats)
+    _, gw64 = refport.make_weights_grad(dw, feats)
+    assert np.array_equal(res["unique"], ids)
+    assert_close(res["w_grad"], gw, what="w_grad", ref64=gw64)
+    _, G = refport.make_embedding_grad(oe, feats, K)
+    _, G64 = refport.make_embedding_grad(de, feats, K)
+    assert_close(res["emb_grad"], G, what="emb_grad", ref64=G64)
