@@ -93,7 +93,7 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* warp_sums, int* t
   return wbase + inc - v;
 }
 
-// DB = bits per digit: 8, or 9 where that saves a whole pass (17-18 and 25-27 key bits: the sharded step's 100 M-row ids)
+// DB = bits per digit: 8 (default), or 9 (B200REC_SORT_DB9=1) where that saves a whole pass -- see segsum_sort
 template <int DB>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(int n, const unsigned* __restrict__ keys, int shift,
                                                               int* __restrict__ hist, int tiles, int group, int* counters) {
@@ -348,7 +348,12 @@ int segsum_sort(SegSumWorkspace& ws, const SegSum& a, cudaStream_t st) {
   unsigned* keys_sorted = ws.keys_b.as<unsigned>();
   int* hist = ws.cub_tmp.as<int>();
   const int bits = a.key_bits < 1 ? 1 : (a.key_bits > 32 ? 32 : a.key_bits);
-  const int db = (bits + 8) / 9 < (bits + 7) / 8 ? 9 : 8;   // 9-bit digits where they save a pass
+  // 9-bit digits would save a whole pass at 17-18 and 25-27 key bits (the 100 M-row ids of the sharded step: 3 passes
+  // instead of 4) and do cut the sort's kernel time by 6-10 % -- but the 2-GPU step measured 4 % SLOWER with them
+  // (0.477 vs 0.458 ms, same box: the 512-bin scatter blocks hold twice the shared memory and run longer chains
+  // beside the GEMMs).  Off unless B200REC_SORT_DB9=1.
+  static const bool db9 = [] { const char* e = std::getenv("B200REC_SORT_DB9"); return e && e[0] == '1'; }();
+  const int db = db9 && (bits + 8) / 9 < (bits + 7) / 8 ? 9 : 8;
   const int passes = (bits + db - 1) / db, bins = 1 << db;
   int* totals = hist + (size_t)bins * cdiv(n, RS_TILE);
   const int tiles = cdiv(n, RS_TILE);

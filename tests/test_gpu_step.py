@@ -148,9 +148,9 @@ def test_fused_scatter_is_bit_identical(gpu_pkg, name):
 
 @pytest.mark.parametrize("rows", [200_000, 5_000_000, 40_000_000, 100_000_000])
 def test_resident_step_key_widths(gpu_pkg, rows):
-    """The sort half picks its digit width from the table size: 8-bit digits, or 9-bit ones where they save a pass
-    (17-18 and 25-27 key bits -- the 100 M-row tables of the sharded config).  Ids spread over the whole table so
-    that every digit varies; distinct ids exact, summed gradients against the oracle."""
+    """The sort half sizes its passes from the table: 18, 23, 26 and 27 key bits (3-4 passes of 8-bit digits; with
+    B200REC_SORT_DB9=1 the 9-bit digit kernels take the 18 / 26 / 27-bit cases).  Ids spread over the whole table
+    so that every digit varies; distinct ids exact, summed gradients against the oracle."""
     synth = gpu_pkg.synth
     F, K, B = 39, 4, 512
     model = gpu_pkg.make_model("fm", F, K, (), (), 0)
